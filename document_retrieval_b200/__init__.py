@@ -1,0 +1,12 @@
+"""document_retrieval_b200 - B200-native BM25 scoring / top-k / cosine re-rank behind the Python
+surface of Harkeerat2002/document-retrieval's retrieval hot path."""
+from .bm25 import BM25  # noqa: F401
+from .routing import (evaluate_recall_at_k, retrieve_test_queries, retrieve_top_n_batch,  # noqa: F401
+                      LanguageModels)
+from .functional import (compute_tf_df_and_avgdl, compute_idf,  # noqa: F401
+                         score_documents_for_query, score_documents_for_queries, ScoreDocumentsContext,
+                         set_context)
+
+__all__ = ["BM25", "evaluate_recall_at_k", "retrieve_test_queries", "retrieve_top_n_batch", "LanguageModels",
+           "compute_tf_df_and_avgdl", "compute_idf", "score_documents_for_query", "score_documents_for_queries", "set_context",
+           "ScoreDocumentsContext"]

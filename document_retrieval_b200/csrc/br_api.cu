@@ -1,0 +1,43 @@
+// br_api.cu - C ABI (query side), error reporting, version.
+#include "br_common.cuh"
+
+namespace br {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+}  // namespace br
+
+extern "C" {
+
+const char* br_last_error(void) { return br::g_err.c_str(); }
+const char* br_version(void) { return "br_b200 0.1 sm_100a"; }
+
+int br_score_batch(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq, int dedup,
+                   float* out_scores_dev, void* stream) {
+    return br::score_batch(ix, q_terms_dev, q_offsets_dev, nq, dedup, out_scores_dev, (cudaStream_t)stream);
+}
+
+int br_topk_batch(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq, int32_t k,
+                  int dedup, int positive_only, int32_t* out_ids_dev, double* out_scores_dev, int32_t* out_counts_dev,
+                  void* stream) {
+    return br::topk_batch(ix, q_terms_dev, q_offsets_dev, nq, k, dedup, positive_only, out_ids_dev, out_scores_dev,
+                          out_counts_dev, (cudaStream_t)stream);
+}
+
+int br_rescore_docs(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq, int dedup,
+                    const int32_t* cand_ids_dev, const int64_t* cand_off_dev, double* out_scores_dev, void* stream) {
+    return br::rescore_docs(ix, q_terms_dev, q_offsets_dev, nq, dedup, cand_ids_dev, cand_off_dev, out_scores_dev,
+                            (cudaStream_t)stream);
+}
+
+int br_topk_merge(const int64_t* ids_dev, const double* scores_dev, int32_t n_parts, int32_t nq, int32_t k,
+                  int64_t* out_ids_dev, double* out_scores_dev, void* stream) {
+    return br::topk_merge(ids_dev, scores_dev, n_parts, nq, k, out_ids_dev, out_scores_dev, (cudaStream_t)stream);
+}
+
+int br_last_query_stats(const br_index* ix, br_query_stats* out) {
+    BR_REQUIRE(ix && out, BR_ERR_INVALID, "br_last_query_stats: null pointer");
+    *out = ix->stats;
+    return BR_OK;
+}
+
+}  // extern "C"

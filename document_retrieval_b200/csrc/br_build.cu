@@ -1,0 +1,487 @@
+// br_build.cu - index build on the GPU: tokenised docs -> CSR posting lists with packed
+// (doc id, fp32 BM25 weight) postings, raw tf, dl, df, idf and the hot-term skip tables.
+//
+// Replaces BM25.__init__/build (bm25_ranking.ipynb:167-189), compute_tf_df_and_avgdl
+// (cosine_similarity_bm25_reranking.py:129-172) and build_inverted_index (team_run1.py:80-99).
+//
+// Pipeline (all on one stream):
+//   k_make_keys      one warp per doc: key = term << 32 | doc, dl[doc]                 (4 B in, 8 B out / token)
+//   radix sort       64-bit keys, only the significant bits (CUB DeviceRadixSort - library plumbing)
+//   k_rle_count/emit run-length encode equal keys -> one posting per (term, doc) with tf = run length
+//   k_finish         tf (u16), first/last posting of every term -> df histogram
+//   k_exscan         exclusive prefix-scan of df -> row_ptr
+//   [host]           idf[t] = log(..) in float64 with libm (bit-identical to math.log)
+//   k_weights        w = fp32(idf * ((tf*(k1+1)) / (tf + k1*norm(dl))))  evaluated in float64, no FMA
+//   k_skip           per hot term: offset of the first posting of every 2^sub_shift-doc sub-range
+#include <math.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "br_common.cuh"
+#include "br_kernels.cuh"
+
+namespace br {
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+__global__ void k_make_keys(const int32_t* __restrict__ tok, const int64_t* __restrict__ doc_off,
+                            int64_t n_docs, int32_t vocab, uint64_t* __restrict__ keys,
+                            uint32_t* __restrict__ dl, int* __restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t d = warp; d < n_docs; d += n_warps) {
+        const int64_t lo = doc_off[d], hi = doc_off[d + 1];
+        if (hi < lo || hi - lo > 0xffffffffLL) {
+            if (lane == 0) atomicOr(bad, 2);
+            continue;
+        }
+        if (lane == 0) dl[d] = (uint32_t)(hi - lo);
+        for (int64_t i = lo + lane; i < hi; i += 32) {
+            const int32_t t = tok[i];
+            if ((uint32_t)t >= (uint32_t)vocab) atomicOr(bad, 1);
+            keys[i] = ((uint64_t)(uint32_t)t << 32) | (uint32_t)d;
+        }
+    }
+}
+
+constexpr int RLE_T = 256, RLE_I = 8, RLE_TILE = RLE_T * RLE_I;
+
+__global__ void __launch_bounds__(RLE_T) k_rle_count(const uint64_t* __restrict__ keys, int64_t n,
+                                                     uint32_t* __restrict__ block_counts) {
+    const int64_t base = (int64_t)blockIdx.x * RLE_TILE;
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < RLE_I; ++j) {
+        const int64_t i = base + j * RLE_T + threadIdx.x;   // striped: coalesced, order irrelevant
+        if (i < n) c += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+    }
+    uint32_t total;
+    block_excl_scan(c, &total);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(RLE_T) k_rle_emit(const uint64_t* __restrict__ keys, int64_t n,
+                                                    const int64_t* __restrict__ block_off,
+                                                    br_posting* __restrict__ post,
+                                                    uint32_t* __restrict__ post_term,
+                                                    uint32_t* __restrict__ head_pos) {
+    const int64_t base = (int64_t)blockIdx.x * RLE_TILE + (int64_t)threadIdx.x * RLE_I;  // blocked: ordered
+    uint64_t k[RLE_I];
+    uint64_t prev = (base > 0 && base - 1 < n) ? keys[base - 1] : ~0ull;
+    uint32_t c = 0;
+    bool head[RLE_I];
+#pragma unroll
+    for (int j = 0; j < RLE_I; ++j) {
+        const int64_t i = base + j;
+        k[j] = i < n ? keys[i] : 0;
+        head[j] = i < n && (i == 0 || k[j] != prev);
+        prev = k[j];
+        c += head[j] ? 1u : 0u;
+    }
+    uint32_t total;
+    uint32_t ex = block_excl_scan(c, &total);
+    int64_t o = block_off[blockIdx.x] + ex;
+#pragma unroll
+    for (int j = 0; j < RLE_I; ++j) {
+        if (head[j]) {
+            post[o].doc = (uint32_t)k[j];
+            post_term[o] = (uint32_t)(k[j] >> 32);
+            head_pos[o] = (uint32_t)(base + j);
+            ++o;
+        }
+    }
+}
+
+__global__ void k_finish(const uint32_t* __restrict__ post_term, const uint32_t* __restrict__ head_pos,
+                         int64_t nnz, uint32_t n_tokens, uint16_t* __restrict__ tf,
+                         uint32_t* __restrict__ tstart, uint32_t* __restrict__ tend, int* __restrict__ bad) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nnz) return;
+    const uint32_t nxt = j + 1 < nnz ? head_pos[j + 1] : n_tokens;
+    const uint32_t f = nxt - head_pos[j];
+    if (f > 65535u) atomicOr(bad, 4);
+    tf[j] = (uint16_t)f;
+    const uint32_t t = post_term[j];
+    if (j == 0 || post_term[j - 1] != t) tstart[t] = (uint32_t)j;
+    if (j + 1 == nnz || post_term[j + 1] != t) tend[t] = (uint32_t)(j + 1);
+}
+
+__global__ void k_df(const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tend, int32_t vocab,
+                     uint32_t* __restrict__ df) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < vocab) df[t] = tend[t] - tstart[t];
+}
+
+__global__ void k_weights(const int64_t* __restrict__ row_ptr, int32_t vocab, int64_t nnz,
+                          br_posting* __restrict__ post, const uint16_t* __restrict__ tf,
+                          const uint32_t* __restrict__ dl, const double* __restrict__ idf, double avgdl,
+                          double k1, double b, int variant) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nnz) return;
+    // term of posting j: last t with row_ptr[t] <= j
+    int32_t lo = 0, hi = vocab;  // invariant: row_ptr[lo] <= j < row_ptr[hi]
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (row_ptr[mid] <= j) lo = mid; else hi = mid;
+    }
+    const uint32_t d = post[j].doc;
+    const double c = bm25_contrib(idf[lo], (double)tf[j], (double)dl[d], avgdl, k1, b, variant);
+    post[j].w = isnan(c) ? 0.f : (float)c;
+}
+
+__global__ void k_skip(const int64_t* __restrict__ row_ptr, const br_posting* __restrict__ post,
+                       const int32_t* __restrict__ hot_terms, int32_t n_hot, int32_t n_sub, int sub_shift,
+                       uint32_t* __restrict__ skip) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)n_sub + 1;
+    if (i >= (int64_t)n_hot * per) return;
+    const int32_t slot = (int32_t)(i / per);
+    const int64_t j = i - (int64_t)slot * per;
+    const int32_t t = hot_terms[slot];
+    const int64_t base = row_ptr[t];
+    const uint32_t len = (uint32_t)(row_ptr[t + 1] - base);
+    const uint64_t target = (uint64_t)j << sub_shift;   // first doc of sub-range j
+    uint32_t lo = 0, hi = len;                           // first posting with doc >= target
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((uint64_t)post[base + mid].doc < target) lo = mid + 1; else hi = mid;
+    }
+    skip[i] = lo;
+}
+
+__global__ void k_import(const int32_t* __restrict__ doc, const int32_t* __restrict__ tf_in, int64_t nnz,
+                         br_posting* __restrict__ post, uint16_t* __restrict__ tf, int* __restrict__ bad) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nnz) return;
+    post[j].doc = (uint32_t)doc[j];
+    post[j].w = 0.f;
+    if (tf_in[j] < 0 || tf_in[j] > 65535) atomicOr(bad, 4);
+    tf[j] = (uint16_t)tf_in[j];
+}
+
+__global__ void k_export(const br_posting* __restrict__ post, const uint16_t* __restrict__ tf, int64_t nnz,
+                         int32_t* __restrict__ doc_out, int32_t* __restrict__ tf_out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nnz) return;
+    doc_out[j] = (int32_t)post[j].doc;
+    tf_out[j] = (int32_t)tf[j];
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+
+
+void index_free(br_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    cudaFree(ix->row_ptr); cudaFree(ix->post); cudaFree(ix->tf); cudaFree(ix->dl); cudaFree(ix->df);
+    cudaFree(ix->idf); cudaFree(ix->hot_slot); cudaFree(ix->skip);
+    ix->ws_prep.release(); ix->ws_dense.release(); ix->ws_sel.release(); ix->ws_cand.release();
+    ix->ws_misc.release(); ix->ws_tile.release();
+    delete ix;
+}
+
+static int alloc_common(br_index* ix) {
+    BR_CUDA(cudaMalloc(&ix->row_ptr, sizeof(int64_t) * ((size_t)ix->vocab + 1)));
+    BR_CUDA(cudaMalloc(&ix->dl, sizeof(uint32_t) * (size_t)ix->n_docs));
+    BR_CUDA(cudaMalloc(&ix->df, sizeof(uint32_t) * (size_t)ix->vocab));
+    BR_CUDA(cudaMalloc(&ix->idf, sizeof(double) * (size_t)ix->vocab));
+    BR_CUDA(cudaMalloc(&ix->hot_slot, sizeof(int32_t) * (size_t)ix->vocab));
+    return BR_OK;
+}
+
+int index_build(const int32_t* tok, const int64_t* doc_off, int64_t n_docs, int32_t vocab, int64_t doc_base,
+                cudaStream_t st, br_index** out) {
+    BR_REQUIRE(out && tok && doc_off, BR_ERR_INVALID, "br_index_build: null pointer");
+    BR_REQUIRE(n_docs > 0 && n_docs < (1LL << 31), BR_ERR_INVALID,
+               "br_index_build: n_docs must be in [1, 2^31) (empty corpus: the reference divides by zero, "
+               "bm25_ranking.ipynb:171)");
+    BR_REQUIRE(vocab > 0, BR_ERR_INVALID, "br_index_build: vocab must be positive");
+    *out = nullptr;
+    br_index* ix = new br_index();
+    BR_CUDA(cudaGetDevice(&ix->device));
+    ix->n_docs = n_docs; ix->vocab = vocab; ix->doc_base = doc_base;
+    struct Guard { br_index* p; ~Guard() { if (p) index_free(p); } } guard{ix};
+
+    int64_t n_tok = 0;
+    BR_CUDA(cudaMemcpyAsync(&n_tok, doc_off + n_docs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaStreamSynchronize(st));
+    BR_REQUIRE(n_tok >= 0 && n_tok < (1LL << 32), BR_ERR_UNSUPPORTED,
+               "br_index_build: more than 2^32 tokens in one shard");
+    ix->sum_dl = n_tok;
+    BR_TRY(alloc_common(ix));
+
+    int* d_bad = nullptr;
+    uint64_t *keys_a = nullptr, *keys_b = nullptr;
+    uint32_t *block_counts = nullptr, *post_term = nullptr, *head_pos = nullptr, *tstart = nullptr, *tend = nullptr;
+    int64_t* block_off = nullptr;
+    void* sort_tmp = nullptr;
+    struct Tmp { void** p; ~Tmp() { if (*p) cudaFree(*p); } };
+    Tmp t0{(void**)&d_bad}, t1{(void**)&keys_a}, t2{(void**)&keys_b}, t3{(void**)&block_counts},
+        t4{(void**)&post_term}, t5{(void**)&head_pos}, t6{(void**)&tstart}, t7{(void**)&tend},
+        t8{(void**)&block_off}, t9{&sort_tmp};
+
+    BR_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    BR_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    const size_t nk = (size_t)(n_tok > 0 ? n_tok : 1);
+    BR_CUDA(cudaMalloc(&keys_a, sizeof(uint64_t) * nk));
+    BR_CUDA(cudaMalloc(&keys_b, sizeof(uint64_t) * nk));
+    k_make_keys<<<kNumSMs * 8, 256, 0, st>>>(tok, doc_off, n_docs, vocab, keys_a, ix->dl, d_bad);
+    BR_CUDA(cudaGetLastError());
+
+    // sort by (term, doc): only the significant bits
+    int term_bits = 1;
+    while ((1LL << term_bits) < (int64_t)vocab) ++term_bits;
+    cub::DoubleBuffer<uint64_t> dbuf(keys_a, keys_b);
+    size_t tmp_bytes = 0;
+    BR_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, dbuf, (int64_t)n_tok, 0, 32 + term_bits, st));
+    BR_CUDA(cudaMalloc(&sort_tmp, tmp_bytes + 16));
+    BR_CUDA(cub::DeviceRadixSort::SortKeys(sort_tmp, tmp_bytes, dbuf, (int64_t)n_tok, 0, 32 + term_bits, st));
+    const uint64_t* keys = dbuf.Current();
+
+    // run-length encode
+    const int64_t n_blocks = (n_tok + RLE_TILE - 1) / RLE_TILE;
+    BR_CUDA(cudaMalloc(&block_counts, sizeof(uint32_t) * (size_t)(n_blocks + 1)));
+    BR_CUDA(cudaMalloc(&block_off, sizeof(int64_t) * (size_t)(n_blocks + 2)));
+    if (n_blocks > 0) {
+        k_rle_count<<<(unsigned)n_blocks, RLE_T, 0, st>>>(keys, n_tok, block_counts);
+        BR_CUDA(cudaGetLastError());
+    }
+    k_exscan<uint32_t><<<1, 1024, 0, st>>>(block_counts, n_blocks, block_off);
+    BR_CUDA(cudaGetLastError());
+    int64_t nnz = 0;
+    int bad = 0;
+    BR_CUDA(cudaMemcpyAsync(&nnz, block_off + n_blocks, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaStreamSynchronize(st));
+    BR_REQUIRE(!(bad & 1), BR_ERR_INVALID, "br_index_build: token id outside [0, vocab)");
+    BR_REQUIRE(!(bad & 2), BR_ERR_INVALID, "br_index_build: doc_offsets not non-decreasing");
+    ix->nnz = nnz;
+    const size_t np = (size_t)(nnz > 0 ? nnz : 1);
+    BR_CUDA(cudaMalloc(&ix->post, sizeof(br_posting) * np));
+    BR_CUDA(cudaMalloc(&ix->tf, sizeof(uint16_t) * np));
+    BR_CUDA(cudaMalloc(&post_term, sizeof(uint32_t) * np));
+    BR_CUDA(cudaMalloc(&head_pos, sizeof(uint32_t) * np));
+    BR_CUDA(cudaMalloc(&tstart, sizeof(uint32_t) * (size_t)vocab));
+    BR_CUDA(cudaMalloc(&tend, sizeof(uint32_t) * (size_t)vocab));
+    BR_CUDA(cudaMemsetAsync(tstart, 0, sizeof(uint32_t) * (size_t)vocab, st));
+    BR_CUDA(cudaMemsetAsync(tend, 0, sizeof(uint32_t) * (size_t)vocab, st));
+    if (n_blocks > 0) {
+        k_rle_emit<<<(unsigned)n_blocks, RLE_T, 0, st>>>(keys, n_tok, block_off, ix->post, post_term, head_pos);
+        BR_CUDA(cudaGetLastError());
+    }
+    if (nnz > 0) {
+        k_finish<<<blocks_for(nnz, 256), 256, 0, st>>>(post_term, head_pos, nnz, (uint32_t)n_tok, ix->tf, tstart,
+                                                       tend, d_bad);
+        BR_CUDA(cudaGetLastError());
+    }
+    k_df<<<blocks_for(vocab, 256), 256, 0, st>>>(tstart, tend, vocab, ix->df);
+    BR_CUDA(cudaGetLastError());
+    k_exscan<uint32_t><<<1, 1024, 0, st>>>(ix->df, vocab, ix->row_ptr);
+    BR_CUDA(cudaGetLastError());
+    ix->h_df.resize((size_t)vocab);
+    BR_CUDA(cudaMemcpyAsync(ix->h_df.data(), ix->df, sizeof(uint32_t) * (size_t)vocab, cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaStreamSynchronize(st));
+    BR_REQUIRE(!(bad & 4), BR_ERR_UNSUPPORTED, "br_index_build: a term occurs more than 65535 times in one doc");
+    guard.p = nullptr;
+    *out = ix;
+    return BR_OK;
+}
+
+int index_import(const int64_t* row_ptr, const int32_t* doc, const int32_t* tf, const int32_t* dl, int64_t n_docs,
+                 int32_t vocab, int64_t doc_base, cudaStream_t st, br_index** out) {
+    BR_REQUIRE(out && row_ptr && doc && tf && dl, BR_ERR_INVALID, "br_index_import_csr: null pointer");
+    BR_REQUIRE(n_docs > 0 && n_docs < (1LL << 31) && vocab > 0, BR_ERR_INVALID, "br_index_import_csr: bad sizes");
+    *out = nullptr;
+    br_index* ix = new br_index();
+    BR_CUDA(cudaGetDevice(&ix->device));
+    ix->n_docs = n_docs; ix->vocab = vocab; ix->doc_base = doc_base;
+    struct Guard { br_index* p; ~Guard() { if (p) index_free(p); } } guard{ix};
+    const int64_t nnz = row_ptr[vocab];
+    BR_REQUIRE(nnz >= 0 && row_ptr[0] == 0, BR_ERR_INVALID, "br_index_import_csr: bad row_ptr");
+    ix->nnz = nnz;
+    BR_TRY(alloc_common(ix));
+    const size_t np = (size_t)(nnz > 0 ? nnz : 1);
+    BR_CUDA(cudaMalloc(&ix->post, sizeof(br_posting) * np));
+    BR_CUDA(cudaMalloc(&ix->tf, sizeof(uint16_t) * np));
+    int32_t *d_doc = nullptr, *d_tf = nullptr;
+    int* d_bad = nullptr;
+    struct Tmp { void** p; ~Tmp() { if (*p) cudaFree(*p); } };
+    Tmp t0{(void**)&d_doc}, t1{(void**)&d_tf}, t2{(void**)&d_bad};
+    BR_CUDA(cudaMalloc(&d_doc, sizeof(int32_t) * np));
+    BR_CUDA(cudaMalloc(&d_tf, sizeof(int32_t) * np));
+    BR_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    BR_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    BR_CUDA(cudaMemcpyAsync(d_doc, doc, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    BR_CUDA(cudaMemcpyAsync(d_tf, tf, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    BR_CUDA(cudaMemcpyAsync(ix->row_ptr, row_ptr, sizeof(int64_t) * ((size_t)vocab + 1), cudaMemcpyHostToDevice, st));
+    BR_CUDA(cudaMemcpyAsync(ix->dl, dl, sizeof(int32_t) * (size_t)n_docs, cudaMemcpyHostToDevice, st));
+    if (nnz > 0) {
+        k_import<<<blocks_for(nnz, 256), 256, 0, st>>>(d_doc, d_tf, nnz, ix->post, ix->tf, d_bad);
+        BR_CUDA(cudaGetLastError());
+    }
+    ix->h_df.resize((size_t)vocab);
+    int64_t sum = 0;
+    for (int32_t t = 0; t < vocab; ++t) {
+        BR_REQUIRE(row_ptr[t + 1] >= row_ptr[t], BR_ERR_INVALID, "br_index_import_csr: row_ptr not monotone");
+        ix->h_df[(size_t)t] = (uint32_t)(row_ptr[t + 1] - row_ptr[t]);
+    }
+    for (int64_t d = 0; d < n_docs; ++d) sum += dl[d];
+    ix->sum_dl = sum;
+    BR_CUDA(cudaMemcpyAsync(ix->df, ix->h_df.data(), sizeof(uint32_t) * (size_t)vocab, cudaMemcpyHostToDevice, st));
+    int bad = 0;
+    BR_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaStreamSynchronize(st));
+    BR_REQUIRE(!bad, BR_ERR_INVALID, "br_index_import_csr: tf outside [0, 65535]");
+    guard.p = nullptr;
+    *out = ix;
+    return BR_OK;
+}
+
+int index_finalize(br_index* ix, double k1, double b, int variant, double n_stat, double sum_dl_stat,
+                   const int64_t* df_stat_host, cudaStream_t st) {
+    BR_REQUIRE(ix, BR_ERR_INVALID, "br_index_finalize: null handle");
+    BR_REQUIRE(variant >= 0 && variant <= 2, BR_ERR_INVALID, "br_index_finalize: unknown variant");
+    BR_CUDA(cudaSetDevice(ix->device));
+    ix->k1 = k1; ix->b = b; ix->variant = variant;
+    ix->n_stat = n_stat > 0 ? n_stat : (double)ix->n_docs;
+    const double sum_dl = sum_dl_stat > 0 ? sum_dl_stat : (double)ix->sum_dl;
+    ix->avgdl = sum_dl / ix->n_stat;                       // sum(len(doc)) / corpus_size, :171
+    const size_t V = (size_t)ix->vocab;
+    ix->h_df_stat.resize(V);
+    ix->h_idf.resize(V);
+    for (size_t t = 0; t < V; ++t) {
+        const int64_t d = df_stat_host ? df_stat_host[t] : (int64_t)ix->h_df[t];
+        ix->h_df_stat[t] = d;
+        if (d > 0) {
+            const double x = (ix->n_stat - (double)d + 0.5) / ((double)d + 0.5);
+            ix->h_idf[t] = variant == BR_OKAPI_NO_PLUS1 ? log(x) : log(1 + x);   // math.log, :189
+        } else {
+            ix->h_idf[t] = NAN;
+        }
+    }
+    BR_CUDA(cudaMemcpyAsync(ix->idf, ix->h_idf.data(), sizeof(double) * V, cudaMemcpyHostToDevice, st));
+    if (ix->nnz > 0) {
+        k_weights<<<blocks_for(ix->nnz, 256), 256, 0, st>>>(ix->row_ptr, ix->vocab, ix->nnz, ix->post, ix->tf,
+                                                            ix->dl, ix->idf, ix->avgdl, k1, b, variant);
+        BR_CUDA(cudaGetLastError());
+    }
+    // hot-term skip tables (shard-local structure: decided from the local df)
+    if (!ix->skip) {
+        ix->sub_shift = 9;
+        const char* e = getenv("BR_SUB_SHIFT");
+        if (e) { int v = atoi(e); if (v >= 5 && v <= 16) ix->sub_shift = v; }
+        ix->n_sub = (int32_t)((ix->n_docs + (1LL << ix->sub_shift) - 1) >> ix->sub_shift);
+        double frac = 0.25;
+        const char* f = getenv("BR_HOT_FRAC");
+        if (f) { double v = atof(f); if (v > 0) frac = v; }
+        const uint32_t hot_min = (uint32_t)fmax(4.0, frac * (double)ix->n_sub);
+        std::vector<int32_t> slot(V, -1), hot_terms;
+        for (size_t t = 0; t < V; ++t)
+            if (ix->h_df[t] >= hot_min) { slot[t] = (int32_t)hot_terms.size(); hot_terms.push_back((int32_t)t); }
+        ix->n_hot = (int32_t)hot_terms.size();
+        BR_CUDA(cudaMemcpyAsync(ix->hot_slot, slot.data(), sizeof(int32_t) * V, cudaMemcpyHostToDevice, st));
+        if (ix->n_hot > 0) {
+            const int64_t n_entries = (int64_t)ix->n_hot * ((int64_t)ix->n_sub + 1);
+            int32_t* d_hot = nullptr;
+            BR_CUDA(cudaMalloc(&ix->skip, sizeof(uint32_t) * (size_t)n_entries));
+            BR_CUDA(cudaMalloc(&d_hot, sizeof(int32_t) * (size_t)ix->n_hot));
+            BR_CUDA(cudaMemcpyAsync(d_hot, hot_terms.data(), sizeof(int32_t) * (size_t)ix->n_hot,
+                                    cudaMemcpyHostToDevice, st));
+            k_skip<<<blocks_for(n_entries, 256), 256, 0, st>>>(ix->row_ptr, ix->post, d_hot, ix->n_hot, ix->n_sub,
+                                                               ix->sub_shift, ix->skip);
+            BR_CUDA(cudaGetLastError());
+            BR_CUDA(cudaStreamSynchronize(st));
+            cudaFree(d_hot);
+        }
+    }
+    BR_CUDA(cudaStreamSynchronize(st));
+    ix->finalized = true;
+    return BR_OK;
+}
+
+}  // namespace br
+
+// ------------------------------------------------------------------------------------------
+// C ABI (build / export side)
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int br_index_build(const int32_t* token_ids_dev, const int64_t* doc_offsets_dev, int64_t n_docs, int32_t vocab,
+                   int64_t doc_base, void* stream, br_index** out) {
+    return br::index_build(token_ids_dev, doc_offsets_dev, n_docs, vocab, doc_base, (cudaStream_t)stream, out);
+}
+
+int br_index_finalize(br_index* ix, double k1, double b, int variant, double n_stat, double sum_dl_stat,
+                      const int64_t* df_stat_host, void* stream) {
+    return br::index_finalize(ix, k1, b, variant, n_stat, sum_dl_stat, df_stat_host, (cudaStream_t)stream);
+}
+
+int br_index_import_csr(const int64_t* row_ptr_host, const int32_t* doc_host, const int32_t* tf_host,
+                        const int32_t* dl_host, int64_t n_docs, int32_t vocab, int64_t doc_base, void* stream,
+                        br_index** out) {
+    return br::index_import(row_ptr_host, doc_host, tf_host, dl_host, n_docs, vocab, doc_base,
+                            (cudaStream_t)stream, out);
+}
+
+void br_index_destroy(br_index* ix) { br::index_free(ix); }
+
+int br_index_stats(const br_index* ix, int64_t* n_docs, int32_t* vocab, int64_t* nnz, double* avgdl,
+                   int64_t* sum_dl, int64_t* doc_base) {
+    BR_REQUIRE(ix, BR_ERR_INVALID, "br_index_stats: null handle");
+    if (n_docs) *n_docs = ix->n_docs;
+    if (vocab) *vocab = ix->vocab;
+    if (nnz) *nnz = ix->nnz;
+    if (avgdl) *avgdl = ix->finalized ? ix->avgdl : (double)ix->sum_dl / (double)ix->n_docs;
+    if (sum_dl) *sum_dl = ix->sum_dl;
+    if (doc_base) *doc_base = ix->doc_base;
+    return BR_OK;
+}
+
+const uint32_t* br_index_df_dev(const br_index* ix) { return ix ? ix->df : nullptr; }
+
+int br_index_export_df_idf(const br_index* ix, int64_t* df_host, double* idf_host) {
+    BR_REQUIRE(ix, BR_ERR_INVALID, "br_index_export_df_idf: null handle");
+    const size_t V = (size_t)ix->vocab;
+    if (df_host) {
+        if (ix->finalized) for (size_t t = 0; t < V; ++t) df_host[t] = ix->h_df_stat[t];
+        else for (size_t t = 0; t < V; ++t) df_host[t] = (int64_t)ix->h_df[t];
+    }
+    if (idf_host) {
+        BR_REQUIRE(ix->finalized, BR_ERR_STATE, "br_index_export_df_idf: idf needs br_index_finalize first");
+        for (size_t t = 0; t < V; ++t) idf_host[t] = ix->h_idf[t];
+    }
+    return BR_OK;
+}
+
+int br_index_export_csr(const br_index* ix, int64_t* row_ptr_host, int32_t* doc_host, int32_t* tf_host,
+                        int32_t* dl_host) {
+    BR_REQUIRE(ix, BR_ERR_INVALID, "br_index_export_csr: null handle");
+    BR_CUDA(cudaSetDevice(ix->device));
+    if (row_ptr_host)
+        BR_CUDA(cudaMemcpy(row_ptr_host, ix->row_ptr, sizeof(int64_t) * ((size_t)ix->vocab + 1), cudaMemcpyDeviceToHost));
+    if (dl_host) BR_CUDA(cudaMemcpy(dl_host, ix->dl, sizeof(uint32_t) * (size_t)ix->n_docs, cudaMemcpyDeviceToHost));
+    if ((doc_host || tf_host) && ix->nnz > 0) {
+        BR_REQUIRE(doc_host && tf_host, BR_ERR_INVALID, "br_index_export_csr: doc_host and tf_host go together");
+        int32_t *d_doc = nullptr, *d_tf = nullptr;
+        BR_CUDA(cudaMalloc(&d_doc, sizeof(int32_t) * (size_t)ix->nnz));
+        if (cudaMalloc(&d_tf, sizeof(int32_t) * (size_t)ix->nnz) != cudaSuccess) {
+            cudaFree(d_doc);
+            br::set_error("br_index_export_csr: out of device memory");
+            return BR_ERR_CUDA;
+        }
+        br::k_export<<<br::blocks_for(ix->nnz, 256), 256>>>(ix->post, ix->tf, ix->nnz, d_doc, d_tf);
+        cudaError_t e1 = cudaMemcpy(doc_host, d_doc, sizeof(int32_t) * (size_t)ix->nnz, cudaMemcpyDeviceToHost);
+        cudaError_t e2 = cudaMemcpy(tf_host, d_tf, sizeof(int32_t) * (size_t)ix->nnz, cudaMemcpyDeviceToHost);
+        cudaFree(d_doc); cudaFree(d_tf);
+        BR_CUDA(e1);
+        BR_CUDA(e2);
+    }
+    return BR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// br_common.cuh - shared declarations of the br_b200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/br_b200.h"
+
+namespace br {
+
+void set_error(const std::string& msg);
+
+#define BR_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            br::set_error(std::string(#call) + ": " + cudaGetErrorString(_e) + " (" +       \
+                          __FILE__ + ":" + std::to_string(__LINE__) + ")");                 \
+            return BR_ERR_CUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+
+#define BR_TRY(call)                  \
+    do {                              \
+        int _s = (call);              \
+        if (_s != BR_OK) return _s;   \
+    } while (0)
+
+#define BR_REQUIRE(cond, status, msg) \
+    do {                              \
+        if (!(cond)) {                \
+            br::set_error(msg);       \
+            return status;            \
+        }                             \
+    } while (0)
+
+// Grow-only device scratch buffer (never shrinks; freed with the handle).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return BR_OK;
+        if (p) BR_CUDA(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        BR_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return BR_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int kNumSMs = 148;          // B200
+constexpr float kBandRel = 1e-5f;     // fp32 candidate band kept below the k-th fp32 score
+
+}  // namespace br
+
+// One posting: doc id + precomputed fp32 BM25 weight, 8 bytes, read as one 64-bit word
+// (two postings per 128-bit load).
+struct __align__(8) br_posting {
+    uint32_t doc;
+    float w;
+};
+
+struct br_index {
+    int device = 0;
+    int64_t n_docs = 0, doc_base = 0, nnz = 0, sum_dl = 0;
+    int32_t vocab = 0;
+    bool finalized = false;
+    int variant = 0;
+    double k1 = 1.5, b = 0.75, n_stat = 0, avgdl = 0;
+
+    // CSR by term (device)
+    int64_t* row_ptr = nullptr;     // [V+1]
+    br_posting* post = nullptr;     // [nnz]   doc ids ascending inside a term
+    uint16_t* tf = nullptr;         // [nnz]   raw term frequency (for the float64 re-score)
+    uint32_t* dl = nullptr;         // [N]
+    uint32_t* df = nullptr;         // [V]     shard-local document frequency
+    double* idf = nullptr;          // [V]     statistics in force (NaN where df_stat == 0)
+
+    // hot-term skip tables for the tiled scorer: term t is "hot" when hot_slot[t] >= 0; then
+    // skip[hot_slot[t] * (n_sub+1) + j] = offset (relative to row_ptr[t]) of the first posting
+    // with doc >= j << sub_shift.
+    int sub_shift = 0;
+    int32_t n_sub = 0, n_hot = 0;
+    int32_t* hot_slot = nullptr;    // [V]
+    uint32_t* skip = nullptr;       // [n_hot, n_sub+1]
+
+    // host mirrors
+    std::vector<uint32_t> h_df;     // shard-local
+    std::vector<int64_t> h_df_stat; // statistics in force
+    std::vector<double> h_idf;
+
+    // query-time scratch
+    br::DevBuf ws_prep, ws_dense, ws_sel, ws_cand, ws_misc, ws_tile;
+    br_query_stats stats{};
+};
+
+namespace br {
+// br_build.cu
+int index_build(const int32_t* token_ids, const int64_t* doc_offsets, int64_t n_docs, int32_t vocab,
+                int64_t doc_base, cudaStream_t st, br_index** out);
+int index_finalize(br_index* ix, double k1, double b, int variant, double n_stat, double sum_dl_stat,
+                   const int64_t* df_stat_host, cudaStream_t st);
+int index_import(const int64_t* row_ptr, const int32_t* doc, const int32_t* tf, const int32_t* dl,
+                 int64_t n_docs, int32_t vocab, int64_t doc_base, cudaStream_t st, br_index** out);
+void index_free(br_index* ix);
+// br_query.cu
+int score_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, int32_t nq, int dedup,
+                float* out_scores, cudaStream_t st);
+int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, int32_t nq, int32_t k,
+               int dedup, int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts,
+               cudaStream_t st);
+int rescore_docs(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, int32_t nq, int dedup,
+                 const int32_t* cand_ids, const int64_t* cand_off, double* out_scores, cudaStream_t st);
+int topk_merge(const int64_t* ids, const double* scores, int32_t n_parts, int32_t nq, int32_t k,
+               int64_t* out_ids, double* out_scores, cudaStream_t st);
+}  // namespace br

@@ -1,0 +1,564 @@
+// br_query.cu - query-time kernels of the dense ("generic") BM25 path and the shared tail:
+//
+//   k_prep_queries   per query: drop OOV terms, de-duplicate (set(query), bm25_ranking.ipynb:193)
+//                    or keep multiplicities (team_run1.py:183), sort by term id, prefix df
+//   k_score_dense    term-at-a-time scatter-add of packed postings into fp32 [nq, N] accumulators
+//                    (get_scores, bm25_ranking.ipynb:191-204)
+//   k_select_radix   per query row: exact k-th largest fp32 score by 3-pass radix select, then the
+//                    candidate band  s >= kth - 1e-5*|kth|   (retrieve_top_n, :206-213)
+//   k_emit_cands     band members -> candidate list (doc-id order; zero-score tail in doc-id order)
+//   k_rescore        exact float64 re-evaluation of the reference formula for every candidate
+//   k_final_select   (score64 desc, doc id asc) order, top-k, duplicate ids removed
+//
+// Why a band + float64 re-score: the reference ranks float64 scores; fp32 accumulation can swap
+// near-ties.  Every doc outside the band has fp32 score < kth32*(1-1e-5), hence (fp32 error of a
+// <=64-term positive sum is < 4e-6 relative) a float64 score below that of the k band members that
+// define kth32 - so the true top-k is inside the band, and re-scoring the band in float64 gives the
+// reference's ranking exactly ("exactness").
+#include <math_constants.h>
+
+#include "br_common.cuh"
+#include "br_kernels.cuh"
+
+namespace br {
+
+// ------------------------------------------------------------------------------------------
+// query preparation
+// ------------------------------------------------------------------------------------------
+struct PrepView {
+    int32_t* u_terms;   // [T]  per query segment: unique valid terms ascending
+    int32_t* u_mult;    // [T]  multiplicity (1 when dedup)
+    int64_t* u_cum;     // [T]  exclusive prefix of df over the unique terms
+    int32_t* u_cnt;     // [nq]
+    int32_t* o_terms;   // [T]  valid terms in query order (duplicates kept)
+    int32_t* o_cnt;     // [nq]
+    int64_t* P;         // [nq] total postings of the unique terms
+    uint32_t* n_chunks; // [nq]
+    int32_t* tmp;       // [T]
+};
+
+constexpr int SCORE_CHUNK = 8192;
+
+__global__ void k_prep_queries(const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_off, int32_t nq,
+                               int32_t vocab, const int64_t* __restrict__ row_ptr, int dedup, PrepView v) {
+    const int lane = threadIdx.x & 31;
+    const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (q >= nq) return;
+    const int32_t off = q_off[q], M = q_off[q + 1] - off;
+    // phase 1: validity, ordered compaction into o_terms
+    int32_t n_valid = 0;
+    for (int32_t base = 0; base < M; base += 32) {
+        const int32_t i = base + lane;
+        int32_t t = -1;
+        bool ok = false;
+        if (i < M) {
+            t = q_terms[off + i];
+            ok = t >= 0 && t < vocab && row_ptr[t + 1] > row_ptr[t];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) v.o_terms[off + n_valid + __popc(m & ((1u << lane) - 1))] = t;
+        n_valid += __popc(m);
+    }
+    __syncwarp();
+    // phase 2: first-occurrence flag + multiplicity among the valid terms
+    for (int32_t i = lane; i < n_valid; i += 32) {
+        const int32_t t = v.o_terms[off + i];
+        int32_t mult = 0;
+        bool first = true;
+        for (int32_t j = 0; j < n_valid; ++j) {
+            const bool eq = v.o_terms[off + j] == t;
+            mult += eq ? 1 : 0;
+            if (eq && j < i) first = false;
+        }
+        v.tmp[off + i] = first ? mult : 0;
+    }
+    __syncwarp();
+    // phase 3: rank among the distinct terms -> ascending unique list
+    int32_t n_uniq = 0;
+    for (int32_t base = 0; base < n_valid; base += 32) {
+        const int32_t i = base + lane;
+        const bool first = i < n_valid && v.tmp[off + i] > 0;
+        if (first) {
+            const int32_t t = v.o_terms[off + i];
+            int32_t rank = 0;
+            for (int32_t j = 0; j < n_valid; ++j) rank += (v.tmp[off + j] > 0 && v.o_terms[off + j] < t) ? 1 : 0;
+            v.u_terms[off + rank] = t;
+            v.u_mult[off + rank] = dedup ? 1 : v.tmp[off + i];
+        }
+        n_uniq += __popc(__ballot_sync(0xffffffffu, first));
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int64_t cum = 0;
+        for (int32_t i = 0; i < n_uniq; ++i) {
+            const int32_t t = v.u_terms[off + i];
+            v.u_cum[off + i] = cum;
+            cum += row_ptr[t + 1] - row_ptr[t];
+        }
+        v.u_cnt[q] = n_uniq;
+        v.o_cnt[q] = n_valid;
+        v.P[q] = cum;
+        v.n_chunks[q] = (uint32_t)((cum + SCORE_CHUNK - 1) / SCORE_CHUNK);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// dense scoring: one work item = SCORE_CHUNK consecutive postings of one query's concatenated lists
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_score_dense(const br_posting* __restrict__ post,
+                                                     const int64_t* __restrict__ row_ptr,
+                                                     const int32_t* __restrict__ q_off, PrepView v,
+                                                     const int64_t* __restrict__ chunk_start, int32_t q_begin,
+                                                     int32_t nq, float* __restrict__ out, int64_t n_docs) {
+    const int64_t w_begin = chunk_start[q_begin], w_end = chunk_start[q_begin + nq];
+    for (int64_t w = w_begin + blockIdx.x; w < w_end; w += gridDim.x) {
+        // query of this work item: last q with chunk_start[q] <= w
+        int32_t lo = q_begin, hi = q_begin + nq;
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (chunk_start[mid] <= w) lo = mid; else hi = mid;
+        }
+        const int32_t q = lo;
+        const int32_t off = q_off[q], nt = v.u_cnt[q];
+        const int64_t e0 = (w - chunk_start[q]) * SCORE_CHUNK;
+        const int64_t e1 = min(e0 + (int64_t)SCORE_CHUNK, v.P[q]);
+        float* row = out + (int64_t)(q - q_begin) * n_docs;
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            int32_t a = 0, b = nt;  // last term index with u_cum <= e
+            while (b - a > 1) {
+                const int32_t mid = (a + b) >> 1;
+                if (v.u_cum[off + mid] <= e) a = mid; else b = mid;
+            }
+            const int32_t t = v.u_terms[off + a];
+            const br_posting p = post[row_ptr[t] + (e - v.u_cum[off + a])];
+            atomicAdd(row + p.doc, p.w * (float)v.u_mult[off + a]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// radix select
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t score_key(float s, int positive_only) {
+    if (positive_only && s == 0.0f) return 0u;
+    const uint32_t u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_score(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct SelView {
+    float* lo;         // [nq] band lower bound
+    int32_t* mode;     // [nq] 0 band, 1 band over positives + zero fill, 2 all non-zero
+    int32_t* zfill;    // [nq] number of zero-score docs to take in doc-id order (mode 1)
+    int64_t* cnt;      // [nq] number of candidates the emit kernel writes
+};
+
+constexpr int SEL_T = 1024;
+
+__global__ void __launch_bounds__(SEL_T) k_select_radix(const float* __restrict__ scores, int64_t n_docs, int32_t k,
+                                                        int positive_only, SelView sv, int32_t q_begin) {
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t s_bin, s_above;
+    __shared__ unsigned long long s_cnt[2];
+    const float* row = scores + (int64_t)blockIdx.x * n_docs;
+    const int q = q_begin + blockIdx.x;
+    uint32_t prefix = 0, mask = 0;
+    uint32_t k_rem = (uint32_t)min((int64_t)k, n_docs);
+    const int shifts[3] = {21, 10, 0};
+    const int widths[3] = {11, 11, 10};
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = shifts[pass], nb = 1 << widths[pass];
+        for (int i = threadIdx.x; i < 2048; i += SEL_T) hist[i] = 0;
+        __syncthreads();
+        for (int64_t i = threadIdx.x; i < n_docs; i += SEL_T) {
+            const uint32_t u = score_key(row[i], positive_only);
+            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & (nb - 1)], 1u);
+        }
+        __syncthreads();
+        // bins from the top: thread t owns reversed bins 2t, 2t+1
+        const int r0 = 2 * threadIdx.x, r1 = r0 + 1;
+        const uint32_t v0 = r0 < nb ? hist[nb - 1 - r0] : 0u, v1 = r1 < nb ? hist[nb - 1 - r1] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_excl_scan(v0 + v1, &total);
+        if (ex < k_rem && k_rem <= ex + v0) { s_bin = nb - 1 - r0; s_above = ex; }
+        else if (ex + v0 < k_rem && k_rem <= ex + v0 + v1) { s_bin = nb - 1 - r1; s_above = ex + v0; }
+        __syncthreads();
+        prefix |= s_bin << shift;
+        mask |= (uint32_t)(nb - 1) << shift;
+        k_rem -= s_above;
+        __syncthreads();
+    }
+    // prefix = key of the k-th largest score
+    const uint32_t kth_key = prefix;
+    int mode = 0;
+    float lo = 0.f;
+    if (positive_only && kth_key == 0u) {
+        mode = 2;                                   // fewer than k docs with a hit: take them all
+    } else {
+        const float kth = key_score(kth_key);
+        if (!positive_only && kth == 0.0f) mode = 1; // fewer than k positive docs: zero tail in doc order
+        lo = kth - kBandRel * fabsf(kth);
+    }
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long c_band = 0, c_pos = 0;
+    for (int64_t i = threadIdx.x; i < n_docs; i += SEL_T) {
+        const float s = row[i];
+        if (mode == 2) c_band += (s != 0.0f);
+        else if (mode == 1) c_pos += (s > 0.0f);
+        else c_band += (s >= lo && !(positive_only && s == 0.0f));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        c_band += __shfl_xor_sync(0xffffffffu, c_band, o);
+        c_pos += __shfl_xor_sync(0xffffffffu, c_pos, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt[0], c_band); atomicAdd(&s_cnt[1], c_pos); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int64_t kk = min((int64_t)k, n_docs);
+        sv.lo[q] = lo;
+        sv.mode[q] = mode;
+        if (mode == 1) {
+            sv.zfill[q] = (int32_t)(kk - (int64_t)s_cnt[1]);
+            sv.cnt[q] = kk;
+        } else {
+            sv.zfill[q] = 0;
+            sv.cnt[q] = (int64_t)s_cnt[0];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SEL_T) k_emit_cands(const float* __restrict__ scores, int64_t n_docs,
+                                                      int positive_only, SelView sv, int32_t q_begin,
+                                                      const int64_t* __restrict__ cand_off, int32_t* __restrict__ cand) {
+    const float* row = scores + (int64_t)blockIdx.x * n_docs;
+    const int q = q_begin + blockIdx.x;
+    const int mode = sv.mode[q];
+    const float lo = sv.lo[q];
+    const uint32_t zfill = (uint32_t)sv.zfill[q];
+    int32_t* out = cand + cand_off[q];
+    uint32_t n_out = 0, n_zero = 0;   // running totals (identical in all threads)
+    for (int64_t base = 0; base < n_docs; base += SEL_T) {
+        const int64_t i = base + threadIdx.x;
+        const float s = i < n_docs ? row[i] : -CUDART_INF_F;
+        bool take, zero = false;
+        if (mode == 2) take = i < n_docs && s != 0.0f;
+        else if (mode == 1) { take = s > 0.0f; zero = i < n_docs && s == 0.0f; }
+        else take = i < n_docs && s >= lo && !(positive_only && s == 0.0f);
+        uint32_t total, ztotal = 0, zex = 0;
+        if (mode == 1) {
+            zex = block_excl_scan(zero ? 1u : 0u, &ztotal);
+            if (zero && n_zero + zex < zfill) take = true;
+        }
+        const uint32_t ex = block_excl_scan(take ? 1u : 0u, &total);
+        if (take) out[n_out + ex] = (int32_t)i;
+        n_out += total;
+        n_zero += ztotal;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// exact float64 re-score of candidates
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rescore_one(const br_posting* __restrict__ post, const uint16_t* __restrict__ tf,
+                                              const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ dl,
+                                              const double* __restrict__ idf, const int32_t* __restrict__ terms,
+                                              int32_t nt, uint32_t doc, double avgdl, double k1, double b,
+                                              int variant) {
+    double s = 0.0;
+    const double dld = (double)dl[doc];
+    for (int32_t i = 0; i < nt; ++i) {
+        const int32_t t = terms[i];
+        int64_t lo = row_ptr[t], hi = row_ptr[t + 1];
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (post[mid].doc < doc) lo = mid + 1; else hi = mid;
+        }
+        if (lo < row_ptr[t + 1] && post[lo].doc == doc)
+            s = __dadd_rn(s, bm25_contrib(idf[t], (double)tf[lo], dld, avgdl, k1, b, variant));
+    }
+    return s;
+}
+
+__global__ void k_rescore(const br_posting* __restrict__ post, const uint16_t* __restrict__ tf,
+                          const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ dl,
+                          const double* __restrict__ idf, const int32_t* __restrict__ q_off, PrepView v, int dedup,
+                          const int64_t* __restrict__ cand_off, int32_t q_begin, int32_t nq,
+                          const int32_t* __restrict__ cand, double* __restrict__ cand_score, double avgdl, double k1,
+                          double b, int variant) {
+    const int64_t c0 = cand_off[q_begin], c1 = cand_off[q_begin + nq];
+    for (int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += (int64_t)gridDim.x * blockDim.x) {
+        int32_t lo = q_begin, hi = q_begin + nq;
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (cand_off[mid] <= c) lo = mid; else hi = mid;
+        }
+        const int32_t q = lo, off = q_off[q];
+        const int32_t* terms = dedup ? v.u_terms + off : v.o_terms + off;
+        const int32_t nt = dedup ? v.u_cnt[q] : v.o_cnt[q];
+        cand_score[c] = rescore_one(post, tf, row_ptr, dl, idf, terms, nt, (uint32_t)cand[c], avgdl, k1, b, variant);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// final select: (score desc, id asc), duplicates removed, streaming over any number of candidates
+// ------------------------------------------------------------------------------------------
+constexpr int FS_T = 256, FS_N = 2048;
+
+struct FsKey {
+    double s;
+    int64_t id;
+};
+__device__ __forceinline__ bool fs_before(const FsKey& a, const FsKey& b) {
+    return a.s > b.s || (a.s == b.s && a.id < b.id);
+}
+
+__device__ void fs_sort(FsKey* keys) {  // bitonic, FS_N elements, "before" order ascending in index
+    for (int size = 2; size <= FS_N; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < FS_N / 2; i += FS_T) {
+                const int a = 2 * i - (i & (stride - 1));
+                const int b = a + stride;
+                const bool up = (a & size) == 0;
+                const FsKey ka = keys[a], kb = keys[b];
+                if (fs_before(kb, ka) == up) { keys[a] = kb; keys[b] = ka; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Candidates of query q: parts p = 0..n_parts-1, each the range [off_p, off_p + cnt_p) of ids/scores.
+template <class IdT>
+__global__ void __launch_bounds__(FS_T) k_final_select(const IdT* __restrict__ ids, const double* __restrict__ sc,
+                                                       const int64_t* __restrict__ cand_off, int32_t q_begin,
+                                                       int32_t n_parts, int64_t part_stride, int32_t fixed_cnt,
+                                                       int32_t k, int64_t id_base, int positive_only,
+                                                       IdT* __restrict__ out_ids, double* __restrict__ out_sc,
+                                                       int32_t* __restrict__ out_cnt) {
+    __shared__ FsKey keys[FS_N];
+    __shared__ uint32_t s_flag[FS_N];
+    const int q = q_begin + blockIdx.x;
+    const FsKey pad = {-CUDART_INF, INT64_MAX};
+    int n_best = 0;  // unique entries currently kept in keys[0, n_best)
+    int part = 0;
+    int64_t pos = 0;
+    bool done = false;
+    while (!done) {
+        // fill keys[n_best, FS_N) from the candidate stream
+        int filled = n_best;
+        __syncthreads();
+        while (filled < FS_N && part < n_parts) {
+            const int64_t base = cand_off ? cand_off[q] : (int64_t)part * part_stride + (int64_t)q * fixed_cnt;
+            const int64_t cnt = cand_off ? cand_off[q + 1] - cand_off[q] : fixed_cnt;
+            const int64_t take = min((int64_t)(FS_N - filled), cnt - pos);
+            for (int64_t i = threadIdx.x; i < take; i += FS_T) {
+                const IdT id = ids[base + pos + i];
+                FsKey kk = {sc[base + pos + i], (int64_t)id};
+                if (id < 0) kk = pad;
+                keys[filled + i] = kk;
+            }
+            filled += (int)take;
+            pos += take;
+            if (pos >= cnt) { ++part; pos = 0; }
+        }
+        done = part >= n_parts;
+        for (int i = filled + threadIdx.x; i < FS_N; i += FS_T) keys[i] = pad;
+        fs_sort(keys);
+        // unique-compact the head into keys[0, k)
+        for (int i = threadIdx.x; i < FS_N; i += FS_T)
+            s_flag[i] = (keys[i].id != INT64_MAX && (i == 0 || keys[i].id != keys[i - 1].id ||
+                                                     keys[i].s != keys[i - 1].s)) ? 1u : 0u;
+        __syncthreads();
+        // exclusive scan of flags over FS_N (FS_N / FS_T per thread, blocked)
+        constexpr int PER = FS_N / FS_T;
+        uint32_t loc[PER], sum = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) { loc[j] = s_flag[threadIdx.x * PER + j]; sum += loc[j]; }
+        uint32_t total;
+        uint32_t ex = block_excl_scan(sum, &total);
+        FsKey mine[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) mine[j] = keys[threadIdx.x * PER + j];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (loc[j]) { if (ex < (uint32_t)k) keys[ex] = mine[j]; ++ex; }
+        }
+        __syncthreads();
+        n_best = (int)min(total, (uint32_t)k);
+    }
+    for (int i = threadIdx.x; i < k; i += FS_T) {
+        const bool valid = i < n_best && !(positive_only && keys[i].s == 0.0);
+        out_ids[(int64_t)q * k + i] = valid ? (IdT)(keys[i].id + id_base) : (IdT)-1;
+        out_sc[(int64_t)q * k + i] = valid ? keys[i].s : 0.0;
+    }
+    if (out_cnt && threadIdx.x == 0) {
+        int c = n_best;
+        if (positive_only) { c = 0; while (c < n_best && keys[c].s != 0.0) ++c; }
+        out_cnt[q] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host drivers
+// ------------------------------------------------------------------------------------------
+static int prep_queries(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, int dedup,
+                        cudaStream_t st, PrepView* pv, int64_t** chunk_start, int32_t* total_terms) {
+    int32_t T = 0;
+    BR_CUDA(cudaMemcpyAsync(&T, q_off + nq, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaStreamSynchronize(st));
+    BR_REQUIRE(T >= 0, BR_ERR_INVALID, "query offsets: negative total");
+    *total_terms = T;
+    const size_t Tn = (size_t)T + 1, Q = (size_t)nq + 2;
+    // carve ws_prep
+    size_t bytes = 0;
+    auto carve = [&](size_t n) { size_t o = bytes; bytes += (n + 255) & ~(size_t)255; return o; };
+    const size_t o_ut = carve(Tn * 4), o_um = carve(Tn * 4), o_uc = carve(Tn * 8), o_un = carve(Q * 4),
+                 o_ot = carve(Tn * 4), o_on = carve(Q * 4), o_P = carve(Q * 8), o_nc = carve(Q * 4),
+                 o_tmp = carve(Tn * 4), o_cs = carve(Q * 8);
+    BR_TRY(ix->ws_prep.reserve(bytes));
+    char* p = ix->ws_prep.as<char>();
+    pv->u_terms = (int32_t*)(p + o_ut); pv->u_mult = (int32_t*)(p + o_um); pv->u_cum = (int64_t*)(p + o_uc);
+    pv->u_cnt = (int32_t*)(p + o_un); pv->o_terms = (int32_t*)(p + o_ot); pv->o_cnt = (int32_t*)(p + o_on);
+    pv->P = (int64_t*)(p + o_P); pv->n_chunks = (uint32_t*)(p + o_nc); pv->tmp = (int32_t*)(p + o_tmp);
+    *chunk_start = (int64_t*)(p + o_cs);
+    k_prep_queries<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(q_terms, q_off, nq, ix->vocab, ix->row_ptr, dedup, *pv);
+    BR_CUDA(cudaGetLastError());
+    k_exscan<uint32_t><<<1, 1024, 0, st>>>(pv->n_chunks, nq, *chunk_start);
+    BR_CUDA(cudaGetLastError());
+    ix->stats.kernel_launches += 2;
+    return BR_OK;
+}
+
+int score_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, int dedup, float* out,
+                cudaStream_t st) {
+    BR_REQUIRE(ix && q_terms && q_off && out, BR_ERR_INVALID, "br_score_batch: null pointer");
+    BR_REQUIRE(ix->finalized, BR_ERR_STATE, "br_score_batch: call br_index_finalize first");
+    BR_REQUIRE(nq >= 0, BR_ERR_INVALID, "br_score_batch: nq < 0");
+    if (nq == 0) return BR_OK;
+    BR_CUDA(cudaSetDevice(ix->device));
+    ix->stats = br_query_stats{};
+    PrepView pv;
+    int64_t* chunk_start;
+    int32_t T;
+    BR_TRY(prep_queries(ix, q_terms, q_off, nq, dedup, st, &pv, &chunk_start, &T));
+    BR_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)nq * (size_t)ix->n_docs, st));
+    k_score_dense<<<kNumSMs * 8, 256, 0, st>>>(ix->post, ix->row_ptr, q_off, pv, chunk_start, 0, nq, out, ix->n_docs);
+    BR_CUDA(cudaGetLastError());
+    ix->stats.kernel_launches += 1;
+    ix->stats.queries_dense += nq;
+    return BR_OK;
+}
+
+// Dense path for queries [q_begin, q_begin + nq) of a prepared batch; results into out_* rows.
+static int topk_dense(br_index* ix, const int32_t* q_off, const PrepView& pv, const int64_t* chunk_start,
+                      int32_t q_begin, int32_t nq, int32_t k, int dedup, int positive_only, int32_t* out_ids,
+                      double* out_scores, int32_t* out_counts, cudaStream_t st) {
+    const int64_t N = ix->n_docs;
+    // queries per pass: dense fp32 rows within ~1 GiB
+    int32_t qb = (int32_t)std::max<int64_t>(1, std::min<int64_t>(nq, (1LL << 30) / (4 * N)));
+    BR_TRY(ix->ws_dense.reserve(sizeof(float) * (size_t)qb * (size_t)N));
+    float* dense = ix->ws_dense.as<float>();
+    // selection scratch for the whole batch slice
+    size_t bytes = 0;
+    auto carve = [&](size_t n) { size_t o = bytes; bytes += (n + 255) & ~(size_t)255; return o; };
+    const size_t Q = (size_t)(q_begin + nq) + 2;
+    const size_t o_lo = carve(Q * 4), o_mode = carve(Q * 4), o_z = carve(Q * 4), o_cnt = carve(Q * 8), o_off = carve(Q * 8);
+    BR_TRY(ix->ws_sel.reserve(bytes));
+    char* p = ix->ws_sel.as<char>();
+    SelView sv{(float*)(p + o_lo), (int32_t*)(p + o_mode), (int32_t*)(p + o_z), (int64_t*)(p + o_cnt)};
+    int64_t* cand_off = (int64_t*)(p + o_off);
+    std::vector<int64_t> h_cnt((size_t)qb), h_off((size_t)qb + 1);
+    for (int32_t s = 0; s < nq; s += qb) {
+        const int32_t b0 = q_begin + s, bn = std::min(qb, nq - s);
+        BR_CUDA(cudaMemsetAsync(dense, 0, sizeof(float) * (size_t)bn * (size_t)N, st));
+        k_score_dense<<<kNumSMs * 8, 256, 0, st>>>(ix->post, ix->row_ptr, q_off, pv, chunk_start, b0, bn, dense, N);
+        BR_CUDA(cudaGetLastError());
+        k_select_radix<<<bn, SEL_T, 0, st>>>(dense, N, k, positive_only, sv, b0);
+        BR_CUDA(cudaGetLastError());
+        BR_CUDA(cudaMemcpyAsync(h_cnt.data(), sv.cnt + b0, sizeof(int64_t) * (size_t)bn, cudaMemcpyDeviceToHost, st));
+        BR_CUDA(cudaStreamSynchronize(st));
+        int64_t total = 0;
+        for (int32_t i = 0; i < bn; ++i) { h_off[(size_t)i] = total; total += h_cnt[(size_t)i]; }
+        h_off[(size_t)bn] = total;
+        BR_CUDA(cudaMemcpyAsync(cand_off + b0, h_off.data(), sizeof(int64_t) * ((size_t)bn + 1), cudaMemcpyHostToDevice, st));
+        BR_TRY(ix->ws_cand.reserve((size_t)(total + 1) * (sizeof(int32_t) + sizeof(double)) + 256));
+        int32_t* cand = ix->ws_cand.as<int32_t>();
+        double* cand_sc = (double*)(ix->ws_cand.as<char>() + (((size_t)(total + 1) * sizeof(int32_t) + 255) & ~(size_t)255));
+        k_emit_cands<<<bn, SEL_T, 0, st>>>(dense, N, positive_only, sv, b0, cand_off, cand);
+        BR_CUDA(cudaGetLastError());
+        if (total > 0) {
+            const unsigned rb = (unsigned)std::min<int64_t>((total + 127) / 128, kNumSMs * 16);
+            k_rescore<<<rb, 128, 0, st>>>(ix->post, ix->tf, ix->row_ptr, ix->dl, ix->idf, q_off, pv, dedup, cand_off, b0,
+                                          bn, cand, cand_sc, ix->avgdl, ix->k1, ix->b, ix->variant);
+            BR_CUDA(cudaGetLastError());
+        }
+        k_final_select<int32_t><<<bn, FS_T, 0, st>>>(cand, cand_sc, cand_off, b0, 1, 0, 0, k, 0, positive_only, out_ids,
+                                                     out_scores, out_counts);
+        BR_CUDA(cudaGetLastError());
+        // cand_off/h_off are reused by the next pass
+        BR_CUDA(cudaStreamSynchronize(st));
+        ix->stats.kernel_launches += 5;
+        ix->stats.candidates_rescored += total;
+    }
+    ix->stats.queries_dense += nq;
+    return BR_OK;
+}
+
+int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, int32_t k, int dedup,
+               int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st) {
+    BR_REQUIRE(ix && q_terms && q_off && out_ids && out_scores, BR_ERR_INVALID, "br_topk_batch: null pointer");
+    BR_REQUIRE(ix->finalized, BR_ERR_STATE, "br_topk_batch: call br_index_finalize first");
+    BR_REQUIRE(k >= 1 && k <= BR_MAX_K, BR_ERR_INVALID, "br_topk_batch: k must be in [1, BR_MAX_K]");
+    BR_REQUIRE(nq >= 0, BR_ERR_INVALID, "br_topk_batch: nq < 0");
+    if (nq == 0) return BR_OK;
+    BR_CUDA(cudaSetDevice(ix->device));
+    ix->stats = br_query_stats{};
+    PrepView pv;
+    int64_t* chunk_start;
+    int32_t T;
+    BR_TRY(prep_queries(ix, q_terms, q_off, nq, dedup, st, &pv, &chunk_start, &T));
+    BR_TRY(topk_dense(ix, q_off, pv, chunk_start, 0, nq, k, dedup, positive_only, out_ids, out_scores, out_counts, st));
+    // algorithmic bytes of this batch: 8 B per posting of every distinct in-vocab query term
+    std::vector<int64_t> hP((size_t)nq);
+    BR_CUDA(cudaMemcpyAsync(hP.data(), pv.P, sizeof(int64_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaStreamSynchronize(st));
+    int64_t sum = 0;
+    for (int64_t v : hP) sum += v;
+    ix->stats.postings_bytes = 8 * sum;
+    return BR_OK;
+}
+
+int rescore_docs(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, int dedup,
+                 const int32_t* cand_ids, const int64_t* cand_off, double* out_scores, cudaStream_t st) {
+    BR_REQUIRE(ix && q_terms && q_off && cand_ids && cand_off && out_scores, BR_ERR_INVALID, "br_rescore_docs: null pointer");
+    BR_REQUIRE(ix->finalized, BR_ERR_STATE, "br_rescore_docs: call br_index_finalize first");
+    if (nq <= 0) return BR_OK;
+    BR_CUDA(cudaSetDevice(ix->device));
+    PrepView pv;
+    int64_t* chunk_start;
+    int32_t T;
+    BR_TRY(prep_queries(ix, q_terms, q_off, nq, dedup, st, &pv, &chunk_start, &T));
+    k_rescore<<<kNumSMs * 16, 128, 0, st>>>(ix->post, ix->tf, ix->row_ptr, ix->dl, ix->idf, q_off, pv, dedup, cand_off, 0, nq,
+                                            cand_ids, out_scores, ix->avgdl, ix->k1, ix->b, ix->variant);
+    BR_CUDA(cudaGetLastError());
+    return BR_OK;
+}
+
+int topk_merge(const int64_t* ids, const double* scores, int32_t n_parts, int32_t nq, int32_t k, int64_t* out_ids,
+               double* out_scores, cudaStream_t st) {
+    BR_REQUIRE(ids && scores && out_ids && out_scores, BR_ERR_INVALID, "br_topk_merge: null pointer");
+    BR_REQUIRE(n_parts >= 1 && nq >= 0 && k >= 1 && k <= BR_MAX_K, BR_ERR_INVALID, "br_topk_merge: bad sizes");
+    if (nq == 0) return BR_OK;
+    k_final_select<int64_t><<<nq, FS_T, 0, st>>>(ids, scores, nullptr, 0, n_parts, (int64_t)nq * k, k, k, 0, 0, out_ids,
+                                                 out_scores, nullptr);
+    BR_CUDA(cudaGetLastError());
+    return BR_OK;
+}
+
+}  // namespace br

@@ -1,0 +1,91 @@
+"""Module-level functions of the reference's hot path with their original signatures:
+``compute_tf_df_and_avgdl`` / ``compute_idf`` (cosine_similarity_bm25_reranking.py:129-182),
+``score_documents_for_query`` (team_run1.py:173-199)."""
+from __future__ import annotations
+
+import pickle
+
+import numpy as np
+
+from .bm25 import BM25
+
+
+def compute_tf_df_and_avgdl(corpus_df, path_to_saved_file=None, device=None, return_model=False):
+    """cosine_similarity_bm25_reranking.py:129-172 -> ``(tf_dict, df_dict, avgdl, num_docs)`` with
+    term-major ``tf_dict = {term: {docid: tf}}``; the four pickles are written as a side effect when
+    ``path_to_saved_file`` is given (:163-170).  tf / df / avgdl come from the GPU index build."""
+    doc_ids = list(corpus_df["docid"])
+    docs = [str(t).split() for t in corpus_df["preprocessed_text"]]
+    model = BM25(docs, variant="okapi_no_plus1", device=device)
+    c = model._export_csr()
+    rp = c["row_ptr"]
+    tf_dict = {}
+    for t, term in enumerate(model.terms):
+        lo, hi = rp[t], rp[t + 1]
+        if hi > lo:
+            tf_dict[term] = {doc_ids[d]: f for d, f in zip(c["doc"][lo:hi].tolist(), c["tf"][lo:hi].tolist())}
+    df_dict = {term: int(rp[t + 1] - rp[t]) for t, term in enumerate(model.terms) if rp[t + 1] > rp[t]}
+    avgdl = model.avgdl
+    num_docs = len(doc_ids)
+    if path_to_saved_file is not None:
+        for name, obj in (("tf_dict", tf_dict), ("df_dict", df_dict), ("avgdl", avgdl), ("num_docs", num_docs)):
+            with open(path_to_saved_file + name + ".pkl", "wb") as f:
+                pickle.dump(obj, f)
+    if return_model:
+        return tf_dict, df_dict, avgdl, num_docs, model
+    return tf_dict, df_dict, avgdl, num_docs
+
+
+def compute_idf(df_dict, num_docs):
+    """cosine_similarity_bm25_reranking.py:176-182: ``{term: np.log((N - df + .5) / (df + .5))}`` - no
+    +1, negative when df > N/2.  A dict-to-dict host function (V logs); the device-side idf of an
+    index lives in ``BM25(variant="okapi_no_plus1").idf``."""
+    terms = list(df_dict.keys())
+    df = np.fromiter((df_dict[t] for t in terms), dtype=np.float64, count=len(terms))
+    idf = np.log((num_docs - df + 0.5) / (df + 0.5))
+    return {t: v for t, v in zip(terms, idf.tolist())}
+
+
+class ScoreDocumentsContext:
+    """What ``score_documents_for_query`` reads from module globals in the reference
+    (``inverted_index``, ``doc_lengths``, ``N``, ``avg_doc_length``, team_run1.py:88-124): here one
+    okapi-variant index with duplicate-counting queries."""
+
+    def __init__(self, model: BM25, doc_ids=None, top=100):
+        if model.variant != "okapi" or model.dedup_query:
+            raise ValueError("score_documents_for_query needs BM25(variant='okapi', dedup_query=False)")
+        self.model, self.doc_ids, self.top = model, doc_ids, top
+
+
+_context = None
+
+
+def set_context(ctx):
+    global _context
+    _context = ctx
+
+
+def score_documents_for_queries(args_list, ctx=None):
+    """Batched form: [(query_id, query_tokens), ...] -> [(query_id, [doc ids] <= 100), ...]."""
+    ctx = ctx or _context
+    if ctx is None:
+        raise RuntimeError("score_documents_for_query: call set_context(ScoreDocumentsContext(...)) first")
+    if not args_list:
+        return []
+    k = min(ctx.top, ctx.model.corpus_size)
+    ids, _, cnt = ctx.model.retrieve_top_n_batch([a[1] for a in args_list], k, positive_only=True,
+                                                 return_counts=True)
+    ids, cnt = ids.cpu().numpy(), cnt.cpu().numpy()
+    out = []
+    for (qid, _), row, c in zip(args_list, ids, cnt):
+        docs = row[:c].tolist()
+        out.append((qid, [ctx.doc_ids[d] for d in docs] if ctx.doc_ids is not None else docs))
+    return out
+
+
+def score_documents_for_query(args):
+    """team_run1.py:173-199: ``(query_id, query_tokens)`` -> ``(query_id, top_docs)``: okapi BM25,
+    duplicates counted, only docs with a hit, ``heapq.nlargest(100, ...)`` order (ties by doc id
+    here).  Do not fork after CUDA initialisation (the reference runs this under process_map,
+    :202): use ``score_documents_for_queries`` for the whole list instead."""
+    return score_documents_for_queries([args])[0]

@@ -1,0 +1,108 @@
+"""Per-language routing + Recall@10 evaluation (the L4 layer of the reference):
+``bm25_models[lang]`` / ``doc_id_maps[lang]`` (bm25_ranking.ipynb:282-316), ``evaluate_recall_at_k``
+(:329-354), ``retrieve_test_queries`` (:368-389) and ``retrieve_top_n_batch``
+(final_implementation.py:179-181).
+
+The reference walks the DataFrame row by row; here queries are grouped by language and each
+group goes through one batched GPU call, which changes nothing in the results (queries are
+independent).  Text preprocessing (nltk / konlpy, bm25_ranking.ipynb:84-110) is out of scope:
+pass ``preprocess`` (``(text, lang) -> list[str]``); by default a query that is already a token
+list is used as is and a string is ``.split()``.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+
+import numpy as np
+
+
+def _default_preprocess(query, lang):
+    if isinstance(query, str):
+        return query.split()
+    return list(query)
+
+
+def _rows(data):
+    """DataFrame | list[dict] -> list of dict-like rows in order (DataFrame.iterrows order)."""
+    if hasattr(data, "iterrows"):
+        return [row for _, row in data.iterrows()]
+    return list(data)
+
+
+class LanguageModels(dict):
+    """``bm25_models`` with the matching ``doc_id_maps`` attached (bm25_ranking.ipynb:282-316)."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.doc_id_maps = {}
+
+    def add(self, lang, model, doc_ids):
+        self[lang] = model
+        self.doc_id_maps[lang] = doc_ids
+        return self
+
+
+def _batched_top(bm25_models, rows, k, preprocess, batch_size):
+    """-> list (aligned with rows) of np.ndarray local ids, or None when the language is unknown."""
+    by_lang = defaultdict(list)
+    for i, row in enumerate(rows):
+        by_lang[row["lang"]].append(i)
+    out = [None] * len(rows)
+    for lang, idxs in by_lang.items():
+        if lang not in bm25_models:              # bm25_ranking.ipynb:336-337 / :374-376
+            continue
+        model = bm25_models[lang]
+        for s in range(0, len(idxs), batch_size):
+            chunk = idxs[s:s + batch_size]
+            toks = [preprocess(rows[i]["query"], lang) for i in chunk]
+            kk = min(k, model.corpus_size)
+            if kk < 1:
+                continue
+            ids, _ = model.retrieve_top_n_batch(toks, kk)
+            ids = ids.cpu().numpy()
+            for j, i in enumerate(chunk):
+                out[i] = ids[j][ids[j] >= 0]
+    return out
+
+
+def evaluate_recall_at_k(bm25_models, doc_id_maps, val_data, k=10, preprocess=None, batch_size=4096):
+    """bm25_ranking.ipynb:329-354: hits / len(val_data); queries of an unknown language are skipped
+    but still counted in the denominator (:331,353)."""
+    rows = _rows(val_data)
+    total = len(rows)
+    top = _batched_top(bm25_models, rows, k, preprocess or _default_preprocess, batch_size)
+    recall_count = 0
+    for row, ids in zip(rows, top):
+        if ids is None:
+            continue
+        doc_ids = doc_id_maps[row["lang"]]
+        retrieved = [doc_ids[int(i)] for i in ids]
+        if row["positive_docs"] in retrieved:
+            recall_count += 1
+    return recall_count / total if total > 0 else 0
+
+
+def retrieve_test_queries(bm25_models, doc_id_maps, test_df, k=10, preprocess=None, batch_size=4096):
+    """bm25_ranking.ipynb:368-389 -> list[list[docid]]; ``[]`` for an unknown language."""
+    rows = _rows(test_df)
+    top = _batched_top(bm25_models, rows, k, preprocess or _default_preprocess, batch_size)
+    out = []
+    for row, ids in zip(rows, top):
+        if ids is None:
+            out.append([])
+            continue
+        doc_ids = doc_id_maps[row["lang"]]
+        out.append([doc_ids[int(i)] for i in ids])
+    return out
+
+
+def retrieve_top_n_batch(args):
+    """final_implementation.py:179-181: ``(bm25_model, tokenized_query_batch, k)`` ->
+    ``[np.ndarray of local indices, ...]``."""
+    bm25_model, tokenized_query_batch, k = args
+    if len(tokenized_query_batch) == 0:
+        return []
+    if k >= bm25_model.corpus_size:
+        return [bm25_model.retrieve_top_n(q, n=k) for q in tokenized_query_batch]
+    ids, _ = bm25_model.retrieve_top_n_batch(tokenized_query_batch, k)
+    return [r.astype(np.int64) for r in ids.cpu().numpy()]

@@ -1,0 +1,149 @@
+/* br_b200.h - C ABI of the B200-native BM25 / cosine retrieval hot path.
+ *
+ * The reference (Harkeerat2002/document-retrieval) has no FFI layer: its boundary for this path is
+ * a set of Python callables.  This header is the boundary a binding for those
+ * callables sits on; document_retrieval_b200/_lib.py is that binding (ctypes) and INTEGRATION.md
+ * shows the stub a reference maintainer would add.  Each entry point names the reference code it
+ * replaces (file:line in the reference checkout; .ipynb lines are raw JSON lines).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; every function returns 0 on success and a negative
+ *     br_status on failure; br_last_error() gives the message (thread-local).
+ *   - "dev" pointers are CUDA device pointers on the handle's device, caller-owned unless stated;
+ *     "host" pointers are ordinary host memory.  Work is enqueued on the cudaStream_t passed as
+ *     `stream` (an opaque void* here so that C callers need no CUDA headers); calls that must
+ *     return host-visible values synchronise that stream before returning.
+ *   - One handle = one device.  A handle is not thread-safe; distinct handles are independent.
+ *   - Doc ids are 32-bit and local to the handle's shard: global id = doc_base + local id.
+ *   - There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef BR_B200_H
+#define BR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct br_index br_index;
+
+typedef enum br_status {
+    BR_OK = 0,
+    BR_ERR_INVALID = -1,   /* bad argument (null pointer, token id outside [0,vocab), k out of range ...) */
+    BR_ERR_CUDA = -2,      /* a CUDA runtime call or kernel failed */
+    BR_ERR_STATE = -3,     /* call order violated (e.g. query before br_index_finalize) */
+    BR_ERR_UNSUPPORTED = -4
+} br_status;
+
+/* BM25 formula variants:
+ *   NOTEBOOK        idf = ln(1+(N-df+.5)/(df+.5)), norm = 1-b+dl/avgdl      bm25_ranking.ipynb:189,202
+ *   OKAPI           same idf,                       norm = 1-b+b*dl/avgdl   team_run1.py:187,193
+ *   OKAPI_NO_PLUS1  idf = ln((N-df+.5)/(df+.5)),    norm = 1-b+b*dl/avgdl   cosine_similarity_bm25_reranking.py:179 */
+typedef enum br_variant { BR_NOTEBOOK = 0, BR_OKAPI = 1, BR_OKAPI_NO_PLUS1 = 2 } br_variant;
+
+const char* br_last_error(void);
+/* "br_b200 <version> sm_100a" */
+const char* br_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Index build.  Replaces BM25.__init__/build (bm25_ranking.ipynb:167-189,
+ * final_implementation.py:92-118), compute_tf_df_and_avgdl
+ * (cosine_similarity_bm25_reranking.py:129-172) and build_inverted_index (team_run1.py:80-99).
+ *
+ * Phase 1 (br_index_build): tokenised docs -> CSR posting lists sorted by (term, doc) with raw tf,
+ * per-doc length dl and the shard-local df histogram.  token_ids_dev is int32[doc_offsets[n_docs]],
+ * doc_offsets_dev is int64[n_docs+1]; both are only read and may be freed after the call.
+ * Phase 2 (br_index_finalize): fixes the corpus statistics the weights depend on - N, sum of
+ * doc lengths and the df histogram.  A single-GPU caller passes n_stat = 0, sum_dl_stat = 0,
+ * df_stat_host = NULL (the shard's own statistics are used).  A doc-sharded caller all-reduces
+ * (sum) br_index_df_dev()/n_docs/sum_dl across ranks between the two phases and passes the
+ * global values, so every shard computes bit-identical idf / avgdl.  idf is evaluated on the host
+ * in float64 with libm log() - the same routine CPython's math.log uses
+ * (bm25_ranking.ipynb:189) - and each posting gets w = fp32(idf*((tf*(k1+1))/(tf+k1*norm))).
+ * ------------------------------------------------------------------------------------------- */
+int br_index_build(const int32_t* token_ids_dev, const int64_t* doc_offsets_dev, int64_t n_docs,
+                   int32_t vocab, int64_t doc_base, void* stream, br_index** out);
+int br_index_finalize(br_index* ix, double k1, double b, int variant, double n_stat,
+                      double sum_dl_stat, const int64_t* df_stat_host, void* stream);
+void br_index_destroy(br_index* ix);
+
+/* corpus_size / nnz / avgdl / sum(dl) attributes (bm25_ranking.ipynb:170-171). Any out may be NULL. */
+int br_index_stats(const br_index* ix, int64_t* n_docs, int32_t* vocab, int64_t* nnz,
+                   double* avgdl, int64_t* sum_dl, int64_t* doc_base);
+/* Device pointer to the shard-local df histogram, uint32[vocab] (for the cross-shard all-reduce). */
+const uint32_t* br_index_df_dev(const br_index* ix);
+/* `df` / `idf` attributes (bm25_ranking.ipynb:173-174,188-189; compute_idf
+ * cosine_similarity_bm25_reranking.py:176-182): df_host int64[vocab] (statistics in force),
+ * idf_host double[vocab] (NaN where df == 0).  Either may be NULL. */
+int br_index_export_df_idf(const br_index* ix, int64_t* df_host, double* idf_host);
+/* CSR export for `inverted_index` / `term_freqs` / `doc_lengths` attributes and for pickling
+ * (joblib.dump(bm25_model, ...), bm25_ranking.ipynb:312).  row_ptr_host int64[vocab+1],
+ * doc_host int32[nnz], tf_host int32[nnz], dl_host int32[n_docs]; any may be NULL. */
+int br_index_export_csr(const br_index* ix, int64_t* row_ptr_host, int32_t* doc_host,
+                        int32_t* tf_host, int32_t* dl_host);
+/* Rebuild a handle from an exported CSR (unpickling). Call br_index_finalize afterwards. */
+int br_index_import_csr(const int64_t* row_ptr_host, const int32_t* doc_host, const int32_t* tf_host,
+                        const int32_t* dl_host, int64_t n_docs, int32_t vocab, int64_t doc_base,
+                        void* stream, br_index** out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Queries.  A batch is CSR-packed term ids: q_terms_dev int32[q_offsets[nq]], q_offsets_dev
+ * int32[nq+1], device memory.  Term ids outside [0,vocab) or with no postings are skipped, like
+ * `if word not in self.idf: continue` (bm25_ranking.ipynb:195-196).
+ * dedup != 0: set(query) semantics (bm25_ranking.ipynb:193); dedup == 0: every occurrence counts,
+ * in query order (team_run1.py:183).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces BM25.get_scores (bm25_ranking.ipynb:191-204) / calculate_scores
+ * (final_implementation.py:127-145) for a batch: out_scores_dev float32[nq, n_docs] (fp32
+ * accumulation of the precomputed posting weights; within 1e-5 relative of the float64
+ * reference). */
+int br_score_batch(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev,
+                   int32_t nq, int dedup, float* out_scores_dev, void* stream);
+
+/* Replaces BM25.retrieve_top_n (bm25_ranking.ipynb:206-213), retrieve_top_n_batch
+ * (final_implementation.py:179-181) and score_documents_for_query's nlargest
+ * (team_run1.py:196) for a batch.  Outputs are [nq, k], best first, ordered by (float64 score
+ * descending, doc id ascending): out_ids_dev int32 (local ids; -1 pads a short result),
+ * out_scores_dev double (exact float64 re-evaluation of the reference formula, terms summed in
+ * ascending term id for dedup != 0 and in query order otherwise), out_counts_dev int32[nq]
+ * (number of valid entries; may be NULL).  positive_only != 0 keeps only docs with at least one
+ * matching posting (team_run1.py:196); otherwise zero-score docs fill the tail in doc-id order
+ * like the dense argpartition (bm25_ranking.ipynb:211).  1 <= k <= BR_MAX_K.
+ * The call synchronises `stream` before returning. */
+#define BR_MAX_K 1024
+int br_topk_batch(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev,
+                  int32_t nq, int32_t k, int dedup, int positive_only, int32_t* out_ids_dev,
+                  double* out_scores_dev, int32_t* out_counts_dev, void* stream);
+
+/* Exact float64 BM25 of explicit (query, doc) pairs - the arithmetic of the loop body at
+ * bm25_ranking.ipynb:199-203 / team_run1.py:188-194 evaluated doc-at-a-time: query q owns the
+ * candidate docs cand_ids_dev[cand_off_dev[q] .. cand_off_dev[q+1]) (local ids, int32; cand_off
+ * int64[nq+1]); out_scores_dev double[cand_off[nq]].  Used for full rankings (n >= N,
+ * bm25_ranking.ipynb:208-209) and for re-scoring externally chosen candidates. */
+int br_rescore_docs(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq,
+                    int dedup, const int32_t* cand_ids_dev, const int64_t* cand_off_dev,
+                    double* out_scores_dev, void* stream);
+
+/* Merge of per-shard top-k lists after the all-gather (no reference analogue: the reference is
+ * single-process).  ids_dev int64[n_parts, nq, k] (global ids, -1 = padding), scores_dev
+ * double[n_parts, nq, k]; outputs [nq, k] ordered by (score desc, id asc). */
+int br_topk_merge(const int64_t* ids_dev, const double* scores_dev, int32_t n_parts, int32_t nq,
+                  int32_t k, int64_t* out_ids_dev, double* out_scores_dev, void* stream);
+
+/* Counters of the last br_topk_batch call on this handle (bench / tests): kernels launched,
+ * queries served by the fused tiled path, by the dense path, and candidate rows re-scored. */
+typedef struct br_query_stats {
+    int64_t kernel_launches;
+    int64_t queries_fused;
+    int64_t queries_dense;
+    int64_t candidates_rescored;
+    int64_t postings_bytes;      /* algorithmic bytes: 8 * sum over queries of sum df (local shard) */
+} br_query_stats;
+int br_last_query_stats(const br_index* ix, br_query_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BR_B200_H */

@@ -1,0 +1,214 @@
+"""GPU parity tests (B200): the CUDA path through the C ABI against the oracle and the golden
+fixtures made from the unmodified reference.  Bar: top-k doc ids bit-exact (ties by doc id),
+float64 top-k scores equal to the oracle's, dense fp32 scores within 1e-5 relative."""
+import io
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bm25_oracle as orc
+from oracle.c_oracle import COracle
+from document_retrieval_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5   # north_star: BM25 scores within 1e-5 relative in fp32
+
+
+def _q(g, i):
+    return g["q_terms"][int(g["q_offsets"][i]):int(g["q_offsets"][i + 1])]
+
+
+def _model(g, **kw):
+    from document_retrieval_b200 import BM25
+    return BM25.from_token_ids(g["doc_offsets"], g["token_ids"], int(g["vocab"]), **kw)
+
+
+def _assert_dense_close(got, want):
+    scale = np.maximum(np.abs(want), np.abs(want).max() * 1e-3 + 1e-30)
+    assert np.max(np.abs(got - want) / scale) < REL_TOL
+
+
+def test_library_loaded_and_version():
+    from document_retrieval_b200 import _lib
+    assert b"sm_100a" in _lib.load().br_version()
+
+
+@pytest.mark.parametrize("name", ["nb_small", "nb_c1slice"])
+def test_index_build_matches_oracle_and_reference(golden, name):
+    g = golden(name)
+    m = _model(g)
+    ix = orc.build_index(g["doc_offsets"], g["token_ids"], int(g["vocab"]))
+    c = m._export_csr()
+    assert np.array_equal(c["row_ptr"], ix.row_ptr) and np.array_equal(c["doc"], ix.post_doc)
+    assert np.array_equal(c["tf"], ix.post_tf) and np.array_equal(c["dl"], ix.dl)
+    df, idf = m._export_df_idf()
+    assert np.array_equal(df, g["df"])
+    assert np.array_equal(idf[df > 0], g["idf"][df > 0])            # bit-exact vs math.log of the reference
+    assert m.avgdl == float(g["avgdl"]) and m.corpus_size == int(g["corpus_size"])
+
+
+@pytest.mark.parametrize("name", ["nb_small", "nb_c1slice"])
+def test_topk_matches_reference_golden(golden, name):
+    g = golden(name)
+    m = _model(g)
+    ids, sc = m.retrieve_top_n_batch((g["q_terms"], g["q_offsets"]), 10)
+    ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+    assert np.array_equal(ids, g["top_ids"])
+    np.testing.assert_allclose(sc, g["top_scores"], rtol=1e-13, atol=0)
+    # and bit-equal to the oracle (same ascending-term summation order)
+    ix = orc.build_index(g["doc_offsets"], g["token_ids"], int(g["vocab"]))
+    for i in range(0, g["q_offsets"].size - 1, 7):
+        oi, os_ = orc.topk_canonical(orc.get_scores(ix, _q(g, i)), 10)
+        assert np.array_equal(oi, ids[i]) and np.array_equal(os_, sc[i])
+
+
+def test_dense_scores_match_reference_golden(golden):
+    g = golden("nb_small")
+    m = _model(g)
+    got = m.get_scores_batch((g["q_terms"], g["q_offsets"])).double().cpu().numpy()
+    _assert_dense_close(got, g["scores"])
+    one = m.get_scores(_q(g, 0))
+    assert one.dtype == np.float64 and one.shape == (m.corpus_size,)
+    _assert_dense_close(one, g["scores"][0])
+
+
+def test_full_ranking_and_single_query_api(golden):
+    g = golden("nb_small")
+    m = _model(g)
+    ix = orc.build_index(g["doc_offsets"], g["token_ids"], int(g["vocab"]))
+    for i in range(3):
+        s = orc.get_scores(ix, _q(g, i))
+        full = m.retrieve_top_n(_q(g, i), n=m.corpus_size + 5)              # n >= N, :208-209
+        assert full.size == m.corpus_size and np.array_equal(full, orc.topk_canonical(s, m.corpus_size)[0])
+        assert np.array_equal(m.retrieve_top_n(_q(g, i), 10), g["top_ids"][i])
+        assert np.array_equal(m.get_top_n(_q(g, i), 3), g["top_ids"][i][:3])
+        ex = m.exact_scores(_q(g, i)).cpu().numpy()
+        assert np.array_equal(ex, s)                                          # float64 bit-exact
+
+
+def test_edge_cases(golden):
+    g = golden("edge_small")
+    m = _model(g)
+    got = m.get_scores_batch((g["q_terms"], g["q_offsets"])).double().cpu().numpy()
+    _assert_dense_close(got, g["scores"])
+    ids, sc = m.retrieve_top_n_batch((g["q_terms"], g["q_offsets"]), 4)
+    ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+    for i in range(g["q_offsets"].size - 1):
+        oi = np.lexsort((np.arange(8), -g["scores"][i]))[:4]
+        assert np.array_equal(ids[i], oi), (i, ids[i], oi)
+    assert ids[1].tolist()[:3] == [0, 1, 5]          # exact ties -> doc id order
+    assert ids[3].tolist() == [0, 1, 2, 3] and not sc[3].any()   # OOV-only query: zeros in doc order
+    # empty batch entries and an empty query
+    ids2, _ = m.retrieve_top_n_batch([[], [0], []], 2)
+    assert ids2.cpu().numpy()[0].tolist() == [0, 1]
+
+
+def test_okapi_top100_matches_team_run1_golden(golden):
+    g, t = golden("nb_small"), golden("team_run1_top100")
+    m = _model(g, variant="okapi", dedup_query=False)
+    ids, sc, cnt = m.retrieve_top_n_batch((g["q_terms"], g["q_offsets"]), 100, positive_only=True, return_counts=True)
+    ids, sc, cnt = ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
+    ix = orc.build_index(g["doc_offsets"], g["token_ids"], int(g["vocab"]))
+    assert np.array_equal(cnt, t["cnt"])
+    for i in range(cnt.size):
+        oi, os_ = orc.score_documents_for_query(ix, _q(g, i))
+        n = cnt[i]
+        assert np.array_equal(ids[i, :n], oi) and np.array_equal(sc[i, :n], os_)
+        assert (ids[i, n:] == -1).all()
+        s = orc.get_scores(ix, _q(g, i), "okapi", dedup=False)
+        assert np.array_equal(s[ids[i, :n]], s[t["top"][i, :n]])     # same score sequence as heapq.nlargest
+
+
+@pytest.mark.parametrize("variant,dedup", [("notebook", True), ("okapi", False), ("okapi_no_plus1", True)])
+def test_c1_full_vs_c_oracle(variant, dedup):
+    c = synth.make_config("C1")
+    from document_retrieval_b200 import BM25
+    m = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"], variant=variant, dedup_query=dedup)
+    co = COracle(c["doc_offsets"], c["token_ids"], c["vocab"], variant=variant)
+    pos = variant == "okapi"
+    oi, os_, oc = co.topk_batch(c["q_terms"], c["q_offsets"], 10, dedup=dedup, positive_only=pos)
+    ids, sc, cnt = m.retrieve_top_n_batch((c["q_terms"], c["q_offsets"]), 10, positive_only=pos, return_counts=True)
+    assert np.array_equal(ids.cpu().numpy(), oi)
+    assert np.array_equal(sc.cpu().numpy(), os_)
+    assert np.array_equal(cnt.cpu().numpy(), oc)
+    rec = np.mean([c["qrels"][i] in oi[i] for i in range(oi.shape[0])])
+    assert rec > 0.9
+    st = m.query_stats()
+    assert st["kernel_launches"] > 0 and st["postings_bytes"] > 0
+
+
+def test_large_k_and_k_ge_hits():
+    c = synth.make_config("C1", scale=0.2)
+    from document_retrieval_b200 import BM25
+    m = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"])
+    co = COracle(c["doc_offsets"], c["token_ids"], c["vocab"])
+    for k in (1, 100, 1000):
+        oi, os_, _ = co.topk_batch(c["q_terms"], c["q_offsets"], k)
+        ids, sc = m.retrieve_top_n_batch((c["q_terms"], c["q_offsets"]), k)
+        assert np.array_equal(ids.cpu().numpy(), oi) and np.array_equal(sc.cpu().numpy(), os_)
+
+
+def test_string_api_and_attributes(golden):
+    g = golden("nb_small")
+    from document_retrieval_b200 import BM25
+    docs = synth.to_strings(g["doc_offsets"], g["token_ids"])
+    qs = synth.queries_to_strings(g["q_offsets"], g["q_terms"], int(g["vocab"]))
+    m = BM25(docs, k1=1.5, b=0.75)
+    assert m.corpus_size == len(docs) and m.avgdl == float(g["avgdl"])
+    for i in (0, 5, 40, 41, 42):
+        assert np.array_equal(m.retrieve_top_n(qs[i], n=10), g["top_ids"][i])
+    df, idf = m.df, m.idf
+    t0 = docs[0][0]
+    tid = int(t0[1:])
+    assert df[t0] == g["df"][tid] and idf[t0] == g["idf"][tid]
+    assert m.inverted_index[t0] == sorted(set(d for d in range(len(docs)) if t0 in docs[d]))
+    assert m.term_freqs[0][t0] == docs[0].count(t0)
+    assert m.doc_lengths[3] == len(docs[3])
+    with pytest.raises(ZeroDivisionError):
+        BM25([])
+
+
+def test_pickle_roundtrip(golden):
+    g = golden("nb_small")
+    from document_retrieval_b200 import BM25
+    docs = synth.to_strings(g["doc_offsets"], g["token_ids"])
+    m = BM25(docs)
+    buf = io.BytesIO()
+    pickle.dump(m, buf)                       # joblib.dump(bm25_model, ...) uses pickle underneath
+    m2 = pickle.loads(buf.getvalue())
+    qs = synth.queries_to_strings(g["q_offsets"], g["q_terms"], int(g["vocab"]))
+    for i in (0, 7, 21):
+        assert np.array_equal(m2.retrieve_top_n(qs[i], n=10), g["top_ids"][i])
+
+
+def test_recall_and_routing(golden):
+    from document_retrieval_b200 import BM25, evaluate_recall_at_k, retrieve_test_queries, retrieve_top_n_batch
+    langs, queries = synth.make_c2(scale=0.01)
+    models, maps, oracles = {}, {}, {}
+    for lang, c in langs.items():
+        if lang == "ko":
+            continue                                            # an unknown language must be skipped
+        models[lang] = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"])
+        maps[lang] = [f"{lang}-{i}" for i in range(c["n_docs"])]
+        oracles[lang] = orc.build_index(c["doc_offsets"], c["token_ids"], c["vocab"])
+    rows = [dict(query=q["terms"], lang=q["lang"], positive_docs=f"{q['lang']}-{q['qrel']}", query_id=i)
+            for i, q in enumerate(queries)]
+    want_lists = []
+    for r in rows:
+        if r["lang"] not in models:
+            want_lists.append(None)
+            continue
+        ids, _ = orc.retrieve_top_n(oracles[r["lang"]], r["query"], 10)
+        want_lists.append([maps[r["lang"]][i] for i in ids])
+    want = orc.recall_at_k(want_lists, [r["positive_docs"] for r in rows])
+    got = evaluate_recall_at_k(models, maps, rows, k=10)
+    assert got == want and 0 < got < 1.0001
+    lists = retrieve_test_queries(models, maps, rows, k=10)
+    assert lists == [w if w is not None else [] for w in want_lists]
+    any_lang = next(iter(models))
+    some = [r["query"] for r in rows if r["lang"] == any_lang][:3]
+    out = retrieve_top_n_batch((models[any_lang], some, 10))
+    assert [o.tolist() for o in out] == [orc.retrieve_top_n(oracles[any_lang], q, 10)[0].tolist() for q in some]
