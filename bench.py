@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py - BM25 top-10 queries/s on the MS-MARCO-passage-shaped synthetic corpus
+(BASELINE.json configs[3]: 8.8M docs x ~60 tokens, 1M-term Zipf vocab, 10k queries), doc-sharded
+over --gpus N GPUs of one box with an NCCL all-gather + merge of the per-GPU top-k.
+
+A "step" is one pass of the hot path (score + select + float64 re-score + all-gather + merge) over
+the whole 10k-query batch.  Prints ONE JSON line (contract in the task statement):
+  value      queries/s with the queries already resident in HBM
+  e2e        the same through the public API (BM25 / ShardedBM25.retrieve_top_n_batch) from pinned
+             HOST query buffers, H2D + D2H inside the timed region
+  roofline   scoring kernel: algorithmic bytes (8 B x sum df of the distinct query terms)
+             / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the plain-C oracle port (oracle/bm25_oracle.c, query-parallel like the reference's
+             process_map) on this box's host cores, on a bounded query sample at full N
+`--impl reference` times that CPU port alone (the reference itself is Python and has no
+compilable sources; oracle/_ref holds only the port).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BLOCKS = 8   # the corpus is generated in 8 fixed blocks so that it is identical for 1/2/4/8 GPUs
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--docs", type=int, default=8_800_000)
+    p.add_argument("--vocab", type=int, default=1_000_000)
+    p.add_argument("--mean-len", type=int, default=60)
+    p.add_argument("--queries", type=int, default=10_000)
+    p.add_argument("--k", type=int, default=10)
+    p.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def block_bounds(n_docs):
+    per = -(-n_docs // N_BLOCKS)
+    return [(min(n_docs, b * per), min(n_docs, (b + 1) * per)) for b in range(N_BLOCKS)]
+
+
+def gen_blocks(args, blocks, device):
+    """Token ids of the given corpus blocks, generated on the device (synth-v1 distribution)."""
+    import torch
+    from document_retrieval_b200 import synth
+    offs, toks = [], []
+    base = 0
+    for b in blocks:
+        lo, hi = block_bounds(args.docs)[b]
+        if hi <= lo:
+            continue
+        do, tk = synth.make_corpus_torch(hi - lo, args.vocab, args.mean_len, device, seed=synth.ROOT_SEED + 17 * b)
+        offs.append(do[:-1] + base if offs else do[:-1])
+        base += int(do[-1].item())
+        toks.append(tk)
+    doc_offsets = torch.cat(offs + [torch.tensor([base], dtype=torch.int64, device=device)])
+    return doc_offsets, torch.cat(toks)
+
+
+def gen_queries(args, doc_offsets, token_ids, doc_lo, doc_hi, rank, world):
+    """Queries whose source doc falls in [doc_lo, doc_hi) are built by the owning rank, then gathered."""
+    import torch
+    import torch.distributed as dist
+    rng = np.random.Generator(np.random.PCG64(20241105 + 4))
+    src = rng.integers(0, args.docs, size=args.queries)
+    m = rng.integers(5, 16, size=args.queries)
+    mine = np.nonzero((src >= doc_lo) & (src < doc_hi))[0]
+    local = {}
+    if mine.size:
+        s = torch.from_numpy(src[mine] - doc_lo).to(doc_offsets.device)
+        lo = doc_offsets[s].cpu().numpy()
+        hi = doc_offsets[s + 1].cpu().numpy()
+        width = int((hi - lo).max())
+        idx = torch.from_numpy(lo).to(doc_offsets.device)[:, None] + torch.arange(width, device=doc_offsets.device)[None, :]
+        toks = token_ids[idx.clamp_(max=token_ids.numel() - 1)].cpu().numpy()
+        for j, qi in enumerate(mine.tolist()):
+            ln = int(hi[j] - lo[j])
+            take = min(int(m[qi]), ln)
+            pos = np.random.Generator(np.random.PCG64(977 * qi + 13)).choice(ln, size=take, replace=False)
+            t = toks[j, pos].astype(np.int32)
+            if qi % 100 == 99:
+                t = np.concatenate([t, np.array([args.vocab], np.int32)])     # OOV token
+            local[qi] = t
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local)
+        for g in gathered:
+            local.update(g)
+    terms = [local[i] for i in range(args.queries)]
+    q_off = np.zeros(args.queries + 1, np.int32)
+    np.cumsum([t.size for t in terms], out=q_off[1:])
+    return np.concatenate(terms).astype(np.int32), q_off, src
+
+
+def cpu_oracle_run(args, doc_offsets_h, token_ids_h, q_terms, q_off, n_sample, threads, repeats=1):
+    """Times the plain-C port on the host: index build (untimed) then `n_sample` queries."""
+    from oracle.c_oracle import COracle
+    t0 = time.time()
+    co = COracle(doc_offsets_h, token_ids_h, args.vocab, variant="notebook", n_threads=threads)
+    build_s = time.time() - t0
+    qo = q_off[:n_sample + 1]
+    best = None
+    out = None
+    for _ in range(repeats):
+        t0 = time.time()
+        out = co.topk_batch(q_terms[:qo[-1]], qo, args.k, dedup=True, n_threads=threads)
+        dt = time.time() - t0
+        best = dt if best is None else min(best, dt)
+    return n_sample / best, build_s, best, out
+
+
+def main():
+    args = parse()
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return 0                                              # rank 0 alone runs the CPU arm
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist_on = world > 1 and args.impl == "ours"
+    if dist_on:
+        dist.init_process_group("nccl", device_id=dev)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workload = (f"C4 MS-MARCO-shaped synthetic: {args.docs} docs x ~{args.mean_len} tok, {args.vocab}-term Zipf vocab, "
+                f"{args.queries} queries of 5-15 terms, BM25 (notebook variant k1=1.5 b=0.75) top-{args.k}")
+
+    # ------------------------------------------------------------------ reference arm (CPU port)
+    if args.impl == "reference":
+        doc_offsets, token_ids = gen_blocks(args, range(N_BLOCKS), dev)
+        q_terms, q_off, _ = gen_queries(args, doc_offsets, token_ids, 0, args.docs, 0, 1)
+        do_h, tk_h = doc_offsets.cpu().numpy(), token_ids.cpu().numpy()
+        del doc_offsets, token_ids
+        n_sample = args.cpu_sample or max(threads, min(args.queries, 4 * threads))
+        from oracle.c_oracle import COracle
+        co = COracle(do_h, tk_h, args.vocab, variant="notebook", n_threads=threads)
+        qo = q_off[:n_sample + 1]
+        for _ in range(args.warmup):
+            co.topk_batch(q_terms[:qo[-1]], qo, args.k, dedup=True, n_threads=threads)
+        t0 = time.time()
+        for _ in range(args.steps):
+            co.topk_batch(q_terms[:qo[-1]], qo, args.k, dedup=True, n_threads=threads)
+        dt = (time.time() - t0) / args.steps
+        qps = n_sample / dt
+        sample = f"{n_sample} of {args.queries} queries at full N={args.docs} per step, index resident in host RAM"
+        print(json.dumps({
+            "impl": "reference", "metric": "BM25 top-10 queries/sec", "value": qps, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    from document_retrieval_b200.sharded import ShardedBM25
+    blocks_per_rank = N_BLOCKS // world
+    my_blocks = list(range(rank * blocks_per_rank, (rank + 1) * blocks_per_rank))
+    bb = block_bounds(args.docs)
+    doc_lo, doc_hi = bb[my_blocks[0]][0], bb[my_blocks[-1]][1]
+    doc_offsets, token_ids = gen_blocks(args, my_blocks, dev)
+    q_terms, q_off, src = gen_queries(args, doc_offsets, token_ids, doc_lo, doc_hi, rank, world)
+    t0 = time.time()
+    sh = ShardedBM25.from_local_token_ids(doc_offsets, token_ids, args.vocab, doc_base=doc_lo, device=dev)
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    model = sh.local
+    st = model.stats()
+    keep_host = (world == 1 and rank == 0 and not args.no_cpu_baseline)
+    do_h = doc_offsets.cpu().numpy() if keep_host else None
+    tk_h = token_ids.cpu().numpy() if keep_host else None
+    del doc_offsets, token_ids
+    torch.cuda.empty_cache()
+
+    # queries: pinned host copies (e2e) and device-resident copies (value)
+    h_terms = torch.from_numpy(q_terms).pin_memory()
+    h_off = torch.from_numpy(q_off).pin_memory()
+    d_terms, d_off = h_terms.to(dev), h_off.to(dev)
+    h_out = torch.empty((args.queries, args.k), dtype=torch.int64).pin_memory()
+
+    def step_device():
+        return sh.retrieve_top_n_batch((d_terms, d_off), args.k)
+
+    def step_e2e():
+        ids, _ = sh.retrieve_top_n_batch((h_terms, h_off), args.k)       # H2D inside
+        h_out.copy_(ids, non_blocking=True)                               # D2H of the result
+        torch.cuda.current_stream().synchronize()
+        return h_out
+
+    def barrier():
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist_on:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    ids_ref, sc_ref = step_device()
+    model.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_device, args.steps)
+    qstats = model.query_stats()            # last step's counters (identical every step)
+    clocks = sampler.stop() if rank == 0 else None
+    model.set_profiling(False)
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    ids_e2e = h_out.clone()
+    assert torch.equal(ids_e2e, ids_ref.cpu()), "e2e and device-resident results differ"
+
+    ms_step = ms_total / args.steps
+    qps = args.queries / (ms_step * 1e-3)
+    qps_e2e = args.queries / (ms_e2e / args.steps * 1e-3)
+    # roofline of the dominant (scoring) kernel on this rank, max-reduced time / summed bytes over ranks
+    alg_bytes = float(qstats["postings_bytes"])
+    k_ms = float(qstats["score_ms"])
+    if dist_on:
+        t = torch.tensor([alg_bytes, k_ms], device=dev, dtype=torch.float64)
+        tb = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        alg_bytes_rank, k_ms = float(tb[0].item()), float(t[1].item())
+    else:
+        alg_bytes_rank = alg_bytes
+    peak, peak_src = measured_peak()
+    launches = max(1, int(qstats["score_launches"]))
+    achieved = alg_bytes_rank / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    recall = float(np.mean([(int(src[i]) in ids_e2e[i].tolist()) for i in range(args.queries)]))
+
+    line = {
+        "metric": "BM25 top-10 queries/sec", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 accumulate + f64 re-score", "data": "synthetic",
+        "config": {"workload": workload, "sharding": f"docs over {world} GPU(s), NCCL all-gather of [Q,k] + merge",
+                   "l2_policy": "inputs (packed postings, %.2f GB per GPU) larger than L2" % (st["nnz"] * 8 / 1e9),
+                   "index_build_s": build_s, "postings_per_gpu": st["nnz"], "recall_at_10_vs_source_doc": recall},
+        "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h_terms.numel() * 4 + h_off.numel() * 4),
+                "d2h_bytes_per_step": int(h_out.numel() * 8)},
+        "gpu_launches": int(qstats["kernel_launches"]) * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "bm25 scoring (per rank)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "peak_source": peak_src, "launches_per_step": launches,
+                     "algorithmic_bytes_per_launch": alg_bytes_rank / launches,
+                     "kernel_ms_per_launch": k_ms / launches, "kernel_share_of_step": k_ms / ms_step,
+                     "path": {"fused": int(qstats["queries_fused"]), "dense": int(qstats["queries_dense"])}},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_sample = args.cpu_sample or max(threads, min(args.queries, 4 * threads))
+        cpu_qps, cpu_build_s, cpu_s, out = cpu_oracle_run(args, do_h, tk_h, q_terms, q_off, n_sample, threads)
+        same = bool(np.array_equal(out[0], ids_e2e[:n_sample].numpy().astype(np.int32)))
+        line["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                                "sample": f"first {n_sample} of {args.queries} queries at full N={args.docs} "
+                                          f"({cpu_s:.1f} s; host index build {cpu_build_s:.1f} s untimed)",
+                                "top10_ids_identical_to_gpu": same}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist_on:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

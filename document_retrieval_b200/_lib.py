@@ -33,12 +33,14 @@ SIGNATURES = {
     "br_rescore_docs": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, _P, _P, _P, _P]),
     "br_topk_merge": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "br_last_query_stats": (C.c_int, [_P, _P]),
+    "br_set_profiling": (C.c_int, [_P, C.c_int]),
 }
 
 
 class QueryStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("queries_fused", C.c_int64), ("queries_dense", C.c_int64),
-                ("candidates_rescored", C.c_int64), ("postings_bytes", C.c_int64)]
+                ("candidates_rescored", C.c_int64), ("postings_bytes", C.c_int64), ("score_launches", C.c_int64),
+                ("score_ms", C.c_double)]
 
 
 class BRError(RuntimeError):

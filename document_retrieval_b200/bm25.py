@@ -252,6 +252,9 @@ class BM25:
 
     get_top_n = retrieve_top_n             # BASELINE.json's wording (rank_bm25 style)
 
+    def set_profiling(self, on=True):
+        check(_lib.load().br_set_profiling(self._h, int(bool(on))), "br_set_profiling")
+
     def query_stats(self):
         st = _lib.QueryStats()
         check(_lib.load().br_last_query_stats(self._h, C.byref(st)), "br_last_query_stats")

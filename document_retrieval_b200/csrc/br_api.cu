@@ -40,4 +40,10 @@ int br_last_query_stats(const br_index* ix, br_query_stats* out) {
     return BR_OK;
 }
 
+int br_set_profiling(br_index* ix, int on) {
+    BR_REQUIRE(ix, BR_ERR_INVALID, "br_set_profiling: null handle");
+    ix->profiling = on != 0;
+    return BR_OK;
+}
+
 }  // extern "C"

@@ -181,6 +181,7 @@ void index_free(br_index* ix) {
     cudaFree(ix->idf); cudaFree(ix->hot_slot); cudaFree(ix->skip);
     ix->ws_prep.release(); ix->ws_dense.release(); ix->ws_sel.release(); ix->ws_cand.release();
     ix->ws_misc.release(); ix->ws_tile.release();
+    for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
     delete ix;
 }
 

@@ -103,6 +103,33 @@ struct br_index {
     // query-time scratch
     br::DevBuf ws_prep, ws_dense, ws_sel, ws_cand, ws_misc, ws_tile;
     br_query_stats stats{};
+
+    // optional event timing of the scoring kernel
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;   // pairs (start, stop)
+    size_t ev_used = 0;
+    void prof_begin(cudaStream_t st) {
+        if (!profiling) return;
+        if (ev_used + 2 > ev_pool.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            ev_pool.push_back(a); ev_pool.push_back(b);
+        }
+        cudaEventRecord(ev_pool[ev_used], st);
+    }
+    void prof_end(cudaStream_t st) {
+        stats.score_launches += 1;
+        if (!profiling) return;
+        cudaEventRecord(ev_pool[ev_used + 1], st);
+        ev_used += 2;
+    }
+    void prof_collect() {   // call after the stream is synchronised
+        for (size_t i = 0; i + 1 < ev_used; i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]) == cudaSuccess) stats.score_ms += ms;
+        }
+        ev_used = 0;
+    }
 };
 
 namespace br {

@@ -477,8 +477,10 @@ static int topk_dense(br_index* ix, const int32_t* q_off, const PrepView& pv, co
     for (int32_t s = 0; s < nq; s += qb) {
         const int32_t b0 = q_begin + s, bn = std::min(qb, nq - s);
         BR_CUDA(cudaMemsetAsync(dense, 0, sizeof(float) * (size_t)bn * (size_t)N, st));
+        ix->prof_begin(st);
         k_score_dense<<<kNumSMs * 8, 256, 0, st>>>(ix->post, ix->row_ptr, q_off, pv, chunk_start, b0, bn, dense, N);
         BR_CUDA(cudaGetLastError());
+        ix->prof_end(st);
         k_select_radix<<<bn, SEL_T, 0, st>>>(dense, N, k, positive_only, sv, b0);
         BR_CUDA(cudaGetLastError());
         BR_CUDA(cudaMemcpyAsync(h_cnt.data(), sv.cnt + b0, sizeof(int64_t) * (size_t)bn, cudaMemcpyDeviceToHost, st));
@@ -531,6 +533,7 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
     int64_t sum = 0;
     for (int64_t v : hP) sum += v;
     ix->stats.postings_bytes = 8 * sum;
+    ix->prof_collect();
     return BR_OK;
 }
 

@@ -1,0 +1,93 @@
+"""Doc-sharded BM25 across the GPUs of one box (one process per GPU, torch.distributed).
+
+The reference is single-process; sharding follows SURVEY 8e: contiguous doc ranges per rank, the
+corpus statistics (N, sum of doc lengths, df histogram) all-reduced once at build time so that
+every shard computes bit-identical idf / avgdl, and at query time only each rank's [Q, k]
+(global id, float64 score) candidates cross NVLink (all-gather) before the k*G -> k merge.
+Top-k over a doc partition is exactly decomposable, so sharded results equal single-GPU results
+bit for bit.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def shard_bounds(n_docs: int, world: int):
+    """Contiguous doc ranges: shard r = [r*ceil(N/G), min(N, (r+1)*ceil(N/G)))."""
+    per = -(-n_docs // world)
+    return [(min(n_docs, r * per), min(n_docs, (r + 1) * per)) for r in range(world)]
+
+
+def reduce_stats(local_df: torch.Tensor, n_docs: int, sum_dl: int, group=None):
+    """All-reduce (sum) of the df histogram and (N, sum dl) -> (df int64[V] on host, N, sum_dl)."""
+    df = local_df.to(torch.int64)
+    st = torch.tensor([n_docs, sum_dl], dtype=torch.int64, device=df.device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(df, group=group)
+        dist.all_reduce(st, group=group)
+    st = st.cpu()
+    return df.cpu().numpy(), int(st[0]), int(st[1])
+
+
+def gather_candidates(ids: torch.Tensor, scores: torch.Tensor, group=None):
+    """all-gather of per-rank [Q, k] candidates -> ([G, Q, k] ids, [G, Q, k] scores)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return ids[None], scores[None]
+    all_ids = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
+    all_sc = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
+    dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_sc, scores.contiguous(), group=group)
+    return all_ids, all_sc
+
+
+def merge_topk_cuda(all_ids: torch.Tensor, all_sc: torch.Tensor, k: int):
+    """br_topk_merge: [G, Q, k] -> [Q, k] by (score desc, id asc)."""
+    lib = _lib.load()
+    g, q, kk = all_ids.shape
+    dev = all_ids.device
+    out_ids = torch.empty((q, k), dtype=torch.int64, device=dev)
+    out_sc = torch.empty((q, k), dtype=torch.float64, device=dev)
+    if kk != k:
+        raise ValueError("candidate width must equal k")
+    with torch.cuda.device(dev):
+        check(lib.br_topk_merge(ptr(all_ids.contiguous()), ptr(all_sc.contiguous()), g, q, k, ptr(out_ids), ptr(out_sc),
+                                _lib.stream_ptr(dev)), "br_topk_merge")
+    return out_ids, out_sc
+
+
+class ShardedBM25:
+    """One rank's view of a doc-sharded index.  ``local`` is this rank's ``BM25`` shard (built with
+    ``doc_base`` = first global doc id of the shard and the all-reduced statistics)."""
+
+    def __init__(self, local, group=None, merge=merge_topk_cuda):
+        self.local, self.group, self.merge = local, group, merge
+
+    @classmethod
+    def from_local_token_ids(cls, doc_offsets, token_ids, vocab_size, doc_base, k1=1.5, b=0.75, *,
+                             variant="notebook", dedup_query=None, device=None, group=None):
+        from .bm25 import BM25
+        m = BM25.from_token_ids(doc_offsets, token_ids, vocab_size, k1, b, variant=variant, dedup_query=dedup_query,
+                                device=device, doc_base=doc_base, finalize=False)
+        st = m.stats()
+        df, n_stat, sum_dl = reduce_stats(m.local_df_tensor(), st["n_docs"], st["sum_dl"], group)
+        m.finalize(n_stat, sum_dl, df)
+        self = cls(m, group)
+        self.n_docs_global = n_stat
+        return self
+
+    def retrieve_top_n_batch(self, queries, n=10):
+        """-> (global ids int64[Q, n], float64 scores[Q, n]) identical on every rank."""
+        ids, sc = self.local.retrieve_top_n_batch(queries, n)
+        gids = torch.where(ids >= 0, ids.to(torch.int64) + self.local.doc_base, torch.full_like(ids, -1, dtype=torch.int64))
+        all_ids, all_sc = gather_candidates(gids, sc, self.group)
+        if all_ids.shape[0] == 1:
+            return gids, sc
+        return self.merge(all_ids, all_sc, n)

@@ -140,8 +140,14 @@ typedef struct br_query_stats {
     int64_t queries_dense;
     int64_t candidates_rescored;
     int64_t postings_bytes;      /* algorithmic bytes: 8 * sum over queries of sum df (local shard) */
+    int64_t score_launches;      /* launches of the scoring kernel (the dominant kernel) */
+    double score_ms;             /* their summed device time (CUDA events on `stream`); 0 unless
+                                    br_set_profiling(ix, 1) */
 } br_query_stats;
 int br_last_query_stats(const br_index* ix, br_query_stats* out);
+/* Bracket every launch of the scoring kernel with CUDA events on the call's stream (bench.py's
+ * live roofline measurement).  Off by default. */
+int br_set_profiling(br_index* ix, int on);
 
 #ifdef __cplusplus
 }
