@@ -34,6 +34,7 @@ SIGNATURES = {
     "br_topk_merge": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "br_last_query_stats": (C.c_int, [_P, _P]),
     "br_set_profiling": (C.c_int, [_P, C.c_int]),
+    "br_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
 }
 
 

@@ -255,6 +255,10 @@ class BM25:
     def set_profiling(self, on=True):
         check(_lib.load().br_set_profiling(self._h, int(bool(on))), "br_set_profiling")
 
+    def set_option(self, name, value):
+        """Library tuning / test switches: "fused" (0 = dense path only), "tile_g" (0 auto, 1/2/4/8)."""
+        check(_lib.load().br_set_option(self._h, name.encode(), int(value)), "br_set_option")
+
     def query_stats(self):
         st = _lib.QueryStats()
         check(_lib.load().br_last_query_stats(self._h, C.byref(st)), "br_last_query_stats")

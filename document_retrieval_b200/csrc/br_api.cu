@@ -46,4 +46,19 @@ int br_set_profiling(br_index* ix, int on) {
     return BR_OK;
 }
 
+int br_set_option(br_index* ix, const char* name, int value) {
+    BR_REQUIRE(ix && name, BR_ERR_INVALID, "br_set_option: null pointer");
+    const std::string n(name);
+    if (n == "fused") ix->allow_fused = value != 0;
+    else if (n == "tile_g") {
+        BR_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 8, BR_ERR_INVALID,
+                   "br_set_option: tile_g must be 0, 1, 2, 4 or 8");
+        ix->tile_g = value;
+    } else {
+        br::set_error("br_set_option: unknown option " + n);
+        return BR_ERR_INVALID;
+    }
+    return BR_OK;
+}
+
 }  // extern "C"

@@ -104,6 +104,9 @@ struct br_index {
     br::DevBuf ws_prep, ws_dense, ws_sel, ws_cand, ws_misc, ws_tile;
     br_query_stats stats{};
 
+    bool allow_fused = true;
+    int tile_g = 0;
+
     // optional event timing of the scoring kernel
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;   // pairs (start, stop)

@@ -19,24 +19,13 @@
 
 #include "br_common.cuh"
 #include "br_kernels.cuh"
+#include "br_query.cuh"
 
 namespace br {
 
 // ------------------------------------------------------------------------------------------
 // query preparation
 // ------------------------------------------------------------------------------------------
-struct PrepView {
-    int32_t* u_terms;   // [T]  per query segment: unique valid terms ascending
-    int32_t* u_mult;    // [T]  multiplicity (1 when dedup)
-    int64_t* u_cum;     // [T]  exclusive prefix of df over the unique terms
-    int32_t* u_cnt;     // [nq]
-    int32_t* o_terms;   // [T]  valid terms in query order (duplicates kept)
-    int32_t* o_cnt;     // [nq]
-    int64_t* P;         // [nq] total postings of the unique terms
-    uint32_t* n_chunks; // [nq]
-    int32_t* tmp;       // [T]
-};
-
 constexpr int SCORE_CHUNK = 8192;
 
 __global__ void k_prep_queries(const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_off, int32_t nq,
@@ -263,34 +252,55 @@ __global__ void __launch_bounds__(SEL_T) k_emit_cands(const float* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // exact float64 re-score of candidates
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double rescore_one(const br_posting* __restrict__ post, const uint16_t* __restrict__ tf,
-                                              const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ dl,
-                                              const double* __restrict__ idf, const int32_t* __restrict__ terms,
-                                              int32_t nt, uint32_t doc, double avgdl, double k1, double b,
-                                              int variant) {
+struct RescoreIndex {
+    const br_posting* post;
+    const uint16_t* tf;
+    const int64_t* row_ptr;
+    const uint32_t* dl;
+    const double* idf;
+    const int32_t* hot_slot;
+    const uint32_t* skip;
+    int32_t n_sub;
+    int sub_shift;
+    double avgdl, k1, b;
+    int variant;
+};
+
+// float64 score of one doc for one query: the reference loop body (bm25_ranking.ipynb:199-203)
+// doc-at-a-time; terms are visited in the given order (ascending id / query order) so the sum is
+// reproducible.  Hot terms use the skip table to narrow the search to one sub-range.
+__device__ __forceinline__ double rescore_one(const RescoreIndex& r, const int32_t* __restrict__ terms, int32_t nt,
+                                              uint32_t doc) {
     double s = 0.0;
-    const double dld = (double)dl[doc];
+    const double dld = (double)r.dl[doc];
     for (int32_t i = 0; i < nt; ++i) {
         const int32_t t = terms[i];
-        int64_t lo = row_ptr[t], hi = row_ptr[t + 1];
+        const int64_t base = r.row_ptr[t], end = r.row_ptr[t + 1];
+        int64_t lo = base, hi = end;
+        const int32_t slot = r.skip ? r.hot_slot[t] : -1;
+        if (slot >= 0) {
+            const uint32_t* sk = r.skip + (int64_t)slot * (r.n_sub + 1) + (doc >> r.sub_shift);
+            lo = base + sk[0];
+            hi = base + sk[1];
+        }
+        const int64_t stop = hi;
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
-            if (post[mid].doc < doc) lo = mid + 1; else hi = mid;
+            if (r.post[mid].doc < doc) lo = mid + 1; else hi = mid;
         }
-        if (lo < row_ptr[t + 1] && post[lo].doc == doc)
-            s = __dadd_rn(s, bm25_contrib(idf[t], (double)tf[lo], dld, avgdl, k1, b, variant));
+        if (lo < stop && r.post[lo].doc == doc)
+            s = __dadd_rn(s, bm25_contrib(r.idf[t], (double)r.tf[lo], dld, r.avgdl, r.k1, r.b, r.variant));
     }
     return s;
 }
 
-__global__ void k_rescore(const br_posting* __restrict__ post, const uint16_t* __restrict__ tf,
-                          const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ dl,
-                          const double* __restrict__ idf, const int32_t* __restrict__ q_off, PrepView v, int dedup,
+__global__ void k_rescore(RescoreIndex r, const int32_t* __restrict__ q_off, PrepView v, int dedup,
                           const int64_t* __restrict__ cand_off, int32_t q_begin, int32_t nq,
-                          const int32_t* __restrict__ cand, double* __restrict__ cand_score, double avgdl, double k1,
-                          double b, int variant) {
+                          const int32_t* __restrict__ cand, double* __restrict__ cand_score) {
     const int64_t c0 = cand_off[q_begin], c1 = cand_off[q_begin + nq];
     for (int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t doc = cand[c];
+        if (doc < 0) continue;                       // unused candidate slot
         int32_t lo = q_begin, hi = q_begin + nq;
         while (hi - lo > 1) {
             const int32_t mid = (lo + hi) >> 1;
@@ -299,7 +309,7 @@ __global__ void k_rescore(const br_posting* __restrict__ post, const uint16_t* _
         const int32_t q = lo, off = q_off[q];
         const int32_t* terms = dedup ? v.u_terms + off : v.o_terms + off;
         const int32_t nt = dedup ? v.u_cnt[q] : v.o_cnt[q];
-        cand_score[c] = rescore_one(post, tf, row_ptr, dl, idf, terms, nt, (uint32_t)cand[c], avgdl, k1, b, variant);
+        cand_score[c] = rescore_one(r, terms, nt, (uint32_t)doc);
     }
 }
 
@@ -404,9 +414,43 @@ __global__ void __launch_bounds__(FS_T) k_final_select(const IdT* __restrict__ i
     }
 }
 
+__global__ void k_scatter_rows(const int32_t* __restrict__ rows, int32_t ns, int32_t k, const int32_t* __restrict__ ids,
+                               const double* __restrict__ sc, const int32_t* __restrict__ cnt, int32_t* __restrict__ out_ids,
+                               double* __restrict__ out_sc, int32_t* __restrict__ out_cnt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)ns * k) return;
+    const int32_t r = (int32_t)(i / k), c = (int32_t)(i - (int64_t)r * k);
+    const int64_t o = (int64_t)rows[r] * k + c;
+    out_ids[o] = ids[i];
+    out_sc[o] = sc[i];
+    if (c == 0 && out_cnt) out_cnt[rows[r]] = cnt[r];
+}
+
 // ------------------------------------------------------------------------------------------
 // host drivers
 // ------------------------------------------------------------------------------------------
+
+static RescoreIndex rescore_view(const br_index* ix) {
+    return RescoreIndex{ix->post, ix->tf, ix->row_ptr, ix->dl, ix->idf, ix->hot_slot, ix->skip, ix->n_sub,
+                        ix->sub_shift, ix->avgdl, ix->k1, ix->b, ix->variant};
+}
+
+int launch_rescore(br_index* ix, const int32_t* q_off, const PrepView& pv, int dedup, const int64_t* cand_off,
+                   int32_t q_begin, int32_t nq, const int32_t* cand, double* cand_score, int64_t total, cudaStream_t st) {
+    const unsigned rb = (unsigned)std::max<int64_t>(1, std::min<int64_t>((total + 127) / 128, kNumSMs * 16));
+    k_rescore<<<rb, 128, 0, st>>>(rescore_view(ix), q_off, pv, dedup, cand_off, q_begin, nq, cand, cand_score);
+    BR_CUDA(cudaGetLastError());
+    return BR_OK;
+}
+
+int launch_final_select(const int32_t* cand, const double* cand_score, const int64_t* cand_off, int32_t q_begin,
+                        int32_t nq, int32_t k, int positive_only, int32_t* out_ids, double* out_scores,
+                        int32_t* out_counts, cudaStream_t st) {
+    k_final_select<int32_t><<<nq, FS_T, 0, st>>>(cand, cand_score, cand_off, q_begin, 1, 0, 0, k, 0, positive_only, out_ids,
+                                                 out_scores, out_counts);
+    BR_CUDA(cudaGetLastError());
+    return BR_OK;
+}
 static int prep_queries(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, int dedup,
                         cudaStream_t st, PrepView* pv, int64_t** chunk_start, int32_t* total_terms) {
     int32_t T = 0;
@@ -494,15 +538,8 @@ static int topk_dense(br_index* ix, const int32_t* q_off, const PrepView& pv, co
         double* cand_sc = (double*)(ix->ws_cand.as<char>() + (((size_t)(total + 1) * sizeof(int32_t) + 255) & ~(size_t)255));
         k_emit_cands<<<bn, SEL_T, 0, st>>>(dense, N, positive_only, sv, b0, cand_off, cand);
         BR_CUDA(cudaGetLastError());
-        if (total > 0) {
-            const unsigned rb = (unsigned)std::min<int64_t>((total + 127) / 128, kNumSMs * 16);
-            k_rescore<<<rb, 128, 0, st>>>(ix->post, ix->tf, ix->row_ptr, ix->dl, ix->idf, q_off, pv, dedup, cand_off, b0,
-                                          bn, cand, cand_sc, ix->avgdl, ix->k1, ix->b, ix->variant);
-            BR_CUDA(cudaGetLastError());
-        }
-        k_final_select<int32_t><<<bn, FS_T, 0, st>>>(cand, cand_sc, cand_off, b0, 1, 0, 0, k, 0, positive_only, out_ids,
-                                                     out_scores, out_counts);
-        BR_CUDA(cudaGetLastError());
+        if (total > 0) BR_TRY(launch_rescore(ix, q_off, pv, dedup, cand_off, b0, bn, cand, cand_sc, total, st));
+        BR_TRY(launch_final_select(cand, cand_sc, cand_off, b0, bn, k, positive_only, out_ids, out_scores, out_counts, st));
         // cand_off/h_off are reused by the next pass
         BR_CUDA(cudaStreamSynchronize(st));
         ix->stats.kernel_launches += 5;
@@ -525,10 +562,54 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
     int64_t* chunk_start;
     int32_t T;
     BR_TRY(prep_queries(ix, q_terms, q_off, nq, dedup, st, &pv, &chunk_start, &T));
-    BR_TRY(topk_dense(ix, q_off, pv, chunk_start, 0, nq, k, dedup, positive_only, out_ids, out_scores, out_counts, st));
     // algorithmic bytes of this batch: 8 B per posting of every distinct in-vocab query term
     std::vector<int64_t> hP((size_t)nq);
     BR_CUDA(cudaMemcpyAsync(hP.data(), pv.P, sizeof(int64_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    if (!fused_supported(ix, k)) {
+        BR_TRY(topk_dense(ix, q_off, pv, chunk_start, 0, nq, k, dedup, positive_only, out_ids, out_scores, out_counts, st));
+    } else {
+        std::vector<int32_t> flags;
+        BR_TRY(topk_fused(ix, q_off, pv, nq, k, dedup, positive_only, out_ids, out_scores, out_counts, st, &flags));
+        std::vector<int32_t> redo;
+        for (int32_t q = 0; q < nq; ++q) if (flags[(size_t)q]) redo.push_back(q);
+        ix->stats.queries_fused += nq - (int64_t)redo.size();
+        if (!redo.empty()) {
+            // the few queries the fused path cannot serve exactly (too many distinct terms, candidate
+            // overflow, fewer than k docs with a hit) go through the dense path as a compacted sub-batch
+            std::vector<int32_t> h_off((size_t)nq + 1), h_terms((size_t)std::max(T, 1));
+            BR_CUDA(cudaMemcpyAsync(h_off.data(), q_off, 4 * ((size_t)nq + 1), cudaMemcpyDeviceToHost, st));
+            BR_CUDA(cudaMemcpyAsync(h_terms.data(), q_terms, 4 * (size_t)T, cudaMemcpyDeviceToHost, st));
+            BR_CUDA(cudaStreamSynchronize(st));
+            const int32_t ns = (int32_t)redo.size();
+            std::vector<int32_t> s_off((size_t)ns + 1, 0), s_terms;
+            for (int32_t i = 0; i < ns; ++i) {
+                const int32_t q = redo[(size_t)i];
+                s_terms.insert(s_terms.end(), h_terms.begin() + h_off[(size_t)q], h_terms.begin() + h_off[(size_t)q + 1]);
+                s_off[(size_t)i + 1] = (int32_t)s_terms.size();
+            }
+            size_t bytes = 0;
+            auto carve = [&](size_t n) { size_t o = bytes; bytes += (n + 255) & ~(size_t)255; return o; };
+            const size_t o_t = carve(4 * (s_terms.size() + 1)), o_o = carve(4 * ((size_t)ns + 1)), o_q = carve(4 * (size_t)ns),
+                         o_i = carve(4 * (size_t)ns * k), o_s = carve(8 * (size_t)ns * k), o_c = carve(4 * (size_t)ns);
+            BR_TRY(ix->ws_misc.reserve(bytes));
+            char* p = ix->ws_misc.as<char>();
+            int32_t *d_t = (int32_t*)(p + o_t), *d_o = (int32_t*)(p + o_o), *d_q = (int32_t*)(p + o_q),
+                    *d_i = (int32_t*)(p + o_i), *d_c = (int32_t*)(p + o_c);
+            double* d_s = (double*)(p + o_s);
+            BR_CUDA(cudaMemcpyAsync(d_t, s_terms.data(), 4 * s_terms.size(), cudaMemcpyHostToDevice, st));
+            BR_CUDA(cudaMemcpyAsync(d_o, s_off.data(), 4 * ((size_t)ns + 1), cudaMemcpyHostToDevice, st));
+            BR_CUDA(cudaMemcpyAsync(d_q, redo.data(), 4 * (size_t)ns, cudaMemcpyHostToDevice, st));
+            PrepView spv;
+            int64_t* s_chunk;
+            int32_t sT;
+            BR_TRY(prep_queries(ix, d_t, d_o, ns, dedup, st, &spv, &s_chunk, &sT));
+            BR_TRY(topk_dense(ix, d_o, spv, s_chunk, 0, ns, k, dedup, positive_only, d_i, d_s, d_c, st));
+            k_scatter_rows<<<blocks_for((int64_t)ns * k, 256), 256, 0, st>>>(d_q, ns, k, d_i, d_s, d_c, out_ids, out_scores,
+                                                                            out_counts);
+            BR_CUDA(cudaGetLastError());
+            ix->stats.kernel_launches += 1;
+        }
+    }
     BR_CUDA(cudaStreamSynchronize(st));
     int64_t sum = 0;
     for (int64_t v : hP) sum += v;
@@ -547,8 +628,7 @@ int rescore_docs(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int
     int64_t* chunk_start;
     int32_t T;
     BR_TRY(prep_queries(ix, q_terms, q_off, nq, dedup, st, &pv, &chunk_start, &T));
-    k_rescore<<<kNumSMs * 16, 128, 0, st>>>(ix->post, ix->tf, ix->row_ptr, ix->dl, ix->idf, q_off, pv, dedup, cand_off, 0, nq,
-                                            cand_ids, out_scores, ix->avgdl, ix->k1, ix->b, ix->variant);
+    k_rescore<<<kNumSMs * 16, 128, 0, st>>>(rescore_view(ix), q_off, pv, dedup, cand_off, 0, nq, cand_ids, out_scores);
     BR_CUDA(cudaGetLastError());
     return BR_OK;
 }

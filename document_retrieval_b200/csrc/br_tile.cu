@@ -1,0 +1,417 @@
+// br_tile.cu - the fused BM25 path for small k: doc-range tiled term-at-a-time scoring with the
+// accumulators in shared memory and the top-k selection fused into the tile epilogue.
+//
+// Why: a dense [Q, N] fp32 accumulator costs 8 B x N of HBM traffic per query (zero + read back) and
+// global atomics for every posting; at N = 8.8M that is more than the postings themselves
+// (hard part 2).  Here a CTA owns (a tile of W x 512 consecutive docs) x (a group of G
+// queries); each of its W warps owns one 512-doc sub-range and walks, for every term of the
+// group's union term list, the slice of that term's posting list that falls in its sub-range (slice
+// bounds come from the per-term skip table built with the index) and adds the packed fp32 weights
+// into its private [G, 512] accumulator rows: plain LDS/FADD/STS, no atomics, no block barrier after
+// the prologue, deterministic order.  A posting loaded once serves every query of the group that
+// contains the term, and the CTAs of all groups visit a tile back to back (blockIdx.x = group), so the
+// tile's posting slices are read from HBM once per batch and from L2 afterwards.
+// Epilogue: per query a running global threshold thr[q] (a lower bound of the k-th best fp32 score,
+// raised with atomicMax from any sub-range that holds k better docs); a doc is emitted as a candidate
+// iff its fp32 score >= thr*(1-1e-5).  Candidates are re-scored exactly in float64 (k_rescore) and
+// ranked by (score desc, id asc) (k_final_select) - see br_query.cu for the exactness argument.
+// Terms too rare for a skip table ("cold", df < hot_min) never enter the tile kernel: every doc on a
+// cold list of a query is made a candidate of that query instead (k_cold_cands) and gets its full
+// score from the float64 re-score; a doc that is on no cold list has fp32 tile score == its full
+// score, so the candidate set still contains the true top-k.
+#include <math_constants.h>
+
+#include "br_common.cuh"
+#include "br_kernels.cuh"
+#include "br_query.cuh"
+
+namespace br {
+
+constexpr int TILE_W = 8;            // warps per CTA = sub-ranges per tile
+constexpr int TILE_SHIFT = 9;        // 512 docs per sub-range (must equal br_index::sub_shift)
+constexpr int TILE_S = 1 << TILE_SHIFT;
+constexpr int TILE_QT = 32;          // max distinct hot terms of one query on this path
+constexpr int TILE_CAP = 2048;       // tile-emitted candidates kept per query
+
+struct __align__(16) TileEntry {
+    int32_t term;
+    int32_t slot;
+    uint8_t mult[8];
+};
+
+// ------------------------------------------------------------------------------------------
+// group preparation: union of the hot terms of G consecutive queries, per-query multiplicities
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* __restrict__ q_off,
+                                                   const int32_t* __restrict__ hot_slot,
+                                                   const int64_t* __restrict__ row_ptr, int32_t nq, int G, int umax,
+                                                   TileEntry* __restrict__ entries, int32_t* __restrict__ n_entries,
+                                                   int32_t* __restrict__ elig, uint32_t* __restrict__ cold_cnt,
+                                                   uint32_t* __restrict__ region) {
+    __shared__ int32_t s_term[4][256];
+    __shared__ uint8_t s_q[4][256], s_m[4][256];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int g = blockIdx.x * 4 + wl;
+    const int n_groups = (nq + G - 1) / G;
+    if (g >= n_groups) return;
+    int n = 0;
+    for (int i = 0; i < G; ++i) {
+        const int q = g * G + i;
+        if (q >= nq) break;
+        const int32_t off = q_off[q], nu = pv.u_cnt[q];
+        int hot = 0, bad = 0;
+        unsigned long long cold = 0;
+        for (int base = 0; base < nu; base += 32) {
+            const int j = base + lane;
+            const int32_t t = j < nu ? pv.u_terms[off + j] : -1;
+            const bool is_hot = t >= 0 && hot_slot[t] >= 0;
+            if (t >= 0 && !is_hot) cold += (unsigned long long)(row_ptr[t + 1] - row_ptr[t]);
+            if (is_hot && pv.u_mult[off + j] > 255) bad = 1;
+            hot += __popc(__ballot_sync(0xffffffffu, is_hot));
+        }
+        for (int o = 16; o > 0; o >>= 1) cold += __shfl_xor_sync(0xffffffffu, cold, o);
+        bad = __any_sync(0xffffffffu, bad);
+        const bool ok = hot <= TILE_QT && !bad && cold < (1ull << 24);
+        if (lane == 0) {
+            elig[q] = ok ? 1 : 0;
+            cold_cnt[q] = ok ? (uint32_t)cold : 0u;
+            region[q] = ok ? (uint32_t)cold + TILE_CAP : 0u;
+        }
+        if (!ok) continue;
+        for (int base = 0; base < nu; base += 32) {
+            const int j = base + lane;
+            const int32_t t = j < nu ? pv.u_terms[off + j] : -1;
+            const bool is_hot = t >= 0 && hot_slot[t] >= 0;
+            const unsigned m = __ballot_sync(0xffffffffu, is_hot);
+            if (is_hot) {
+                const int p = n + __popc(m & ((1u << lane) - 1));
+                s_term[wl][p] = t;
+                s_q[wl][p] = (uint8_t)i;
+                s_m[wl][p] = (uint8_t)pv.u_mult[off + j];
+            }
+            n += __popc(m);
+        }
+    }
+    __syncwarp();
+    int U = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool first = i < n;
+        if (first) {
+            const int32_t t = s_term[wl][i];
+            for (int j = 0; j < i; ++j)
+                if (s_term[wl][j] == t) { first = false; break; }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, first);
+        if (first) {
+            TileEntry e;
+            e.term = s_term[wl][i];
+            e.slot = hot_slot[e.term];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) e.mult[x] = 0;
+            for (int j = i; j < n; ++j)
+                if (s_term[wl][j] == e.term) e.mult[s_q[wl][j]] = s_m[wl][j];
+            entries[(int64_t)g * umax + U + __popc(m & ((1u << lane) - 1))] = e;
+        }
+        U += __popc(m);
+    }
+    if (lane == 0) n_entries[g] = U;
+}
+
+// candidate layout: region q = [cand_off[q], cand_off[q+1]) = cold docs first, then TILE_CAP tile slots
+__global__ void k_cold_cands(PrepView pv, const int32_t* __restrict__ q_off, const int32_t* __restrict__ hot_slot,
+                             const int64_t* __restrict__ row_ptr, const br_posting* __restrict__ post, int32_t nq,
+                             const int32_t* __restrict__ elig, const int64_t* __restrict__ cand_off,
+                             int32_t* __restrict__ cand) {
+    const int lane = threadIdx.x & 31;
+    const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (q >= nq || !elig[q]) return;
+    const int32_t off = q_off[q], nu = pv.u_cnt[q];
+    int64_t o = cand_off[q];
+    for (int j = 0; j < nu; ++j) {
+        const int32_t t = pv.u_terms[off + j];
+        if (hot_slot[t] >= 0) continue;
+        const int64_t lo = row_ptr[t], n = row_ptr[t + 1] - lo;
+        for (int64_t i = lane; i < n; i += 32) cand[o + i] = (int32_t)post[lo + i].doc;
+        o += n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the tile kernel
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sort_desc(float v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+            v = (lower == up) ? fmaxf(v, o) : fminf(v, o);
+        }
+    }
+    return v;   // lane i holds the i-th largest
+}
+
+struct TileArgs {
+    const br_posting* post;
+    const int64_t* row_ptr;
+    const uint32_t* skip;
+    int32_t n_sub;
+    int64_t n_docs;
+    const TileEntry* entries;
+    const int32_t* n_entries;
+    int umax;
+    int32_t nq;
+    const int32_t* elig;
+    float* thr;
+    int32_t* cand_cnt;
+    int32_t* cand;
+    const int64_t* cand_off;
+    const uint32_t* cold_cnt;
+    int K;
+    int tile0;
+};
+
+template <int G>
+__global__ void __launch_bounds__(TILE_W * 32) k_tile_score(TileArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* acc = reinterpret_cast<float*>(smem_raw);                                     // [G][W][S]
+    TileEntry* ent = reinterpret_cast<TileEntry*>(smem_raw + sizeof(float) * G * TILE_W * TILE_S);
+    int64_t* s_base = reinterpret_cast<int64_t*>(ent + a.umax);                          // [umax]
+    uint32_t* s_bnd = reinterpret_cast<uint32_t*>(s_base + a.umax);                      // [umax][W+1]
+
+    const int g = blockIdx.x, tile = a.tile0 + blockIdx.y;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int U = a.n_entries[g];
+    const int sub0 = tile * TILE_W;
+
+    for (int u = threadIdx.x; u < U; u += TILE_W * 32) {
+        const TileEntry e = a.entries[(int64_t)g * a.umax + u];
+        ent[u] = e;
+        s_base[u] = a.row_ptr[e.term];
+    }
+    for (int i = threadIdx.x; i < U * (TILE_W + 1); i += TILE_W * 32) {
+        const int u = i / (TILE_W + 1), j = i - u * (TILE_W + 1);
+        const int32_t slot = a.entries[(int64_t)g * a.umax + u].slot;
+        const int sub = min(sub0 + j, a.n_sub);
+        s_bnd[i] = a.skip[(int64_t)slot * (a.n_sub + 1) + sub];
+    }
+    {   // each warp zeroes its own accumulator rows
+        float4* z = reinterpret_cast<float4*>(acc);
+#pragma unroll
+        for (int q = 0; q < G; ++q)
+            for (int i = lane; i < TILE_S / 4; i += 32) z[((q * TILE_W + w) * TILE_S) / 4 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const int sub = sub0 + w;
+    if (sub >= a.n_sub) return;
+    const uint32_t doc0 = (uint32_t)sub << TILE_SHIFT;
+    float* my = acc + w * TILE_S;                       // + q * TILE_W * TILE_S per query
+
+    for (int u = 0; u < U; ++u) {
+        const uint32_t lo = s_bnd[u * (TILE_W + 1) + w], hi = s_bnd[u * (TILE_W + 1) + w + 1];
+        if (lo >= hi) continue;
+        const TileEntry e = ent[u];
+        float fm[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) fm[q] = (float)e.mult[q];
+        const uint2* p = reinterpret_cast<const uint2*>(a.post) + s_base[u];
+        for (uint32_t i = lo + lane; i < hi; i += 128) {
+            uint2 v[4];
+            bool ok[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                ok[x] = i + 32 * x < hi;
+                if (ok[x]) v[x] = __ldg(p + i + 32 * x);
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                if (ok[x]) {
+                    const uint32_t l = v[x].x - doc0;
+                    const float wt = __uint_as_float(v[x].y);
+#pragma unroll
+                    for (int q = 0; q < G; ++q)
+                        if (fm[q] != 0.f) my[q * TILE_W * TILE_S + l] = fmaf(wt, fm[q], my[q * TILE_W * TILE_S + l]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // epilogue: threshold filter per query of the group
+    const uint32_t n_valid = (uint32_t)min((int64_t)TILE_S, a.n_docs - (int64_t)doc0);
+#pragma unroll 1
+    for (int q = 0; q < G; ++q) {
+        const int qi = g * G + q;
+        if (qi >= a.nq || !a.elig[qi]) continue;
+        float v[TILE_S / 32];
+        float mx = 0.f;
+#pragma unroll
+        for (int j = 0; j < TILE_S / 32; ++j) {
+            v[j] = my[q * TILE_W * TILE_S + j * 32 + lane];
+            if ((uint32_t)(j * 32 + lane) >= n_valid) v[j] = 0.f;
+            mx = fmaxf(mx, v[j]);
+        }
+        float th = __ldcg(a.thr + qi);
+        float lo_thr = th * (1.f - kBandRel);
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < TILE_S / 32; ++j) c += (v[j] >= lo_thr && v[j] > 0.f) ? 1 : 0;
+        int tot = c;
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (tot == 0) continue;
+        if (tot >= a.K) {
+            // K distinct docs (one per lane) score >= the K-th largest lane maximum: a valid lower
+            // bound of the K-th best score of this query over the whole shard
+            const float srt = warp_sort_desc(mx, lane);
+            const float kth = __shfl_sync(0xffffffffu, srt, a.K - 1);
+            if (kth > th) {
+                th = kth;
+                if (lane == 0) atomicMax(reinterpret_cast<int*>(a.thr + qi), __float_as_int(kth));   // scores >= 0
+                lo_thr = th * (1.f - kBandRel);
+                c = 0;
+#pragma unroll
+                for (int j = 0; j < TILE_S / 32; ++j) c += (v[j] >= lo_thr && v[j] > 0.f) ? 1 : 0;
+            }
+        }
+        // warp-exclusive offsets, one global atomic per (query, sub-range)
+        int incl = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.cand_cnt + qi, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        int pos = base + incl - c;
+        int32_t* out = a.cand + a.cand_off[qi] + a.cold_cnt[qi];
+#pragma unroll
+        for (int j = 0; j < TILE_S / 32; ++j) {
+            if (v[j] >= lo_thr && v[j] > 0.f) {
+                if (pos < TILE_CAP) out[pos] = (int32_t)(doc0 + j * 32 + lane);
+                ++pos;
+            }
+        }
+    }
+}
+
+__global__ void k_fused_flags(const int32_t* __restrict__ elig, const int32_t* __restrict__ cand_cnt,
+                              const int32_t* __restrict__ out_cnt, int32_t nq, int32_t need, int positive_only,
+                              int32_t* __restrict__ flags) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    flags[q] = (!elig[q] || cand_cnt[q] > TILE_CAP || (!positive_only && out_cnt[q] < need)) ? 1 : 0;
+}
+
+template <int G>
+static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t smem, cudaStream_t st, br_index* ix) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        BR_CUDA(cudaFuncSetAttribute(k_tile_score<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    // seed launch over the first tiles so that thresholds exist before the bulk of the shard
+    const int n_seed = std::max(1, n_tiles / 64);
+    int t0 = 0;
+    const int parts[2] = {n_seed, n_tiles - n_seed};
+    for (int p = 0; p < 2; ++p) {
+        int left = parts[p];
+        while (left > 0) {
+            const int ny = std::min(left, 32768);
+            TileArgs a = a0;
+            a.tile0 = t0;
+            ix->prof_begin(st);
+            k_tile_score<G><<<dim3((unsigned)n_groups, (unsigned)ny), TILE_W * 32, smem, st>>>(a);
+            BR_CUDA(cudaGetLastError());
+            ix->prof_end(st);
+            ix->stats.kernel_launches += 1;
+            t0 += ny;
+            left -= ny;
+        }
+    }
+    return BR_OK;
+}
+
+bool fused_supported(const br_index* ix, int32_t k) {
+    static const bool disabled = getenv("BR_DISABLE_FUSED") != nullptr;
+    return !disabled && ix->allow_fused && k <= 32 && ix->variant != BR_OKAPI_NO_PLUS1 && ix->n_hot > 0 && ix->sub_shift == TILE_SHIFT &&
+           ix->skip != nullptr;
+}
+
+// Fused path over the whole prepared batch.  h_flags[q] != 0 afterwards -> query q must be served by
+// the dense path (not eligible, candidate overflow, or fewer than k docs with a positive score).
+int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t nq, int32_t k, int dedup,
+               int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st,
+               std::vector<int32_t>* h_flags) {
+    int G = nq >= 4 * kNumSMs ? 4 : (nq >= 2 * kNumSMs ? 2 : 1);
+    if (const char* e = getenv("BR_TILE_G")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) G = v; }
+    if (ix->tile_g) G = ix->tile_g;
+    const int n_groups = (nq + G - 1) / G, umax = G * TILE_QT;
+    const int n_tiles = (ix->n_sub + TILE_W - 1) / TILE_W;
+    size_t bytes = 0;
+    auto carve = [&](size_t n) { size_t o = bytes; bytes += (n + 255) & ~(size_t)255; return o; };
+    const size_t Q = (size_t)nq + 2;
+    const size_t o_ent = carve(sizeof(TileEntry) * (size_t)n_groups * umax), o_ne = carve(4 * (size_t)n_groups),
+                 o_el = carve(4 * Q), o_cc = carve(4 * Q), o_rg = carve(4 * Q), o_thr = carve(4 * Q), o_cnt = carve(4 * Q),
+                 o_off = carve(8 * Q), o_fl = carve(4 * Q), o_oc = carve(4 * Q);
+    BR_TRY(ix->ws_tile.reserve(bytes));
+    char* p = ix->ws_tile.as<char>();
+    TileEntry* entries = (TileEntry*)(p + o_ent);
+    int32_t* n_entries = (int32_t*)(p + o_ne);
+    int32_t* elig = (int32_t*)(p + o_el);
+    uint32_t* cold_cnt = (uint32_t*)(p + o_cc);
+    uint32_t* region = (uint32_t*)(p + o_rg);
+    float* thr = (float*)(p + o_thr);
+    int32_t* cand_cnt = (int32_t*)(p + o_cnt);
+    int64_t* cand_off = (int64_t*)(p + o_off);
+    int32_t* flags = (int32_t*)(p + o_fl);
+    int32_t* cnt_tmp = out_counts ? out_counts : (int32_t*)(p + o_oc);
+
+    k_tile_prep<<<(n_groups + 3) / 4, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, nq, G, umax, entries, n_entries,
+                                                    elig, cold_cnt, region);
+    BR_CUDA(cudaGetLastError());
+    k_exscan<uint32_t><<<1, 1024, 0, st>>>(region, nq, cand_off);
+    BR_CUDA(cudaGetLastError());
+    int64_t total = 0;
+    BR_CUDA(cudaMemcpyAsync(&total, cand_off + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaMemsetAsync(thr, 0, 4 * Q, st));
+    BR_CUDA(cudaMemsetAsync(cand_cnt, 0, 4 * Q, st));
+    BR_CUDA(cudaStreamSynchronize(st));
+    const size_t id_bytes = ((size_t)(total + 1) * sizeof(int32_t) + 255) & ~(size_t)255;
+    BR_TRY(ix->ws_cand.reserve(id_bytes + (size_t)(total + 1) * sizeof(double)));
+    int32_t* cand = ix->ws_cand.as<int32_t>();
+    double* cand_sc = (double*)(ix->ws_cand.as<char>() + id_bytes);
+    BR_CUDA(cudaMemsetAsync(cand, 0xFF, (size_t)(total + 1) * sizeof(int32_t), st));
+    k_cold_cands<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, ix->post, nq, elig,
+                                                                    cand_off, cand);
+    BR_CUDA(cudaGetLastError());
+    ix->stats.kernel_launches += 3;
+
+    TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, elig, thr, cand_cnt,
+               cand, cand_off, cold_cnt, (int)k, 0};
+    const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
+                                                                            sizeof(uint32_t) * (TILE_W + 1));
+    switch (G) {
+        case 1: BR_TRY(launch_tiles<1>(a, n_groups, n_tiles, smem, st, ix)); break;
+        case 2: BR_TRY(launch_tiles<2>(a, n_groups, n_tiles, smem, st, ix)); break;
+        case 4: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix)); break;
+        default: BR_TRY(launch_tiles<8>(a, n_groups, n_tiles, smem, st, ix)); break;
+    }
+    if (total > 0) {
+        BR_TRY(launch_rescore(ix, q_off, pv, dedup, cand_off, 0, nq, cand, cand_sc, total, st));
+    }
+    BR_TRY(launch_final_select(cand, cand_sc, cand_off, 0, nq, k, positive_only, out_ids, out_scores, cnt_tmp, st));
+    const int32_t need = (int32_t)std::min<int64_t>(k, ix->n_docs);
+    k_fused_flags<<<blocks_for(nq, 256), 256, 0, st>>>(elig, cand_cnt, cnt_tmp, nq, need, positive_only, flags);
+    BR_CUDA(cudaGetLastError());
+    ix->stats.kernel_launches += 3;
+    ix->stats.candidates_rescored += total;
+    h_flags->resize((size_t)nq);
+    BR_CUDA(cudaMemcpyAsync(h_flags->data(), flags, 4 * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaStreamSynchronize(st));
+    return BR_OK;
+}
+
+}  // namespace br

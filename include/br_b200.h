@@ -148,6 +148,9 @@ int br_last_query_stats(const br_index* ix, br_query_stats* out);
 /* Bracket every launch of the scoring kernel with CUDA events on the call's stream (bench.py's
  * live roofline measurement).  Off by default. */
 int br_set_profiling(br_index* ix, int on);
+/* Tuning / test switches.  name = "fused" (0 forces the dense path for every query; default 1),
+ * "tile_g" (queries per group of the tiled kernel: 0 auto, 1, 2, 4 or 8). */
+int br_set_option(br_index* ix, const char* name, int value);
 
 #ifdef __cplusplus
 }

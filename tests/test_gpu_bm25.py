@@ -213,3 +213,42 @@ def test_recall_and_routing(golden):
     some = [r["query"] for r in rows if r["lang"] == any_lang][:3]
     out = retrieve_top_n_batch((models[any_lang], some, 10))
     assert [o.tolist() for o in out] == [orc.retrieve_top_n(oracles[any_lang], q, 10)[0].tolist() for q in some]
+
+
+@pytest.mark.parametrize("g", [0, 1, 2, 4, 8])
+def test_fused_path_equals_dense_path(g):
+    """The tiled smem-accumulator path and the dense path must return identical ids / scores."""
+    c = synth.make_config("C1")
+    from document_retrieval_b200 import BM25
+    m = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"])
+    q = (c["q_terms"], c["q_offsets"])
+    m.set_option("fused", 0)
+    ids_d, sc_d = m.retrieve_top_n_batch(q, 10)
+    assert m.query_stats()["queries_fused"] == 0
+    m.set_option("fused", 1)
+    m.set_option("tile_g", g)
+    ids_f, sc_f = m.retrieve_top_n_batch(q, 10)
+    st = m.query_stats()
+    assert st["queries_fused"] > 0.9 * c["q_offsets"].size
+    assert torch.equal(ids_d, ids_f) and torch.equal(sc_d, sc_f)
+    # okapi / duplicates counted / only docs with a hit
+    m2 = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"], variant="okapi", dedup_query=False)
+    m2.set_option("tile_g", g)
+    a = m2.retrieve_top_n_batch(q, 10, positive_only=True, return_counts=True)
+    m2.set_option("fused", 0)
+    b = m2.retrieve_top_n_batch(q, 10, positive_only=True, return_counts=True)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_fused_path_single_query_and_small_batches():
+    c = synth.make_config("C1", scale=0.3)
+    from document_retrieval_b200 import BM25
+    m = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"])
+    co = COracle(c["doc_offsets"], c["token_ids"], c["vocab"])
+    oi, os_, _ = co.topk_batch(c["q_terms"], c["q_offsets"], 10)
+    for i in (0, 1, 17):
+        q = c["q_terms"][c["q_offsets"][i]:c["q_offsets"][i + 1]]
+        assert np.array_equal(m.retrieve_top_n(q, 10), oi[i])
+    for nq in (2, 3, 5):
+        ids, sc = m.retrieve_top_n_batch((c["q_terms"][:c["q_offsets"][nq]], c["q_offsets"][:nq + 1]), 10)
+        assert np.array_equal(ids.cpu().numpy(), oi[:nq]) and np.array_equal(sc.cpu().numpy(), os_[:nq])
