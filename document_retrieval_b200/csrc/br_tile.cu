@@ -2,23 +2,28 @@
 // accumulators in shared memory and the top-k selection fused into the tile epilogue.
 //
 // Why: a dense [Q, N] fp32 accumulator costs 8 B x N of HBM traffic per query (zero + read back) and
-// global atomics for every posting; at N = 8.8M that is more than the postings themselves
-// (hard part 2).  Here a CTA owns (a tile of W x 512 consecutive docs) x (a group of G
-// queries); each of its W warps owns one 512-doc sub-range and walks, for every term of the
-// group's union term list, the slice of that term's posting list that falls in its sub-range (slice
-// bounds come from the per-term skip table built with the index) and adds the packed fp32 weights
-// into its private [G, 512] accumulator rows: plain LDS/FADD/STS, no atomics, no block barrier after
-// the prologue, deterministic order.  A posting loaded once serves every query of the group that
-// contains the term, and the CTAs of all groups visit a tile back to back (blockIdx.x = group), so the
-// tile's posting slices are read from HBM once per batch and from L2 afterwards.
-// Epilogue: per query a running global threshold thr[q] (a lower bound of the k-th best fp32 score,
-// raised with atomicMax from any sub-range that holds k better docs); a doc is emitted as a candidate
-// iff its fp32 score >= thr*(1-1e-5).  Candidates are re-scored exactly in float64 (k_rescore) and
-// ranked by (score desc, id asc) (k_final_select) - see br_query.cu for the exactness argument.
-// Terms too rare for a skip table ("cold", df < hot_min) never enter the tile kernel: every doc on a
-// cold list of a query is made a candidate of that query instead (k_cold_cands) and gets its full
-// score from the float64 re-score; a doc that is on no cold list has fp32 tile score == its full
-// score, so the candidate set still contains the true top-k.
+// a global atomic per posting; at N = 8.8M that is more than the postings themselves (hard
+// part 2).  Here a CTA owns (a tile of W x 512 consecutive docs) x (a group of G queries); each of
+// its W warps owns one 512-doc sub-range and walks, for every term of the group's union term list,
+// the slice of that term's posting list that falls in its sub-range (slice bounds come from the
+// per-term skip table built with the index) and adds the packed fp32 weights into its private
+// [G, 512] accumulator rows: plain LDS/FFMA/STS, no atomics, no block barrier after the prologue,
+// deterministic order.  A posting loaded once serves every query of the group that contains the term,
+// and the CTAs of all groups visit a tile back to back (blockIdx.x = group), so the tile's posting
+// slices come from HBM once per batch and from L2 afterwards.
+//
+// Terms too rare for a skip table ("cold": df < hot_min) are bucketed per batch instead: a counting
+// sort of their postings by (tile, group) (k_cold_count / scan / k_cold_scatter); the CTA of a bucket
+// adds those few entries with shared-memory atomics before its epilogue.  So the tile accumulators
+// hold the complete fp32 score of every doc.
+//
+// Epilogue + selection: thr[q] is a lower bound of the k-th best fp32 score of query q over the shard.
+// A doc is emitted as a candidate iff score >= thr*(1-1e-5) (the band that makes the float64 re-score
+// exact, see br_query.cu).  thr rises two ways: inside the kernel, when a sub-range holds k better docs
+// in k different lanes (atomicMax); and between launches - tiles are processed in chunks of doubling
+// size, and after each chunk k_tighten sets thr[q] to the k-th best score among the candidates emitted
+// so far and compacts the list.  With doubling chunks every chunk emits about k new candidates per
+// query, so the candidate list stays ~k long and the float64 re-score costs almost nothing.
 #include <math_constants.h>
 
 #include "br_common.cuh"
@@ -30,13 +35,21 @@ namespace br {
 constexpr int TILE_W = 8;            // warps per CTA = sub-ranges per tile
 constexpr int TILE_SHIFT = 9;        // 512 docs per sub-range (must equal br_index::sub_shift)
 constexpr int TILE_S = 1 << TILE_SHIFT;
+constexpr int TILE_DOCS_SHIFT = TILE_SHIFT + 3;   // log2(W * S)
 constexpr int TILE_QT = 32;          // max distinct hot terms of one query on this path
-constexpr int TILE_CAP = 2048;       // tile-emitted candidates kept per query
+constexpr int TILE_CAP = 1024;       // candidates kept per query between tighten rounds
+static_assert((1 << 3) == TILE_W, "TILE_DOCS_SHIFT assumes W == 8");
 
 struct __align__(16) TileEntry {
     int32_t term;
     int32_t slot;
     uint8_t mult[8];
+};
+
+// cold entry: doc offset inside the tile (12 bits) | query slot in the group (3 bits) << 12, weight
+struct __align__(8) ColdEntry {
+    uint32_t key;
+    float w;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -46,8 +59,7 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
                                                    const int32_t* __restrict__ hot_slot,
                                                    const int64_t* __restrict__ row_ptr, int32_t nq, int G, int umax,
                                                    TileEntry* __restrict__ entries, int32_t* __restrict__ n_entries,
-                                                   int32_t* __restrict__ elig, uint32_t* __restrict__ cold_cnt,
-                                                   uint32_t* __restrict__ region) {
+                                                   int32_t* __restrict__ elig, unsigned long long* __restrict__ cold_total) {
     __shared__ int32_t s_term[4][256];
     __shared__ uint8_t s_q[4][256], s_m[4][256];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
@@ -55,6 +67,7 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
     const int n_groups = (nq + G - 1) / G;
     if (g >= n_groups) return;
     int n = 0;
+    unsigned long long cold_sum = 0;
     for (int i = 0; i < G; ++i) {
         const int q = g * G + i;
         if (q >= nq) break;
@@ -66,18 +79,15 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
             const int32_t t = j < nu ? pv.u_terms[off + j] : -1;
             const bool is_hot = t >= 0 && hot_slot[t] >= 0;
             if (t >= 0 && !is_hot) cold += (unsigned long long)(row_ptr[t + 1] - row_ptr[t]);
-            if (is_hot && pv.u_mult[off + j] > 255) bad = 1;
+            if (t >= 0 && pv.u_mult[off + j] > 255) bad = 1;
             hot += __popc(__ballot_sync(0xffffffffu, is_hot));
         }
         for (int o = 16; o > 0; o >>= 1) cold += __shfl_xor_sync(0xffffffffu, cold, o);
         bad = __any_sync(0xffffffffu, bad);
-        const bool ok = hot <= TILE_QT && !bad && cold < (1ull << 24);
-        if (lane == 0) {
-            elig[q] = ok ? 1 : 0;
-            cold_cnt[q] = ok ? (uint32_t)cold : 0u;
-            region[q] = ok ? (uint32_t)cold + TILE_CAP : 0u;
-        }
+        const bool ok = hot <= TILE_QT && !bad;
+        if (lane == 0) elig[q] = ok ? 1 : 0;
         if (!ok) continue;
+        cold_sum += cold;
         for (int base = 0; base < nu; base += 32) {
             const int j = base + lane;
             const int32_t t = j < nu ? pv.u_terms[off + j] : -1;
@@ -115,26 +125,70 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
         }
         U += __popc(m);
     }
-    if (lane == 0) n_entries[g] = U;
+    if (lane == 0) {
+        n_entries[g] = U;
+        if (cold_sum) atomicAdd(cold_total, cold_sum);
+    }
 }
 
-// candidate layout: region q = [cand_off[q], cand_off[q+1]) = cold docs first, then TILE_CAP tile slots
-__global__ void k_cold_cands(PrepView pv, const int32_t* __restrict__ q_off, const int32_t* __restrict__ hot_slot,
-                             const int64_t* __restrict__ row_ptr, const br_posting* __restrict__ post, int32_t nq,
-                             const int32_t* __restrict__ elig, const int64_t* __restrict__ cand_off,
-                             int32_t* __restrict__ cand) {
+// ------------------------------------------------------------------------------------------
+// cold postings -> (tile, group) buckets: counting sort
+// ------------------------------------------------------------------------------------------
+template <bool SCATTER>
+__global__ void k_cold_pass(PrepView pv, const int32_t* __restrict__ q_off, const int32_t* __restrict__ hot_slot,
+                            const int64_t* __restrict__ row_ptr, const br_posting* __restrict__ post, int32_t nq, int G,
+                            int n_groups, const int32_t* __restrict__ elig, uint32_t* __restrict__ counter,
+                            ColdEntry* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (q >= nq || !elig[q]) return;
     const int32_t off = q_off[q], nu = pv.u_cnt[q];
-    int64_t o = cand_off[q];
+    const int g = q / G;
+    const uint32_t slot = (uint32_t)(q - g * G);
     for (int j = 0; j < nu; ++j) {
         const int32_t t = pv.u_terms[off + j];
         if (hot_slot[t] >= 0) continue;
+        const float mult = (float)pv.u_mult[off + j];
         const int64_t lo = row_ptr[t], n = row_ptr[t + 1] - lo;
-        for (int64_t i = lane; i < n; i += 32) cand[o + i] = (int32_t)post[lo + i].doc;
-        o += n;
+        for (int64_t i = lane; i < n; i += 32) {
+            const br_posting p = post[lo + i];
+            const uint32_t tile = p.doc >> TILE_DOCS_SHIFT;
+            const int64_t b = (int64_t)tile * n_groups + g;
+            const uint32_t pos = atomicAdd(counter + b, 1u);
+            if (SCATTER) out[pos] = ColdEntry{(p.doc & ((1u << TILE_DOCS_SHIFT) - 1)) | (slot << TILE_DOCS_SHIFT), p.w * mult};
+        }
     }
+}
+
+// three-kernel exclusive scan of uint32 counts (n up to ~2^31): out[i] = sum_{j<i} in[j], out[n] = total
+constexpr int SCAN_T = 256, SCAN_I = 16, SCAN_TILE = SCAN_T * SCAN_I;
+__global__ void __launch_bounds__(SCAN_T) k_scan_reduce(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ part) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_I; ++j) {
+        const int64_t i = base + j * SCAN_T + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    uint32_t total;
+    block_excl_scan(s, &total);
+    if (threadIdx.x == 0) part[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_apply(const uint32_t* __restrict__ in, int64_t n,
+                                                       const int64_t* __restrict__ part_off, uint32_t* __restrict__ out,
+                                                       uint32_t* __restrict__ out_copy) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_I;
+    uint32_t v[SCAN_I], s = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_I; ++j) { v[j] = base + j < n ? in[base + j] : 0u; s += v[j]; }
+    uint32_t total;
+    uint32_t run = block_excl_scan(s, &total) + (uint32_t)part_off[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < SCAN_I; ++j) {
+        if (base + j < n) { out[base + j] = run; out_copy[base + j] = run; }
+        run += v[j];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_T - 1) { out[n] = run; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -163,12 +217,14 @@ struct TileArgs {
     const int32_t* n_entries;
     int umax;
     int32_t nq;
+    int n_groups;
     const int32_t* elig;
+    const uint32_t* cold_off;     // [n_tiles * n_groups + 1] or null
+    const ColdEntry* cold;
     float* thr;
     int32_t* cand_cnt;
-    int32_t* cand;
-    const int64_t* cand_off;
-    const uint32_t* cold_cnt;
+    int32_t* cand;                // [nq, TILE_CAP]
+    float* cand_h;                // [nq, TILE_CAP]
     int K;
     int tile0;
 };
@@ -238,6 +294,17 @@ __global__ void __launch_bounds__(TILE_W * 32) k_tile_score(TileArgs a) {
         }
         __syncwarp();
     }
+    // cold postings of this (tile, group) bucket that fall in this warp's sub-range
+    if (a.cold_off) {
+        const int64_t b = (int64_t)tile * a.n_groups + g;
+        const uint32_t c0 = a.cold_off[b], c1 = a.cold_off[b + 1];
+        for (uint32_t i = c0 + lane; i < c1; i += 32) {
+            const ColdEntry ce = a.cold[i];
+            const uint32_t l = ce.key & ((1u << TILE_DOCS_SHIFT) - 1), q = ce.key >> TILE_DOCS_SHIFT;
+            if ((l >> TILE_SHIFT) == (uint32_t)w) atomicAdd(acc + (q * TILE_W + w) * TILE_S + (l & (TILE_S - 1)), ce.w);
+        }
+        __syncwarp();
+    }
 
     // epilogue: threshold filter per query of the group
     const uint32_t n_valid = (uint32_t)min((int64_t)TILE_S, a.n_docs - (int64_t)doc0);
@@ -282,62 +349,125 @@ __global__ void __launch_bounds__(TILE_W * 32) k_tile_score(TileArgs a) {
             if (lane >= o) incl += n;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
         int base = 0;
         if (lane == 0) base = atomicAdd(a.cand_cnt + qi, total);
         base = __shfl_sync(0xffffffffu, base, 0);
         int pos = base + incl - c;
-        int32_t* out = a.cand + a.cand_off[qi] + a.cold_cnt[qi];
+        int32_t* out = a.cand + (int64_t)qi * TILE_CAP;
+        float* out_h = a.cand_h + (int64_t)qi * TILE_CAP;
 #pragma unroll
         for (int j = 0; j < TILE_S / 32; ++j) {
             if (v[j] >= lo_thr && v[j] > 0.f) {
-                if (pos < TILE_CAP) out[pos] = (int32_t)(doc0 + j * 32 + lane);
+                if (pos < TILE_CAP) { out[pos] = (int32_t)(doc0 + j * 32 + lane); out_h[pos] = v[j]; }
                 ++pos;
             }
         }
     }
 }
 
-__global__ void k_fused_flags(const int32_t* __restrict__ elig, const int32_t* __restrict__ cand_cnt,
+// Between chunks: thr[q] = max(thr[q], K-th best fp32 score emitted so far); keep only the candidates
+// inside the band of the new threshold (sorted by score); sticky overflow flag.
+constexpr int TG_T = 256;
+__global__ void __launch_bounds__(TG_T) k_tighten(float* __restrict__ thr, int32_t* __restrict__ cand_cnt,
+                                                  int32_t* __restrict__ prev_cnt, int32_t* __restrict__ cand,
+                                                  float* __restrict__ cand_h, int K, int32_t* __restrict__ overflow) {
+    __shared__ float s_h[TILE_CAP];
+    __shared__ int32_t s_id[TILE_CAP];
+    __shared__ int s_keep;
+    const int q = blockIdx.x;
+    int n = cand_cnt[q];
+    if (n == prev_cnt[q]) return;                      // nothing emitted since the last round
+    if (n > TILE_CAP) {
+        if (threadIdx.x == 0) overflow[q] = 1;
+        n = TILE_CAP;
+    }
+    int32_t* ids = cand + (int64_t)q * TILE_CAP;
+    float* hs = cand_h + (int64_t)q * TILE_CAP;
+    for (int i = threadIdx.x; i < TILE_CAP; i += TG_T) {
+        s_h[i] = i < n ? hs[i] : -1.f;
+        s_id[i] = i < n ? ids[i] : -1;
+    }
+    if (threadIdx.x == 0) s_keep = 0;
+    for (int size = 2; size <= TILE_CAP; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < TILE_CAP / 2; i += TG_T) {
+                const int x = 2 * i - (i & (stride - 1)), y = x + stride;
+                const bool up = (x & size) == 0;
+                const float hx = s_h[x], hy = s_h[y];
+                if ((hy > hx) == up) {
+                    s_h[x] = hy; s_h[y] = hx;
+                    const int32_t t = s_id[x]; s_id[x] = s_id[y]; s_id[y] = t;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float th = thr[q];
+    if (n >= K && s_h[K - 1] > th) th = s_h[K - 1];
+    const float lo = th * (1.f - kBandRel);
+    int keep = 0;
+    for (int i = threadIdx.x; i < n; i += TG_T) keep += (s_h[i] >= lo) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    if ((threadIdx.x & 31) == 0 && keep) atomicAdd(&s_keep, keep);
+    __syncthreads();
+    keep = s_keep;
+    for (int i = threadIdx.x; i < n; i += TG_T) {
+        ids[i] = i < keep ? s_id[i] : -1;
+        hs[i] = i < keep ? s_h[i] : 0.f;
+    }
+    if (threadIdx.x == 0) {
+        thr[q] = th;
+        cand_cnt[q] = keep;
+        prev_cnt[q] = keep;
+    }
+}
+
+__global__ void k_fused_flags(const int32_t* __restrict__ elig, const int32_t* __restrict__ overflow,
                               const int32_t* __restrict__ out_cnt, int32_t nq, int32_t need, int positive_only,
                               int32_t* __restrict__ flags) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
-    flags[q] = (!elig[q] || cand_cnt[q] > TILE_CAP || (!positive_only && out_cnt[q] < need)) ? 1 : 0;
+    flags[q] = (!elig[q] || overflow[q] || (!positive_only && out_cnt[q] < need)) ? 1 : 0;
+}
+
+__global__ void k_fill_offsets(int64_t* __restrict__ off, int32_t nq, int64_t stride) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q <= nq) off[q] = (int64_t)q * stride;
 }
 
 template <int G>
-static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t smem, cudaStream_t st, br_index* ix) {
+static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t smem, cudaStream_t st, br_index* ix,
+                        int32_t* prev_cnt, int32_t* overflow) {
     static bool attr_set = false;
     if (!attr_set) {
         BR_CUDA(cudaFuncSetAttribute(k_tile_score<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    // seed launch over the first tiles so that thresholds exist before the bulk of the shard
-    const int n_seed = std::max(1, n_tiles / 64);
-    int t0 = 0;
-    const int parts[2] = {n_seed, n_tiles - n_seed};
-    for (int p = 0; p < 2; ++p) {
-        int left = parts[p];
-        while (left > 0) {
-            const int ny = std::min(left, 32768);
-            TileArgs a = a0;
-            a.tile0 = t0;
-            ix->prof_begin(st);
-            k_tile_score<G><<<dim3((unsigned)n_groups, (unsigned)ny), TILE_W * 32, smem, st>>>(a);
-            BR_CUDA(cudaGetLastError());
-            ix->prof_end(st);
-            ix->stats.kernel_launches += 1;
-            t0 += ny;
-            left -= ny;
-        }
+    // chunks of doubling size: thresholds learnt on the first 2^c tiles filter the next 2^c
+    int t0 = 0, chunk = 1;
+    while (t0 < n_tiles) {
+        const int ny = std::min(std::min(chunk, n_tiles - t0), 32768);
+        TileArgs a = a0;
+        a.tile0 = t0;
+        ix->prof_begin(st);
+        k_tile_score<G><<<dim3((unsigned)n_groups, (unsigned)ny), TILE_W * 32, smem, st>>>(a);
+        BR_CUDA(cudaGetLastError());
+        ix->prof_end(st);
+        k_tighten<<<a0.nq, TG_T, 0, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, overflow);
+        BR_CUDA(cudaGetLastError());
+        ix->stats.kernel_launches += 2;
+        t0 += ny;
+        chunk *= 2;
     }
     return BR_OK;
 }
 
 bool fused_supported(const br_index* ix, int32_t k) {
     static const bool disabled = getenv("BR_DISABLE_FUSED") != nullptr;
-    return !disabled && ix->allow_fused && k <= 32 && ix->variant != BR_OKAPI_NO_PLUS1 && ix->n_hot > 0 && ix->sub_shift == TILE_SHIFT &&
-           ix->skip != nullptr;
+    return !disabled && ix->allow_fused && k <= 32 && ix->variant != BR_OKAPI_NO_PLUS1 && ix->n_hot > 0 &&
+           ix->sub_shift == TILE_SHIFT && ix->skip != nullptr;
 }
 
 // Fused path over the whole prepared batch.  h_flags[q] != 0 afterwards -> query q must be served by
@@ -350,64 +480,97 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     if (ix->tile_g) G = ix->tile_g;
     const int n_groups = (nq + G - 1) / G, umax = G * TILE_QT;
     const int n_tiles = (ix->n_sub + TILE_W - 1) / TILE_W;
+    const int64_t n_buckets = (int64_t)n_tiles * n_groups;
+    const int64_t n_scan_blocks = (n_buckets + SCAN_TILE - 1) / SCAN_TILE;
     size_t bytes = 0;
     auto carve = [&](size_t n) { size_t o = bytes; bytes += (n + 255) & ~(size_t)255; return o; };
     const size_t Q = (size_t)nq + 2;
     const size_t o_ent = carve(sizeof(TileEntry) * (size_t)n_groups * umax), o_ne = carve(4 * (size_t)n_groups),
-                 o_el = carve(4 * Q), o_cc = carve(4 * Q), o_rg = carve(4 * Q), o_thr = carve(4 * Q), o_cnt = carve(4 * Q),
-                 o_off = carve(8 * Q), o_fl = carve(4 * Q), o_oc = carve(4 * Q);
+                 o_el = carve(4 * Q), o_thr = carve(4 * Q), o_cnt = carve(4 * Q), o_prev = carve(4 * Q), o_ovf = carve(4 * Q),
+                 o_off = carve(8 * Q), o_fl = carve(4 * Q), o_oc = carve(4 * Q), o_ct = carve(16),
+                 o_bc = carve(4 * (size_t)(n_buckets + 1)), o_bo = carve(4 * (size_t)(n_buckets + 1)),
+                 o_cur = carve(4 * (size_t)(n_buckets + 1)), o_part = carve(4 * (size_t)(n_scan_blocks + 1)),
+                 o_poff = carve(8 * (size_t)(n_scan_blocks + 2)),
+                 o_cand = carve(4 * (size_t)nq * TILE_CAP), o_ch = carve(4 * (size_t)nq * TILE_CAP),
+                 o_cs = carve(8 * (size_t)nq * TILE_CAP);
     BR_TRY(ix->ws_tile.reserve(bytes));
     char* p = ix->ws_tile.as<char>();
     TileEntry* entries = (TileEntry*)(p + o_ent);
     int32_t* n_entries = (int32_t*)(p + o_ne);
     int32_t* elig = (int32_t*)(p + o_el);
-    uint32_t* cold_cnt = (uint32_t*)(p + o_cc);
-    uint32_t* region = (uint32_t*)(p + o_rg);
     float* thr = (float*)(p + o_thr);
     int32_t* cand_cnt = (int32_t*)(p + o_cnt);
+    int32_t* prev_cnt = (int32_t*)(p + o_prev);
+    int32_t* overflow = (int32_t*)(p + o_ovf);
     int64_t* cand_off = (int64_t*)(p + o_off);
     int32_t* flags = (int32_t*)(p + o_fl);
     int32_t* cnt_tmp = out_counts ? out_counts : (int32_t*)(p + o_oc);
+    unsigned long long* cold_total = (unsigned long long*)(p + o_ct);
+    uint32_t* b_cnt = (uint32_t*)(p + o_bc);
+    uint32_t* b_off = (uint32_t*)(p + o_bo);
+    uint32_t* b_cur = (uint32_t*)(p + o_cur);
+    uint32_t* part = (uint32_t*)(p + o_part);
+    int64_t* part_off = (int64_t*)(p + o_poff);
+    int32_t* cand = (int32_t*)(p + o_cand);
+    float* cand_h = (float*)(p + o_ch);
+    double* cand_sc = (double*)(p + o_cs);
 
+    // one memset covers thr / cand_cnt / prev_cnt / overflow (contiguous carve)
+    BR_CUDA(cudaMemsetAsync(p + o_thr, 0, o_off - o_thr, st));
+    BR_CUDA(cudaMemsetAsync(cold_total, 0, 16, st));
+    BR_CUDA(cudaMemsetAsync(cand, 0xFF, 4 * (size_t)nq * TILE_CAP, st));
     k_tile_prep<<<(n_groups + 3) / 4, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, nq, G, umax, entries, n_entries,
-                                                    elig, cold_cnt, region);
+                                                    elig, cold_total);
     BR_CUDA(cudaGetLastError());
-    k_exscan<uint32_t><<<1, 1024, 0, st>>>(region, nq, cand_off);
+    k_fill_offsets<<<blocks_for(nq + 1, 256), 256, 0, st>>>(cand_off, nq, TILE_CAP);
     BR_CUDA(cudaGetLastError());
-    int64_t total = 0;
-    BR_CUDA(cudaMemcpyAsync(&total, cand_off + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    BR_CUDA(cudaMemsetAsync(thr, 0, 4 * Q, st));
-    BR_CUDA(cudaMemsetAsync(cand_cnt, 0, 4 * Q, st));
+    unsigned long long h_cold = 0;
+    BR_CUDA(cudaMemcpyAsync(&h_cold, cold_total, sizeof(h_cold), cudaMemcpyDeviceToHost, st));
     BR_CUDA(cudaStreamSynchronize(st));
-    const size_t id_bytes = ((size_t)(total + 1) * sizeof(int32_t) + 255) & ~(size_t)255;
-    BR_TRY(ix->ws_cand.reserve(id_bytes + (size_t)(total + 1) * sizeof(double)));
-    int32_t* cand = ix->ws_cand.as<int32_t>();
-    double* cand_sc = (double*)(ix->ws_cand.as<char>() + id_bytes);
-    BR_CUDA(cudaMemsetAsync(cand, 0xFF, (size_t)(total + 1) * sizeof(int32_t), st));
-    k_cold_cands<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, ix->post, nq, elig,
-                                                                    cand_off, cand);
-    BR_CUDA(cudaGetLastError());
-    ix->stats.kernel_launches += 3;
+    ix->stats.kernel_launches += 2;
+    BR_REQUIRE(h_cold < (1ull << 32), BR_ERR_UNSUPPORTED, "br_topk_batch: more than 2^32 cold postings in one batch");
 
-    TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, elig, thr, cand_cnt,
-               cand, cand_off, cold_cnt, (int)k, 0};
+    const ColdEntry* cold = nullptr;
+    const uint32_t* cold_off = nullptr;
+    if (h_cold > 0) {
+        BR_TRY(ix->ws_misc.reserve(sizeof(ColdEntry) * (size_t)h_cold + 256));
+        ColdEntry* d_cold = ix->ws_misc.as<ColdEntry>();
+        BR_CUDA(cudaMemsetAsync(b_cnt, 0, 4 * (size_t)(n_buckets + 1), st));
+        const unsigned qb = blocks_for((int64_t)nq * 32, 128);
+        k_cold_pass<false><<<qb, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, ix->post, nq, G, n_groups, elig, b_cnt,
+                                              nullptr);
+        BR_CUDA(cudaGetLastError());
+        k_scan_reduce<<<(unsigned)n_scan_blocks, SCAN_T, 0, st>>>(b_cnt, n_buckets, part);
+        BR_CUDA(cudaGetLastError());
+        k_exscan<uint32_t><<<1, 1024, 0, st>>>(part, n_scan_blocks, part_off);
+        BR_CUDA(cudaGetLastError());
+        k_scan_apply<<<(unsigned)n_scan_blocks, SCAN_T, 0, st>>>(b_cnt, n_buckets, part_off, b_off, b_cur);
+        BR_CUDA(cudaGetLastError());
+        k_cold_pass<true><<<qb, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, ix->post, nq, G, n_groups, elig, b_cur,
+                                             d_cold);
+        BR_CUDA(cudaGetLastError());
+        ix->stats.kernel_launches += 5;
+        cold = d_cold;
+        cold_off = b_off;
+    }
+
+    TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
+               cold_off, cold, thr, cand_cnt, cand, cand_h, (int)k, 0};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
                                                                             sizeof(uint32_t) * (TILE_W + 1));
     switch (G) {
-        case 1: BR_TRY(launch_tiles<1>(a, n_groups, n_tiles, smem, st, ix)); break;
-        case 2: BR_TRY(launch_tiles<2>(a, n_groups, n_tiles, smem, st, ix)); break;
-        case 4: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix)); break;
-        default: BR_TRY(launch_tiles<8>(a, n_groups, n_tiles, smem, st, ix)); break;
+        case 1: BR_TRY(launch_tiles<1>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
+        case 2: BR_TRY(launch_tiles<2>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
+        case 4: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
+        default: BR_TRY(launch_tiles<8>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
     }
-    if (total > 0) {
-        BR_TRY(launch_rescore(ix, q_off, pv, dedup, cand_off, 0, nq, cand, cand_sc, total, st));
-    }
+    const int64_t total = (int64_t)nq * TILE_CAP;
+    BR_TRY(launch_rescore(ix, q_off, pv, dedup, cand_off, 0, nq, cand, cand_sc, total, st));
     BR_TRY(launch_final_select(cand, cand_sc, cand_off, 0, nq, k, positive_only, out_ids, out_scores, cnt_tmp, st));
     const int32_t need = (int32_t)std::min<int64_t>(k, ix->n_docs);
-    k_fused_flags<<<blocks_for(nq, 256), 256, 0, st>>>(elig, cand_cnt, cnt_tmp, nq, need, positive_only, flags);
+    k_fused_flags<<<blocks_for(nq, 256), 256, 0, st>>>(elig, overflow, cnt_tmp, nq, need, positive_only, flags);
     BR_CUDA(cudaGetLastError());
     ix->stats.kernel_launches += 3;
-    ix->stats.candidates_rescored += total;
     h_flags->resize((size_t)nq);
     BR_CUDA(cudaMemcpyAsync(h_flags->data(), flags, 4 * (size_t)nq, cudaMemcpyDeviceToHost, st));
     BR_CUDA(cudaStreamSynchronize(st));
