@@ -38,6 +38,7 @@ constexpr int TILE_S = 1 << TILE_SHIFT;
 constexpr int TILE_DOCS_SHIFT = TILE_SHIFT + 3;   // log2(W * S)
 constexpr int TILE_QT = 32;          // max distinct hot terms of one query on this path
 constexpr int TILE_CAP = 1024;       // candidates kept per query between tighten rounds
+constexpr uint32_t TILE_DENSE_MIN = 16;  // postings of a term in a 512-doc sub-range from which the warp works cooperatively
 static_assert((1 << 3) == TILE_W, "TILE_DOCS_SHIFT assumes W == 8");
 
 struct __align__(16) TileEntry {
@@ -207,6 +208,54 @@ __device__ __forceinline__ float warp_sort_desc(float v, int lane) {
     return v;   // lane i holds the i-th largest
 }
 
+
+// ---- dense slice of one term, specialised on the set of queries (MASK) of the group that contain it ----
+// cur[] holds the first chunk (128 postings, 4 per lane) already loaded; chunks are processed with the
+// next chunk (of this term, or the first chunk of the next dense term: np/nstart/nhi) in flight.
+// Full chunks carry no predicates at all; only the last, partial chunk of a slice is predicated per lane.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
+}
+
+// Read-modify-write of up to 4 postings per lane into the accumulator rows of the queries in MASK
+// (straight-line: all LDS, then the adds, then all STS; ok[x] predicates the lanes of a partial chunk).
+template <int G, unsigned MASK, bool MULT>
+__device__ __forceinline__ void rmw_chunk(const uint32_t (&a)[4], const bool (&ok)[4], const uint2 (&cur)[4],
+                                          const float (&fm)[G]) {
+    constexpr uint32_t ROWB = TILE_W * TILE_S * 4;                        // bytes between query rows
+    float r[4][G];
+#pragma unroll
+    for (int q = 0; q < G; ++q)
+        if (MASK & (1u << q)) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+                if (ok[x]) r[x][q] = lds_f32(a[x] + q * ROWB);
+        }
+#pragma unroll
+    for (int q = 0; q < G; ++q)
+        if (MASK & (1u << q)) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const float wt = __uint_as_float(cur[x].y);
+                if (ok[x]) sts_f32(a[x] + q * ROWB, MULT ? fmaf(wt, fm[q], r[x][q]) : r[x][q] + wt);
+            }
+        }
+}
+
+template <int G, bool MULT, unsigned MASK = 1>
+__device__ __forceinline__ void rmw_dispatch(unsigned mask, const uint32_t (&a)[4], const bool (&ok)[4],
+                                             const uint2 (&cur)[4], const float (&fm)[G]) {
+    if constexpr (MASK < (1u << G)) {
+        if (mask == MASK) rmw_chunk<G, MASK, MULT>(a, ok, cur, fm);
+        else rmw_dispatch<G, MULT, MASK + 1>(mask, a, ok, cur, fm);
+    }
+}
+
 struct TileArgs {
     const br_posting* post;
     const int64_t* row_ptr;
@@ -227,10 +276,11 @@ struct TileArgs {
     float* cand_h;                // [nq, TILE_CAP]
     int K;
     int tile0;
+    int has_mult;                 // 0: every multiplicity is 1 (set(query) semantics)
 };
 
 template <int G>
-__global__ void __launch_bounds__(TILE_W * 32) k_tile_score(TileArgs a) {
+__global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* acc = reinterpret_cast<float*>(smem_raw);                                     // [G][W][S]
     TileEntry* ent = reinterpret_cast<TileEntry*>(smem_raw + sizeof(float) * G * TILE_W * TILE_S);
@@ -265,34 +315,166 @@ __global__ void __launch_bounds__(TILE_W * 32) k_tile_score(TileArgs a) {
     const uint32_t doc0 = (uint32_t)sub << TILE_SHIFT;
     float* my = acc + w * TILE_S;                       // + q * TILE_W * TILE_S per query
 
-    for (int u = 0; u < U; ++u) {
-        const uint32_t lo = s_bnd[u * (TILE_W + 1) + w], hi = s_bnd[u * (TILE_W + 1) + w + 1];
-        if (lo >= hi) continue;
-        const TileEntry e = ent[u];
-        float fm[G];
+    constexpr int ROW = TILE_W * TILE_S;
+    // Phase A - sparse slices (< TILE_DENSE_MIN postings of a term in this sub-range).  Walking them
+    // term by term would waste the warp (most (term, sub-range) pairs hold 0-4 postings), so the
+    // slices of 32 union terms at a time are concatenated: a warp-scan of the slice lengths gives every
+    // slice its offset, then lane j takes element j of the concatenation (owner found by a shuffle
+    // binary search).  Lanes of one instruction may now carry the same doc through different terms;
+    // __match_any_sync serialises exactly those (shared float atomics are a CAS loop on sm_100).
+    // Dense slices are only marked here.
+    unsigned dense_mask[(G * TILE_QT + 31) / 32];
 #pragma unroll
-        for (int q = 0; q < G; ++q) fm[q] = (float)e.mult[q];
-        const uint2* p = reinterpret_cast<const uint2*>(a.post) + s_base[u];
-        for (uint32_t i = lo + lane; i < hi; i += 128) {
-            uint2 v[4];
-            bool ok[4];
+    for (int r = 0; r < (G * TILE_QT + 31) / 32; ++r) {
+        dense_mask[r] = 0;
+        if (r * 32 >= U) continue;                          // warp-uniform
+        const int u = r * 32 + lane;
+        uint32_t lo = 0, n = 0;
+        if (u < U) {
+            lo = s_bnd[u * (TILE_W + 1) + w];
+            n = s_bnd[u * (TILE_W + 1) + w + 1] - lo;
+        }
+        const bool dense = n >= TILE_DENSE_MIN;
+        dense_mask[r] = __ballot_sync(0xffffffffu, dense);
+        const uint32_t ns = dense ? 0u : n;
+        uint32_t incl = ns;
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                ok[x] = i + 32 * x < hi;
-                if (ok[x]) v[x] = __ldg(p + i + 32 * x);
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            // owner = first lane whose inclusive prefix exceeds j
+            int own = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, incl, own + step - 1);
+                if (v <= j) own += step;
+            }
+            const bool valid = j < total;
+            own = valid ? own : 0;
+            const uint32_t o_incl = __shfl_sync(0xffffffffu, incl, own);
+            const uint32_t o_n = __shfl_sync(0xffffffffu, ns, own);
+            const uint32_t o_lo = __shfl_sync(0xffffffffu, lo, own);
+            const int ou = r * 32 + own;
+            uint32_t l = 0;
+            float wt = 0.f;
+            unsigned mults = 0;                              // 8 bits per query (G <= 4) / 4 bits (G == 8)
+            if (valid) {
+                const uint32_t idx = j - (o_incl - o_n);
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.post) + s_base[ou] + o_lo + idx);
+                l = v.x - doc0;
+                wt = __uint_as_float(v.y);
             }
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                if (ok[x]) {
-                    const uint32_t l = v[x].x - doc0;
-                    const float wt = __uint_as_float(v[x].y);
-#pragma unroll
-                    for (int q = 0; q < G; ++q)
-                        if (fm[q] != 0.f) my[q * TILE_W * TILE_S + l] = fmaf(wt, fm[q], my[q * TILE_W * TILE_S + l]);
+            for (int q = 0; q < G; ++q) {
+                const float m = valid ? (float)ent[ou].mult[q] : 0.f;
+                bool todo = m != 0.f;
+                (void)mults;
+                while (true) {
+                    const unsigned pend = __ballot_sync(0xffffffffu, todo);
+                    if (!pend) break;
+                    if (todo) {
+                        const unsigned peers = __match_any_sync(pend, l);
+                        if ((peers & ((1u << lane) - 1)) == 0) {
+                            my[q * ROW + l] = fmaf(wt, m, my[q * ROW + l]);
+                            todo = false;
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }
+    }
+    __syncwarp();
+    // Phase B - dense slices, warp-cooperative and software-pipelined (dense_term): the next 128
+    // postings (4 per lane, coalesced 8-byte words) are in flight while the current ones are added.
+    // Inside a chunk all docs are distinct (one term), so the read-modify-writes of a lane are
+    // independent: all LDS first, then the adds, then all STS.  No atomics.
+    auto next_dense = [&](int u) {      // first dense entry with index >= u (U when none)
+#pragma unroll
+        for (int r = 0; r < (G * TILE_QT + 31) / 32; ++r) {
+            if (u < (r + 1) * 32) {
+                const unsigned m = dense_mask[r] & (u <= r * 32 ? 0xffffffffu : (0xffffffffu << (u - r * 32)));
+                if (m) return r * 32 + __ffs(m) - 1;
+            }
+        }
+        return U;
+    };
+    const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
+    int u = next_dense(0);
+    uint32_t start = 0, hi = 0;                     // current chunk = postings [start, min(start+128, hi)) of term u
+    const uint2* p = reinterpret_cast<const uint2*>(a.post);
+    uint2 cur[4];
+    float fm[G];
+    unsigned mask = 0;
+    if (u < U) {
+        start = s_bnd[u * (TILE_W + 1) + w];
+        hi = s_bnd[u * (TILE_W + 1) + w + 1];
+        p = reinterpret_cast<const uint2*>(a.post) + s_base[u];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            if (start + lane + 32 * x < hi) cur[x] = __ldg(p + start + lane + 32 * x);
+        const TileEntry e = ent[u];
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            fm[q] = (float)e.mult[q];
+            mask |= e.mult[q] ? (1u << q) : 0u;
+        }
+    }
+    while (u < U) {
+        // coordinates of the next chunk: same term, or the first chunk of the next dense term
+        int nu = u;
+        uint32_t nstart = start + 128, nhi = hi;
+        const uint2* np = p;
+        if (nstart >= hi) {
+            nu = next_dense(u + 1);
+            nstart = nhi = 0;
+            if (nu < U) {
+                nstart = s_bnd[nu * (TILE_W + 1) + w];
+                nhi = s_bnd[nu * (TILE_W + 1) + w + 1];
+                np = reinterpret_cast<const uint2*>(a.post) + s_base[nu];
+            }
+        }
+        uint2 nxt[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            if (nstart + lane + 32 * x < nhi) nxt[x] = __ldg(np + nstart + lane + 32 * x);
+        uint32_t ad[4];
+        bool ok[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            ok[x] = start + lane + 32 * x < hi;
+            ad[x] = my_s + ((cur[x].x - doc0) << 2);
+        }
+        constexpr uint32_t ROWB = TILE_W * TILE_S * 4;     // bytes between query rows
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            if (mask & (1u << q)) {                        // warp-uniform
+                float r[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+                    if (ok[x]) r[x] = lds_f32(ad[x] + q * ROWB);
+#pragma unroll
+                for (int x = 0; x < 4; ++x)                // fmaf(w, 1.0f, acc) == acc + w exactly
+                    if (ok[x]) sts_f32(ad[x] + q * ROWB, fmaf(__uint_as_float(cur[x].y), fm[q], r[x]));
+            }
+        }
         __syncwarp();
+#pragma unroll
+        for (int x = 0; x < 4; ++x) cur[x] = nxt[x];
+        if (nu != u && nu < U) {
+            const TileEntry e = ent[nu];
+            mask = 0;
+#pragma unroll
+            for (int q = 0; q < G; ++q) {
+                fm[q] = (float)e.mult[q];
+                mask |= e.mult[q] ? (1u << q) : 0u;
+            }
+        }
+        u = nu; start = nstart; hi = nhi; p = np;
     }
     // cold postings of this (tile, group) bucket that fall in this warp's sub-range
     if (a.cold_off) {
@@ -322,6 +504,7 @@ __global__ void __launch_bounds__(TILE_W * 32) k_tile_score(TileArgs a) {
         }
         float th = __ldcg(a.thr + qi);
         float lo_thr = th * (1.f - kBandRel);
+        if (!__any_sync(0xffffffffu, mx >= lo_thr && mx > 0.f)) continue;     // nothing above the threshold here
         int c = 0;
 #pragma unroll
         for (int j = 0; j < TILE_S / 32; ++j) c += (v[j] >= lo_thr && v[j] > 0.f) ? 1 : 0;
@@ -476,8 +659,9 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
                int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st,
                std::vector<int32_t>* h_flags) {
     int G = nq >= 4 * kNumSMs ? 4 : (nq >= 2 * kNumSMs ? 2 : 1);
-    if (const char* e = getenv("BR_TILE_G")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) G = v; }
+    if (const char* e = getenv("BR_TILE_G")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) G = v; }
     if (ix->tile_g) G = ix->tile_g;
+    if (G > 4) G = 4;
     const int n_groups = (nq + G - 1) / G, umax = G * TILE_QT;
     const int n_tiles = (ix->n_sub + TILE_W - 1) / TILE_W;
     const int64_t n_buckets = (int64_t)n_tiles * n_groups;
@@ -555,14 +739,14 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     }
 
     TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
-               cold_off, cold, thr, cand_cnt, cand, cand_h, (int)k, 0};
+               cold_off, cold, thr, cand_cnt, cand, cand_h, (int)k, 0, dedup ? 0 : 1};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
                                                                             sizeof(uint32_t) * (TILE_W + 1));
     switch (G) {
         case 1: BR_TRY(launch_tiles<1>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
         case 2: BR_TRY(launch_tiles<2>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
         case 4: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
-        default: BR_TRY(launch_tiles<8>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
+        default: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
     }
     const int64_t total = (int64_t)nq * TILE_CAP;
     BR_TRY(launch_rescore(ix, q_off, pv, dedup, cand_off, 0, nq, cand, cand_sc, total, st));

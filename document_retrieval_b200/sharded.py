@@ -41,11 +41,12 @@ def gather_candidates(ids: torch.Tensor, scores: torch.Tensor, group=None):
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return ids[None], scores[None]
-    all_ids = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
-    all_sc = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
+    q, k = ids.shape
+    all_ids = torch.empty((world * q, k), dtype=ids.dtype, device=ids.device)
+    all_sc = torch.empty((world * q, k), dtype=scores.dtype, device=scores.device)
     dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=group)
     dist.all_gather_into_tensor(all_sc, scores.contiguous(), group=group)
-    return all_ids, all_sc
+    return all_ids.view(world, q, k), all_sc.view(world, q, k)
 
 
 def merge_topk_cuda(all_ids: torch.Tensor, all_sc: torch.Tensor, k: int):
