@@ -25,6 +25,8 @@
 // so far and compacts the list.  With doubling chunks every chunk emits about k new candidates per
 // query, so the candidate list stays ~k long and the float64 re-score costs almost nothing.
 #include <math_constants.h>
+#include <stdio.h>
+#include <time.h>
 
 #include "br_common.cuh"
 #include "br_kernels.cuh"
@@ -60,7 +62,8 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
                                                    const int32_t* __restrict__ hot_slot,
                                                    const int64_t* __restrict__ row_ptr, int32_t nq, int G, int umax,
                                                    TileEntry* __restrict__ entries, int32_t* __restrict__ n_entries,
-                                                   int32_t* __restrict__ elig, unsigned long long* __restrict__ cold_total) {
+                                                   int32_t* __restrict__ elig, unsigned long long* __restrict__ cold_total,
+                                                   int64_t dense_df_min) {
     __shared__ int32_t s_term[4][256];
     __shared__ uint8_t s_q[4][256], s_m[4][256];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
@@ -104,30 +107,36 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
         }
     }
     __syncwarp();
-    int U = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        bool first = i < n;
-        if (first) {
-            const int32_t t = s_term[wl][i];
-            for (int j = 0; j < i; ++j)
-                if (s_term[wl][j] == t) { first = false; break; }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, first);
-        if (first) {
-            TileEntry e;
-            e.term = s_term[wl][i];
-            e.slot = hot_slot[e.term];
+    // union of the group's hot terms, terms that are dense everywhere (df >= dense_df_min) first
+    int U = 0, Ud = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            bool first = i < n;
+            if (first) {
+                const int32_t t = s_term[wl][i];
+                const bool dense = row_ptr[t + 1] - row_ptr[t] >= dense_df_min;
+                if (dense != (pass == 0)) first = false;
+                for (int j = 0; first && j < i; ++j)
+                    if (s_term[wl][j] == t) first = false;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, first);
+            if (first) {
+                TileEntry e;
+                e.term = s_term[wl][i];
+                e.slot = hot_slot[e.term];
 #pragma unroll
-            for (int x = 0; x < 8; ++x) e.mult[x] = 0;
-            for (int j = i; j < n; ++j)
-                if (s_term[wl][j] == e.term) e.mult[s_q[wl][j]] = s_m[wl][j];
-            entries[(int64_t)g * umax + U + __popc(m & ((1u << lane) - 1))] = e;
+                for (int x = 0; x < 8; ++x) e.mult[x] = 0;
+                for (int j = i; j < n; ++j)
+                    if (s_term[wl][j] == e.term) e.mult[s_q[wl][j]] = s_m[wl][j];
+                entries[(int64_t)g * umax + U + __popc(m & ((1u << lane) - 1))] = e;
+            }
+            U += __popc(m);
         }
-        U += __popc(m);
+        if (pass == 0) Ud = U;
     }
     if (lane == 0) {
-        n_entries[g] = U;
+        n_entries[g] = U | (Ud << 16);
         if (cold_sum) atomicAdd(cold_total, cold_sum);
     }
 }
@@ -286,16 +295,18 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
     TileEntry* ent = reinterpret_cast<TileEntry*>(smem_raw + sizeof(float) * G * TILE_W * TILE_S);
     int64_t* s_base = reinterpret_cast<int64_t*>(ent + a.umax);                          // [umax]
     uint32_t* s_bnd = reinterpret_cast<uint32_t*>(s_base + a.umax);                      // [umax][W+1]
+    float4* s_fm = reinterpret_cast<float4*>(s_bnd + a.umax * (TILE_W + 1));             // [umax] multiplicities as floats
 
     const int g = blockIdx.x, tile = a.tile0 + blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int U = a.n_entries[g];
+    const int U = a.n_entries[g] & 0xffff, Ud = a.n_entries[g] >> 16;
     const int sub0 = tile * TILE_W;
 
     for (int u = threadIdx.x; u < U; u += TILE_W * 32) {
         const TileEntry e = a.entries[(int64_t)g * a.umax + u];
         ent[u] = e;
         s_base[u] = a.row_ptr[e.term];
+        s_fm[u] = make_float4((float)e.mult[0], (float)e.mult[1], (float)e.mult[2], (float)e.mult[3]);
     }
     for (int i = threadIdx.x; i < U * (TILE_W + 1); i += TILE_W * 32) {
         const int u = i / (TILE_W + 1), j = i - u * (TILE_W + 1);
@@ -323,20 +334,15 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
     // binary search).  Lanes of one instruction may now carry the same doc through different terms;
     // __match_any_sync serialises exactly those (shared float atomics are a CAS loop on sm_100).
     // Dense slices are only marked here.
-    unsigned dense_mask[(G * TILE_QT + 31) / 32];
-#pragma unroll
-    for (int r = 0; r < (G * TILE_QT + 31) / 32; ++r) {
-        dense_mask[r] = 0;
-        if (r * 32 >= U) continue;                          // warp-uniform
-        const int u = r * 32 + lane;
+#pragma unroll 1
+    for (int r0 = Ud; r0 < U; r0 += 32) {
+        const int u = r0 + lane;
         uint32_t lo = 0, n = 0;
         if (u < U) {
             lo = s_bnd[u * (TILE_W + 1) + w];
             n = s_bnd[u * (TILE_W + 1) + w + 1] - lo;
         }
-        const bool dense = n >= TILE_DENSE_MIN;
-        dense_mask[r] = __ballot_sync(0xffffffffu, dense);
-        const uint32_t ns = dense ? 0u : n;
+        const uint32_t ns = n;
         uint32_t incl = ns;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -358,7 +364,7 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
             const uint32_t o_incl = __shfl_sync(0xffffffffu, incl, own);
             const uint32_t o_n = __shfl_sync(0xffffffffu, ns, own);
             const uint32_t o_lo = __shfl_sync(0xffffffffu, lo, own);
-            const int ou = r * 32 + own;
+            const int ou = r0 + own;
             uint32_t l = 0;
             float wt = 0.f;
             unsigned mults = 0;                              // 8 bits per query (G <= 4) / 4 bits (G == 8)
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
             }
 #pragma unroll
             for (int q = 0; q < G; ++q) {
-                const float m = valid ? (float)ent[ou].mult[q] : 0.f;
+                const float m = valid ? reinterpret_cast<const float*>(s_fm + ou)[q] : 0.f;
                 bool todo = m != 0.f;
                 (void)mults;
                 while (true) {
@@ -393,38 +399,34 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
     // postings (4 per lane, coalesced 8-byte words) are in flight while the current ones are added.
     // Inside a chunk all docs are distinct (one term), so the read-modify-writes of a lane are
     // independent: all LDS first, then the adds, then all STS.  No atomics.
-    auto next_dense = [&](int u) {      // first dense entry with index >= u (U when none)
-#pragma unroll
-        for (int r = 0; r < (G * TILE_QT + 31) / 32; ++r) {
-            if (u < (r + 1) * 32) {
-                const unsigned m = dense_mask[r] & (u <= r * 32 ? 0xffffffffu : (0xffffffffu << (u - r * 32)));
-                if (m) return r * 32 + __ffs(m) - 1;
-            }
-        }
-        return U;
+    auto next_dense = [&](int u) {      // first dense entry >= u with a non-empty slice here (Ud when none)
+        while (u < Ud && s_bnd[u * (TILE_W + 1) + w] >= s_bnd[u * (TILE_W + 1) + w + 1]) ++u;
+        return u;
     };
     const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
     int u = next_dense(0);
+    const int U_all = U; (void)U_all;
     uint32_t start = 0, hi = 0;                     // current chunk = postings [start, min(start+128, hi)) of term u
     const uint2* p = reinterpret_cast<const uint2*>(a.post);
     uint2 cur[4];
     float fm[G];
     unsigned mask = 0;
-    if (u < U) {
+    if (u < Ud) {
         start = s_bnd[u * (TILE_W + 1) + w];
         hi = s_bnd[u * (TILE_W + 1) + w + 1];
         p = reinterpret_cast<const uint2*>(a.post) + s_base[u];
 #pragma unroll
         for (int x = 0; x < 4; ++x)
             if (start + lane + 32 * x < hi) cur[x] = __ldg(p + start + lane + 32 * x);
-        const TileEntry e = ent[u];
+        const float4 f4 = s_fm[u];
+        const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
 #pragma unroll
         for (int q = 0; q < G; ++q) {
-            fm[q] = (float)e.mult[q];
-            mask |= e.mult[q] ? (1u << q) : 0u;
+            fm[q] = ff[q];
+            mask |= ff[q] != 0.f ? (1u << q) : 0u;
         }
     }
-    while (u < U) {
+    while (u < Ud) {
         // coordinates of the next chunk: same term, or the first chunk of the next dense term
         int nu = u;
         uint32_t nstart = start + 128, nhi = hi;
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
         if (nstart >= hi) {
             nu = next_dense(u + 1);
             nstart = nhi = 0;
-            if (nu < U) {
+            if (nu < Ud) {
                 nstart = s_bnd[nu * (TILE_W + 1) + w];
                 nhi = s_bnd[nu * (TILE_W + 1) + w + 1];
                 np = reinterpret_cast<const uint2*>(a.post) + s_base[nu];
@@ -465,13 +467,14 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
         __syncwarp();
 #pragma unroll
         for (int x = 0; x < 4; ++x) cur[x] = nxt[x];
-        if (nu != u && nu < U) {
-            const TileEntry e = ent[nu];
+        if (nu != u && nu < Ud) {
+            const float4 f4 = s_fm[nu];
+            const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
             mask = 0;
 #pragma unroll
             for (int q = 0; q < G; ++q) {
-                fm[q] = (float)e.mult[q];
-                mask |= e.mult[q] ? (1u << q) : 0u;
+                fm[q] = ff[q];
+                mask |= ff[q] != 0.f ? (1u << q) : 0u;
             }
         }
         u = nu; start = nstart; hi = nhi; p = np;
@@ -655,9 +658,22 @@ bool fused_supported(const br_index* ix, int32_t k) {
 
 // Fused path over the whole prepared batch.  h_flags[q] != 0 afterwards -> query q must be served by
 // the dense path (not eligible, candidate overflow, or fewer than k docs with a positive score).
+static void stage_mark(const char* name, cudaStream_t st) {     // BR_TIMELINE=1: wall-clock per stage (debug)
+    static const bool on = getenv("BR_TIMELINE") != nullptr;
+    static double last = 0;
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    fprintf(stderr, "[br timeline] %-14s +%.3f ms\n", name, last == 0 ? 0.0 : now - last);
+    last = now;
+}
+
 int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t nq, int32_t k, int dedup,
                int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st,
                std::vector<int32_t>* h_flags) {
+    stage_mark("enter", st);
     int G = nq >= 4 * kNumSMs ? 4 : (nq >= 2 * kNumSMs ? 2 : 1);
     if (const char* e = getenv("BR_TILE_G")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) G = v; }
     if (ix->tile_g) G = ix->tile_g;
@@ -704,7 +720,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     BR_CUDA(cudaMemsetAsync(cold_total, 0, 16, st));
     BR_CUDA(cudaMemsetAsync(cand, 0xFF, 4 * (size_t)nq * TILE_CAP, st));
     k_tile_prep<<<(n_groups + 3) / 4, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, nq, G, umax, entries, n_entries,
-                                                    elig, cold_total);
+                                                    elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)TILE_DENSE_MIN) >> TILE_SHIFT));
     BR_CUDA(cudaGetLastError());
     k_fill_offsets<<<blocks_for(nq + 1, 256), 256, 0, st>>>(cand_off, nq, TILE_CAP);
     BR_CUDA(cudaGetLastError());
@@ -712,6 +728,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     BR_CUDA(cudaMemcpyAsync(&h_cold, cold_total, sizeof(h_cold), cudaMemcpyDeviceToHost, st));
     BR_CUDA(cudaStreamSynchronize(st));
     ix->stats.kernel_launches += 2;
+    stage_mark("tile_prep", st);
     BR_REQUIRE(h_cold < (1ull << 32), BR_ERR_UNSUPPORTED, "br_topk_batch: more than 2^32 cold postings in one batch");
 
     const ColdEntry* cold = nullptr;
@@ -738,16 +755,18 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
         cold_off = b_off;
     }
 
+    stage_mark("cold_sort", st);
     TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
                cold_off, cold, thr, cand_cnt, cand, cand_h, (int)k, 0, dedup ? 0 : 1};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
-                                                                            sizeof(uint32_t) * (TILE_W + 1));
+                                                                            sizeof(uint32_t) * (TILE_W + 1) + sizeof(float4));
     switch (G) {
         case 1: BR_TRY(launch_tiles<1>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
         case 2: BR_TRY(launch_tiles<2>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
         case 4: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
         default: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
     }
+    stage_mark("tiles", st);
     const int64_t total = (int64_t)nq * TILE_CAP;
     BR_TRY(launch_rescore(ix, q_off, pv, dedup, cand_off, 0, nq, cand, cand_sc, total, st));
     BR_TRY(launch_final_select(cand, cand_sc, cand_off, 0, nq, k, positive_only, out_ids, out_scores, cnt_tmp, st));
@@ -758,6 +777,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     h_flags->resize((size_t)nq);
     BR_CUDA(cudaMemcpyAsync(h_flags->data(), flags, 4 * (size_t)nq, cudaMemcpyDeviceToHost, st));
     BR_CUDA(cudaStreamSynchronize(st));
+    stage_mark("tail", st);
     return BR_OK;
 }
 
