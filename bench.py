@@ -153,6 +153,13 @@ def gen_queries(args, doc_offsets, token_ids, doc_lo, doc_hi, rank, world):
     return np.concatenate(terms).astype(np.int32), q_off, src
 
 
+def cpu_sample_size(args, threads):
+    """Queries in the CPU sample: about 10-15 s of work (one core scores ~9 postings-heavy queries/s at
+    N = 8.8M; the cost is linear in N)."""
+    per_core_qps = 9.0 * 8_800_000 / max(args.docs, 1)
+    return int(max(threads, min(args.queries, per_core_qps * threads * 12)))
+
+
 def cpu_oracle_run(args, doc_offsets_h, token_ids_h, q_terms, q_off, n_sample, threads, repeats=1):
     """Times the plain-C port on the host: index build (untimed) then `n_sample` queries."""
     from oracle.c_oracle import COracle
@@ -194,7 +201,7 @@ def main():
         q_terms, q_off, _ = gen_queries(args, doc_offsets, token_ids, 0, args.docs, 0, 1)
         do_h, tk_h = doc_offsets.cpu().numpy(), token_ids.cpu().numpy()
         del doc_offsets, token_ids
-        n_sample = args.cpu_sample or max(threads, min(args.queries, 4 * threads))
+        n_sample = args.cpu_sample or cpu_sample_size(args, threads)
         from oracle.c_oracle import COracle
         co = COracle(do_h, tk_h, args.vocab, variant="notebook", n_threads=threads)
         qo = q_off[:n_sample + 1]
@@ -302,6 +309,11 @@ def main():
     else:
         alg_bytes_rank = alg_bytes
     peak, peak_src = measured_peak()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath) and world == 1 and args.docs == 8_800_000 and args.queries == 10_000:
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_step")
     launches = max(1, int(qstats["score_launches"]))
     achieved = alg_bytes_rank / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
     recall = float(np.mean([(int(src[i]) in ids_e2e[i].tolist()) for i in range(args.queries)]))
@@ -318,14 +330,14 @@ def main():
         "gpu_launches": int(qstats["kernel_launches"]) * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "bm25 scoring (per rank)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "peak_source": peak_src, "launches_per_step": launches,
                      "algorithmic_bytes_per_launch": alg_bytes_rank / launches,
                      "kernel_ms_per_launch": k_ms / launches, "kernel_share_of_step": k_ms / ms_step,
                      "path": {"fused": int(qstats["queries_fused"]), "dense": int(qstats["queries_dense"])}},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_sample = args.cpu_sample or max(threads, min(args.queries, 4 * threads))
+        n_sample = args.cpu_sample or cpu_sample_size(args, threads)
         cpu_qps, cpu_build_s, cpu_s, out = cpu_oracle_run(args, do_h, tk_h, q_terms, q_off, n_sample, threads)
         same = bool(np.array_equal(out[0], ids_e2e[:n_sample].numpy().astype(np.int32)))
         line["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": threads, "kind": "port",
