@@ -32,6 +32,9 @@ SIGNATURES = {
     "br_topk_batch": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int, C.c_int, _P, _P, _P, _P]),
     "br_rescore_docs": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, _P, _P, _P, _P]),
     "br_topk_merge": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    "br_row_inv_norms": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
+    "br_cosine_topk": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
+    "br_cosine_rerank": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "br_last_query_stats": (C.c_int, [_P, _P]),
     "br_set_profiling": (C.c_int, [_P, C.c_int]),
     "br_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),

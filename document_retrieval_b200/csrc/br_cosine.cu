@@ -1,0 +1,551 @@
+// br_cosine.cu - dense cosine similarity on bf16 embeddings (team_run1.py:269-295):
+//   e_hat = e / (||e|| + 1e-10) on both sides, sims = E_hat . q_hat, top-k per query.
+//
+//   k_row_inv_norm      1/(||x||_2 + 1e-10) per row, fp32                        (HBM-bound, one pass)
+//   k_cosine_gemm       brute force: bf16 tcgen05 (UMMA) GEMM  docs[128-row tile] x queries[256-col tile],
+//                       TMA (128B swizzle) -> 4-stage smem ring -> tcgen05.mma, fp32 accumulators in TMEM
+//                       (2 x 256 columns, double buffered); epilogue warps read TMEM with tcgen05.ld,
+//                       apply 1/(||d||+eps) * 1/(||q||+eps) and keep only scores above the query's running
+//                       threshold - the [Q, N] score matrix is never written.  Persistent, warp-specialised
+//                       (warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue).        (tensor-bound)
+//   k_tighten_cos       between doc chunks of doubling size: threshold := k-th best so far, compact list
+//   k_cosine_rerank     per query its own c candidate rows (BM25 top-1000 -> cosine): one warp per
+//                       (query, candidate) dot product with 128-bit loads              (gather / HBM-bound)
+// This is the only place tensor cores are used: it is the only dense contraction on the path.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "br_common.cuh"
+#include "br_kernels.cuh"
+#include "br_query.cuh"
+
+namespace br {
+
+constexpr int COS_CAP = 1024;       // candidates kept per query between tighten rounds
+constexpr float COS_EPS = 1e-10f;   // team_run1.py:271,276
+
+// ------------------------------------------------------------------------------------------
+// row norms
+// ------------------------------------------------------------------------------------------
+__global__ void k_row_inv_norm(const __nv_bfloat16* __restrict__ x, int64_t n, int32_t d, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    const __nv_bfloat16* p = x + row * d;
+    float s = 0.f;
+    if ((d & 7) == 0) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(p);
+        for (int i = lane; i < d / 8; i += 32) {
+            const uint4 v = __ldg(p4 + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = __uint_as_float(w[j] << 16), b = __uint_as_float(w[j] & 0xffff0000u);
+                s = fmaf(a, a, s);
+                s = fmaf(b, b, s);
+            }
+        }
+    } else {
+        for (int i = lane; i < d; i += 32) {
+            const float a = __bfloat162float(p[i]);
+            s = fmaf(a, a, s);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[row] = 1.0f / (sqrtf(s) + COS_EPS);
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers (sm_100a)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread i of the warp gets row (lane quarter base + i), columns [c, c+32)
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle operand tile (rows of 64 bf16 = 128 B, 8-row swizzle atoms of 1024 B):
+// start address >> 4 | SBO (1024 B between 8-row groups) >> 4 at bit 32 | version 1 at bit 46 | layout
+// SWIZZLE_128B (2) at bit 61.  LBO is unused for this canonical layout.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------------
+// the GEMM + threshold-filter kernel
+// ------------------------------------------------------------------------------------------
+constexpr int CG_BM = 128, CG_BN = 256, CG_BK = 64, CG_STAGES = 4;
+constexpr int CG_A_BYTES = CG_BM * CG_BK * 2, CG_B_BYTES = CG_BN * CG_BK * 2;
+constexpr int CG_STAGE_BYTES = CG_A_BYTES + CG_B_BYTES;
+constexpr int CG_THREADS = 192;
+constexpr size_t CG_SMEM = 1024 /*align slack*/ + (size_t)CG_STAGES * CG_STAGE_BYTES + 2 * CG_BN * sizeof(float) * 2 + 256;
+// instruction descriptor: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), A,B K-major, N=256 (>>3 at bit 17), M=128 (>>4 at bit 24)
+constexpr uint32_t CG_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CG_BN >> 3) << 17) | ((uint32_t)(CG_BM >> 4) << 24);
+
+struct CosArgs {
+    const float* inv_nd;      // [n_docs]
+    const float* inv_nq;      // [nq]
+    const float* thr;         // [nq] k-th best score so far (-inf initially)
+    int32_t* cand_cnt;        // [nq]
+    int32_t* cand;            // [nq, COS_CAP] local doc ids
+    float* cand_h;            // [nq, COS_CAP]
+    int64_t n_docs;
+    int32_t nq;
+    int32_t d;
+    int32_t tile_begin, tile_end;   // doc tiles [tile_begin, tile_end) of 128 rows
+};
+
+__global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_constant__ CUtensorMap map_docs,
+                                                               const __grid_constant__ CUtensorMap map_q, CosArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;             // 128B swizzle needs 1024-byte alignment
+    unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t s_tiles = base;
+    float* s_thr = reinterpret_cast<float*>(gen + CG_STAGES * CG_STAGE_BYTES);          // [2][CG_BN] scaled thresholds
+    float* s_inq = s_thr + 2 * CG_BN;                                                    // [2][CG_BN] 1/(||q||+eps)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_inq + 2 * CG_BN);                    // full[4] empty[4] tfull[2] tempty[2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (CG_STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * CG_STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * CG_STAGES + 2 + b); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_qt = (a.nq + CG_BN - 1) / CG_BN;
+    const int64_t n_tiles = (int64_t)(a.tile_end - a.tile_begin) * n_qt;
+    const int n_kb = (a.d + CG_BK - 1) / CG_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int dt = a.tile_begin + (int)(t / n_qt), qt = (int)(t % n_qt);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), CG_STAGE_BYTES);
+                    const uint32_t sa = s_tiles + stage * CG_STAGE_BYTES;
+                    tma_load_2d(sa, &map_docs, full_bar(stage), kb * CG_BK, dt * CG_BM);
+                    tma_load_2d(sa + CG_A_BYTES, &map_q, full_bar(stage), kb * CG_BK, qt * CG_BN);
+                    if (++stage == CG_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, acc_phase[2] = {0, 0};
+            int it = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(tempty_bar(buf), acc_phase[buf] ^ 1);
+                acc_phase[buf] ^= 1;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * CG_BN;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = s_tiles + stage * CG_STAGE_BYTES;
+                    const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + CG_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < CG_BK / 16; ++k)          // UMMA_K = 16 bf16 = 32 bytes: +2 in the >>4 address field
+                        tc_mma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), CG_IDESC, (kb | k) != 0);
+                    tc_commit(empty_bar(stage));                    // smem slot free once these MMAs retire
+                    if (++stage == CG_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(buf));                          // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5: TMEM lanes [32*(warp%4), +32) =====
+        const int quarter = warp & 3;
+        const int et = (int)threadIdx.x - 64;                       // 0..127
+        uint32_t acc_phase[2] = {0, 0};
+        int it = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int dt = a.tile_begin + (int)(t / n_qt), qt = (int)(t % n_qt);
+            // scaled thresholds of this query tile (double-buffered: the previous tile may still be read)
+            for (int c = et; c < CG_BN; c += 128) {
+                const int q = qt * CG_BN + c;
+                float th = CUDART_INF_F, iq = 0.f;
+                if (q < a.nq) {
+                    iq = a.inv_nq[q];
+                    const float raw = __ldcg(a.thr + q) / iq;          // compare acc*inv_d against thr/inv_q
+                    th = raw - fabsf(raw) * 4e-6f;                      // superset: rounding of the division
+                }
+                s_thr[buf * CG_BN + c] = th;
+                s_inq[buf * CG_BN + c] = iq;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // epilogue warps only
+            mbar_wait(tfull_bar(buf), acc_phase[buf]);
+            acc_phase[buf] ^= 1;
+            tc_fence_after();
+            const int64_t doc = (int64_t)dt * CG_BM + quarter * 32 + lane;
+            const float inv_d = doc < a.n_docs ? a.inv_nd[doc] : 0.f;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * CG_BN;
+            for (int c0 = 0; c0 < CG_BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld_32x32(taddr + c0, v);
+                tc_wait_ld();
+                if (doc < a.n_docs) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = __uint_as_float(v[j]) * inv_d;
+                        if (s >= s_thr[buf * CG_BN + c0 + j]) {
+                            const int q = qt * CG_BN + c0 + j;
+                            const int pos = atomicAdd(a.cand_cnt + q, 1);
+                            if (pos < COS_CAP) {
+                                a.cand[(int64_t)q * COS_CAP + pos] = (int32_t)doc;
+                                a.cand_h[(int64_t)q * COS_CAP + pos] = s * s_inq[buf * CG_BN + c0 + j];
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// threshold := k-th best candidate so far; keep the candidates >= threshold, sorted (score desc, id asc)
+constexpr int TC_T = 256;
+__global__ void __launch_bounds__(TC_T) k_tighten_cos(float* __restrict__ thr, int32_t* __restrict__ cand_cnt,
+                                                      int32_t* __restrict__ prev_cnt, int32_t* __restrict__ cand,
+                                                      float* __restrict__ cand_h, int K, int32_t* __restrict__ overflow) {
+    __shared__ float s_h[COS_CAP];
+    __shared__ int32_t s_id[COS_CAP];
+    __shared__ int s_keep;
+    const int q = blockIdx.x;
+    int n = cand_cnt[q];
+    if (n == prev_cnt[q]) return;
+    if (n > COS_CAP) {
+        if (threadIdx.x == 0) overflow[q] = 1;
+        n = COS_CAP;
+    }
+    int32_t* ids = cand + (int64_t)q * COS_CAP;
+    float* hs = cand_h + (int64_t)q * COS_CAP;
+    for (int i = threadIdx.x; i < COS_CAP; i += TC_T) {
+        s_h[i] = i < n ? hs[i] : -CUDART_INF_F;
+        s_id[i] = i < n ? ids[i] : 0x7fffffff;
+    }
+    if (threadIdx.x == 0) s_keep = 0;
+    for (int size = 2; size <= COS_CAP; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < COS_CAP / 2; i += TC_T) {
+                const int x = 2 * i - (i & (stride - 1)), y = x + stride;
+                const bool up = (x & size) == 0;
+                const float hx = s_h[x], hy = s_h[y];
+                const int32_t ix = s_id[x], iy = s_id[y];
+                const bool y_first = hy > hx || (hy == hx && iy < ix);
+                if (y_first == up) { s_h[x] = hy; s_h[y] = hx; s_id[x] = iy; s_id[y] = ix; }
+            }
+        }
+    }
+    __syncthreads();
+    float th = thr[q];
+    if (n >= K && s_h[K - 1] > th) th = s_h[K - 1];
+    int keep = 0;
+    for (int i = threadIdx.x; i < n; i += TC_T) keep += (s_h[i] >= th) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    if ((threadIdx.x & 31) == 0 && keep) atomicAdd(&s_keep, keep);
+    __syncthreads();
+    keep = s_keep;
+    for (int i = threadIdx.x; i < n; i += TC_T) {
+        ids[i] = i < keep ? s_id[i] : -1;
+        hs[i] = i < keep ? s_h[i] : 0.f;
+    }
+    if (threadIdx.x == 0) {
+        thr[q] = th;
+        cand_cnt[q] = keep;
+        prev_cnt[q] = keep;
+    }
+}
+
+__global__ void k_cos_output(const int32_t* __restrict__ cand, const float* __restrict__ cand_h,
+                             const int32_t* __restrict__ cand_cnt, int32_t nq, int32_t k, int64_t doc_base,
+                             int64_t* __restrict__ out_ids, float* __restrict__ out_sims) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)nq * k) return;
+    const int q = (int)(i / k), j = (int)(i - (int64_t)q * k);
+    const bool ok = j < cand_cnt[q] && j < COS_CAP;           // lists are sorted by the last k_tighten_cos
+    out_ids[i] = ok ? (int64_t)cand[(int64_t)q * COS_CAP + j] + doc_base : -1;
+    out_sims[i] = ok ? cand_h[(int64_t)q * COS_CAP + j] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// candidate re-rank: query q against its own candidate rows
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cosine_rerank(const __nv_bfloat16* __restrict__ docs,
+                                                       const float* __restrict__ inv_nd, int64_t n_docs, int32_t d,
+                                                       const __nv_bfloat16* __restrict__ queries,
+                                                       const float* __restrict__ inv_nq, const int32_t* __restrict__ cand,
+                                                       int64_t n_pairs, int32_t c, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t pair = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (pair >= n_pairs) return;
+    const int32_t q = (int32_t)(pair / c);
+    const int32_t doc = cand[pair];
+    if (doc < 0 || doc >= n_docs) {
+        if (lane == 0) out[pair] = -CUDART_INF_F;
+        return;
+    }
+    const uint4* pd = reinterpret_cast<const uint4*>(docs + (int64_t)doc * d);
+    const uint4* pq = reinterpret_cast<const uint4*>(queries + (int64_t)q * d);
+    float s = 0.f, nn = 0.f;
+    for (int i = lane; i < d / 8; i += 32) {
+        const uint4 a = __ldg(pd + i), b = __ldg(pq + i);
+        const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a0 = __uint_as_float(wa[j] << 16), a1 = __uint_as_float(wa[j] & 0xffff0000u);
+            const float b0 = __uint_as_float(wb[j] << 16), b1 = __uint_as_float(wb[j] & 0xffff0000u);
+            s = fmaf(a0, b0, s);
+            s = fmaf(a1, b1, s);
+            nn = fmaf(a0, a0, nn);
+            nn = fmaf(a1, a1, nn);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    }
+    if (lane == 0) {
+        const float id = inv_nd ? inv_nd[doc] : 1.0f / (sqrtf(nn) + COS_EPS);
+        out[pair] = s * id * inv_nq[q];
+    }
+}
+
+__global__ void k_f32_to_f64(const float* __restrict__ in, int64_t n, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+__global__ void k_rerank_output(const int32_t* __restrict__ ids, const double* __restrict__ sc, int64_t n,
+                                float* __restrict__ out_sims) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out_sims[i] = ids[i] >= 0 ? (float)sc[i] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int32_t d, int box_rows) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        BR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        BR_REQUIRE(p && qres == cudaDriverEntryPointSuccess, BR_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        fn = (PFN_encodeTiled)p;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)d * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)CG_BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BR_REQUIRE(r == CUDA_SUCCESS, BR_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return BR_OK;
+}
+
+struct AsyncBuf {   // stream-ordered scratch
+    void* p = nullptr;
+    cudaStream_t st;
+    explicit AsyncBuf(cudaStream_t s) : st(s) {}
+    int alloc(size_t bytes) { BR_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, st)); return BR_OK; }
+    ~AsyncBuf() { if (p) cudaFreeAsync(p, st); }
+};
+
+int row_inv_norms(const void* emb, int64_t n, int32_t d, float* out, cudaStream_t st) {
+    BR_REQUIRE(emb && out && n >= 0 && d > 0, BR_ERR_INVALID, "br_row_inv_norms: bad arguments");
+    if (n == 0) return BR_OK;
+    k_row_inv_norm<<<blocks_for(n * 32, 256), 256, 0, st>>>((const __nv_bfloat16*)emb, n, d, out);
+    BR_CUDA(cudaGetLastError());
+    return BR_OK;
+}
+
+int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d, const void* queries, int32_t nq,
+                int32_t k, int64_t doc_base, int64_t* out_ids, float* out_sims, cudaStream_t st) {
+    BR_REQUIRE(docs && inv_nd && queries && out_ids && out_sims, BR_ERR_INVALID, "br_cosine_topk: null pointer");
+    BR_REQUIRE(n_docs > 0 && n_docs < (1LL << 31) && nq >= 0, BR_ERR_INVALID, "br_cosine_topk: bad sizes");
+    BR_REQUIRE(d > 0 && d % 8 == 0, BR_ERR_UNSUPPORTED, "br_cosine_topk: embedding dim must be a multiple of 8 (16-byte rows for TMA)");
+    BR_REQUIRE(k >= 1 && k <= 256, BR_ERR_INVALID, "br_cosine_topk: k must be in [1, 256]");
+    BR_REQUIRE(((uintptr_t)docs & 15) == 0 && ((uintptr_t)queries & 15) == 0, BR_ERR_INVALID, "br_cosine_topk: 16-byte alignment required");
+    if (nq == 0) return BR_OK;
+    CUtensorMap map_d, map_q;
+    BR_TRY(make_map(&map_d, docs, n_docs, d, CG_BM));
+    BR_TRY(make_map(&map_q, queries, nq, d, CG_BN));
+    static bool attr = false;
+    if (!attr) {
+        BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));
+        attr = true;
+    }
+    const size_t Q = (size_t)nq;
+    AsyncBuf b_inq(st), b_thr(st), b_cnt(st), b_prev(st), b_ovf(st), b_cand(st), b_h(st);
+    BR_TRY(b_inq.alloc(4 * Q)); BR_TRY(b_thr.alloc(4 * Q)); BR_TRY(b_cnt.alloc(4 * Q)); BR_TRY(b_prev.alloc(4 * Q));
+    BR_TRY(b_ovf.alloc(4 * Q)); BR_TRY(b_cand.alloc(4 * Q * COS_CAP)); BR_TRY(b_h.alloc(4 * Q * COS_CAP));
+    float* inv_nq = (float*)b_inq.p;
+    float* thr = (float*)b_thr.p;
+    BR_TRY(row_inv_norms(queries, nq, d, inv_nq, st));
+    std::vector<float> ninf(Q, -INFINITY);
+    BR_CUDA(cudaMemcpyAsync(thr, ninf.data(), 4 * Q, cudaMemcpyHostToDevice, st));
+    BR_CUDA(cudaMemsetAsync(b_cnt.p, 0, 4 * Q, st));
+    BR_CUDA(cudaMemsetAsync(b_prev.p, 0, 4 * Q, st));
+    BR_CUDA(cudaMemsetAsync(b_ovf.p, 0, 4 * Q, st));
+    const int n_dt = (int)((n_docs + CG_BM - 1) / CG_BM), n_qt = (nq + CG_BN - 1) / CG_BN;
+    int t0 = 0, chunk = 1;
+    while (t0 < n_dt) {
+        const int nt = std::min(chunk, n_dt - t0);
+        CosArgs a{inv_nd, inv_nq, thr, (int32_t*)b_cnt.p, (int32_t*)b_cand.p, (float*)b_h.p, n_docs, nq, d, t0, t0 + nt};
+        const int grid = (int)std::min<int64_t>((int64_t)nt * n_qt, kNumSMs);
+        k_cosine_gemm<<<grid, CG_THREADS, CG_SMEM, st>>>(map_d, map_q, a);
+        BR_CUDA(cudaGetLastError());
+        k_tighten_cos<<<nq, TC_T, 0, st>>>(thr, (int32_t*)b_cnt.p, (int32_t*)b_prev.p, (int32_t*)b_cand.p, (float*)b_h.p, k,
+                                           (int32_t*)b_ovf.p);
+        BR_CUDA(cudaGetLastError());
+        t0 += nt;
+        chunk *= 2;
+    }
+    k_cos_output<<<blocks_for((int64_t)nq * k, 256), 256, 0, st>>>((int32_t*)b_cand.p, (float*)b_h.p, (int32_t*)b_cnt.p, nq, k,
+                                                                    doc_base, out_ids, out_sims);
+    BR_CUDA(cudaGetLastError());
+    std::vector<int32_t> ovf(Q);
+    BR_CUDA(cudaMemcpyAsync(ovf.data(), b_ovf.p, 4 * Q, cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaStreamSynchronize(st));
+    for (int32_t v : ovf)
+        BR_REQUIRE(!v, BR_ERR_UNSUPPORTED, "br_cosine_topk: more than 1024 near-tied candidates for one query");
+    return BR_OK;
+}
+
+int cosine_rerank(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d, const void* queries, int32_t nq,
+                  const int32_t* cand, int32_t c, int32_t k, int32_t* out_ids, float* out_sims, cudaStream_t st) {
+    BR_REQUIRE(docs && queries && cand && out_ids && out_sims, BR_ERR_INVALID, "br_cosine_rerank: null pointer");
+    BR_REQUIRE(n_docs > 0 && nq >= 0 && c >= 1 && k >= 1 && k <= BR_MAX_K, BR_ERR_INVALID, "br_cosine_rerank: bad sizes");
+    BR_REQUIRE(d > 0 && d % 8 == 0, BR_ERR_UNSUPPORTED, "br_cosine_rerank: embedding dim must be a multiple of 8");
+    if (nq == 0) return BR_OK;
+    const int64_t n_pairs = (int64_t)nq * c;
+    AsyncBuf b_inq(st), b_s(st), b_s64(st), b_off(st), b_o64(st);
+    BR_TRY(b_inq.alloc(4 * (size_t)nq)); BR_TRY(b_s.alloc(4 * (size_t)n_pairs)); BR_TRY(b_s64.alloc(8 * (size_t)n_pairs));
+    BR_TRY(b_off.alloc(8 * ((size_t)nq + 1))); BR_TRY(b_o64.alloc(8 * (size_t)nq * k));
+    BR_TRY(row_inv_norms(queries, nq, d, (float*)b_inq.p, st));
+    k_cosine_rerank<<<blocks_for(n_pairs * 32, 256), 256, 0, st>>>((const __nv_bfloat16*)docs, inv_nd, n_docs, d,
+                                                                   (const __nv_bfloat16*)queries, (const float*)b_inq.p, cand,
+                                                                   n_pairs, c, (float*)b_s.p);
+    BR_CUDA(cudaGetLastError());
+    k_f32_to_f64<<<blocks_for(n_pairs, 256), 256, 0, st>>>((const float*)b_s.p, n_pairs, (double*)b_s64.p);
+    BR_CUDA(cudaGetLastError());
+    std::vector<int64_t> off((size_t)nq + 1);
+    for (int32_t q = 0; q <= nq; ++q) off[(size_t)q] = (int64_t)q * c;
+    BR_CUDA(cudaMemcpyAsync(b_off.p, off.data(), 8 * ((size_t)nq + 1), cudaMemcpyHostToDevice, st));
+    BR_TRY(launch_final_select(cand, (const double*)b_s64.p, (const int64_t*)b_off.p, 0, nq, k, 0, out_ids, (double*)b_o64.p,
+                               nullptr, st));
+    k_rerank_output<<<blocks_for((int64_t)nq * k, 256), 256, 0, st>>>(out_ids, (const double*)b_o64.p, (int64_t)nq * k, out_sims);
+    BR_CUDA(cudaGetLastError());
+    BR_CUDA(cudaStreamSynchronize(st));
+    return BR_OK;
+}
+
+}  // namespace br
+
+extern "C" {
+
+int br_row_inv_norms(const void* emb_bf16_dev, int64_t n, int32_t d, float* out_inv_norm_dev, void* stream) {
+    return br::row_inv_norms(emb_bf16_dev, n, d, out_inv_norm_dev, (cudaStream_t)stream);
+}
+
+int br_cosine_topk(const void* docs_bf16_dev, const float* doc_inv_norm_dev, int64_t n_docs, int32_t d,
+                   const void* queries_bf16_dev, int32_t nq, int32_t k, int64_t doc_base, int64_t* out_ids_dev,
+                   float* out_sims_dev, void* stream) {
+    return br::cosine_topk(docs_bf16_dev, doc_inv_norm_dev, n_docs, d, queries_bf16_dev, nq, k, doc_base, out_ids_dev,
+                           out_sims_dev, (cudaStream_t)stream);
+}
+
+int br_cosine_rerank(const void* docs_bf16_dev, const float* doc_inv_norm_dev, int64_t n_docs, int32_t d,
+                     const void* queries_bf16_dev, int32_t nq, const int32_t* cand_ids_dev, int32_t c, int32_t k,
+                     int32_t* out_ids_dev, float* out_sims_dev, void* stream) {
+    return br::cosine_rerank(docs_bf16_dev, doc_inv_norm_dev, n_docs, d, queries_bf16_dev, nq, cand_ids_dev, c, k, out_ids_dev,
+                             out_sims_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -132,6 +132,29 @@ int br_rescore_docs(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_o
 int br_topk_merge(const int64_t* ids_dev, const double* scores_dev, int32_t n_parts, int32_t nq,
                   int32_t k, int64_t* out_ids_dev, double* out_scores_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Dense cosine similarity on bf16 embeddings.  Replaces the re-rank block of team_run1.py:269-295
+ * (e/(||e||+1e-10) on both sides, torch.matmul, torch.topk) and faiss.IndexFlatIP on normalised
+ * vectors (faiss_based_ANN_Implementation.py:279-283).  Embeddings are row-major bf16 [n, d], d a
+ * multiple of 8, 16-byte aligned, NOT pre-normalised; scores are fp32.
+ * ------------------------------------------------------------------------------------------- */
+/* out_inv_norm_dev[i] = 1 / (||emb[i]||_2 + 1e-10)  (.norm() + 1e-10, team_run1.py:271,276). */
+int br_row_inv_norms(const void* emb_bf16_dev, int64_t n, int32_t d, float* out_inv_norm_dev, void* stream);
+/* Exact brute-force top-k (1 <= k <= 256) of every query over all docs: bf16 tcgen05 GEMM with the
+ * normalisation and the top-k filter fused into the epilogue.  doc_inv_norm_dev from
+ * br_row_inv_norms (computed once per corpus).  Outputs [nq, k], best first, ties by doc id:
+ * out_ids_dev int64 (doc_base + local row, -1 pads), out_sims_dev float.  Synchronises `stream`. */
+int br_cosine_topk(const void* docs_bf16_dev, const float* doc_inv_norm_dev, int64_t n_docs, int32_t d,
+                   const void* queries_bf16_dev, int32_t nq, int32_t k, int64_t doc_base,
+                   int64_t* out_ids_dev, float* out_sims_dev, void* stream);
+/* Re-rank: query q against its own candidates cand_ids_dev[q, 0..c) (local rows, -1 = empty slot),
+ * e.g. the BM25 top-1000 (text_preprocessing_and_embedding_setup.py:342).  doc_inv_norm_dev may be
+ * NULL (norms are then computed on the fly).  Outputs [nq, k] (k <= BR_MAX_K): out_ids_dev int32,
+ * out_sims_dev float, ordered by (cosine desc, doc id asc).  Synchronises `stream`. */
+int br_cosine_rerank(const void* docs_bf16_dev, const float* doc_inv_norm_dev, int64_t n_docs, int32_t d,
+                     const void* queries_bf16_dev, int32_t nq, const int32_t* cand_ids_dev, int32_t c,
+                     int32_t k, int32_t* out_ids_dev, float* out_sims_dev, void* stream);
+
 /* Counters of the last br_topk_batch call on this handle (bench / tests): kernels launched,
  * queries served by the fused tiled path, by the dense path, and candidate rows re-scored. */
 typedef struct br_query_stats {

@@ -1,0 +1,75 @@
+"""GPU: dense cosine top-k (tcgen05 GEMM, fused norm + top-k) and candidate re-rank against the
+oracle restatement of team_run1.py:270-282 and its golden fixture.  Tolerance (north_star): cosine
+scores within 1e-5 relative in fp32 (plus 2e-6 absolute for values near zero); ids identical except
+where two reference scores are closer than that tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bm25_oracle as orc
+from document_retrieval_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 2e-6
+
+
+def _check(ids, sims, docs_f32, q_f32, k):
+    ref_ids, ref_sims = orc.cosine_topk(docs_f32, q_f32, k)
+    d = torch.as_tensor(docs_f32)
+    dn = d / (d.norm(dim=1, keepdim=True) + 1e-10)
+    qn = torch.as_tensor(q_f32)
+    qn = qn / (qn.norm(dim=1, keepdim=True) + 1e-10)
+    full = (qn @ dn.T).numpy()
+    np.testing.assert_allclose(sims, ref_sims, rtol=RTOL, atol=ATOL)
+    for i in range(ids.shape[0]):
+        if not np.array_equal(ids[i], ref_ids[i]):
+            # any difference must be a near-tie in the reference
+            np.testing.assert_allclose(full[i, ids[i]], ref_sims[i], rtol=RTOL, atol=ATOL)
+            assert len(set(ids[i].tolist())) == k
+
+
+def test_cosine_topk_golden(golden):
+    from document_retrieval_b200.cosine import CosineIndex
+    g = golden("cosine_small")
+    docs = torch.from_numpy(g["docs_bf16"]).view(torch.bfloat16)
+    qs = torch.from_numpy(g["queries_bf16"]).view(torch.bfloat16)
+    ix = CosineIndex(docs)
+    ids, sims = ix.topk(qs, 10)
+    ids, sims = ids.cpu().numpy(), sims.cpu().numpy()
+    np.testing.assert_allclose(sims, g["top_sims"], rtol=RTOL, atol=ATOL)
+    assert np.array_equal(ids, g["top_ids"])
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(5000, 768, 300, 10), (777, 128, 5, 3), (130, 64, 257, 10), (20000, 384, 64, 32)])
+def test_cosine_topk_random(n, d, nq, k):
+    from document_retrieval_b200.cosine import CosineIndex
+    g = torch.Generator().manual_seed(synth.ROOT_SEED + n)
+    docs = torch.randn(n, d, generator=g).to(torch.bfloat16)
+    qs = torch.randn(nq, d, generator=g).to(torch.bfloat16)
+    docs[3] = 0                                              # zero-norm doc: e/(0+1e-10) = 0
+    ix = CosineIndex(docs, doc_base=1000)
+    ids, sims = ix.topk(qs, k)
+    _check(ids.cpu().numpy() - 1000, sims.cpu().numpy(), docs.float().numpy(), qs.float().numpy(), k)
+
+
+def test_cosine_rerank_of_bm25_candidates():
+    from document_retrieval_b200 import BM25
+    from document_retrieval_b200.cosine import CosineIndex, rerank_bm25_with_cosine
+    c = synth.make_config("C1", scale=0.3)
+    m = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"])
+    g = torch.Generator().manual_seed(7)
+    emb = torch.randn(c["n_docs"], 768, generator=g).to(torch.bfloat16)
+    qe = torch.randn(c["q_offsets"].size - 1, 768, generator=g).to(torch.bfloat16)
+    ix = CosineIndex(emb)
+    ids, sims = rerank_bm25_with_cosine(m, ix, (c["q_terms"], c["q_offsets"]), qe, n_candidates=200, k=10)
+    ids, sims = ids.cpu().numpy(), sims.cpu().numpy()
+    cand, _ = m.retrieve_top_n_batch((c["q_terms"], c["q_offsets"]), 200)
+    cand = cand.cpu().numpy()
+    e32, q32 = emb.float().numpy(), qe.float().numpy()
+    for i in range(0, ids.shape[0], 17):
+        cc = cand[i][cand[i] >= 0]
+        ri, rs = orc.cosine_topk(e32[cc], q32[i:i + 1], 10)
+        np.testing.assert_allclose(sims[i], rs[0], rtol=RTOL, atol=ATOL)
+        assert set(ids[i].tolist()) <= set(cc.tolist())
+        if not np.array_equal(ids[i], cc[ri[0]]):
+            assert np.allclose(np.sort(sims[i]), np.sort(rs[0]), rtol=RTOL, atol=ATOL)
