@@ -31,6 +31,9 @@ SIGNATURES = {
     "br_score_batch": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, _P, _P]),
     "br_topk_batch": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int, C.c_int, _P, _P, _P, _P]),
     "br_rescore_docs": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, _P, _P, _P, _P]),
+    "br_index_enable_tfidf": (C.c_int, [_P, _P]),
+    "br_tfidf_cosine_topk": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "br_rerank_v3_scores": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "br_topk_merge": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "br_row_inv_norms": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
     "br_cosine_topk": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),

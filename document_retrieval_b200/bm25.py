@@ -235,6 +235,39 @@ class BM25:
                                       ptr(off), ptr(out), _lib.stream_ptr(dev)), "br_rescore_docs")
         return out
 
+    def tfidf_cosine_top_n_batch(self, queries, n=200):
+        """First stage of rank_documents_with_cosine_similarity_and_bm25
+        (cosine_similarity_bm25_reranking.py:210-229): top-``n`` docs by sparse TF-IDF cosine ->
+        (ids int32[Q, n], scores float64[Q, n] = cosine * ||q||) on the device."""
+        self._require()
+        lib = _lib.load()
+        q_terms, q_off = self._to_device(*self.pack_queries(queries))
+        nq = q_off.numel() - 1
+        dev = self._device
+        with torch.cuda.device(dev):
+            ids = torch.empty((nq, n), dtype=torch.int32, device=dev)
+            sc = torch.empty((nq, n), dtype=torch.float64, device=dev)
+            check(lib.br_tfidf_cosine_topk(self._h, ptr(q_terms), ptr(q_off), nq, int(n), ptr(ids), ptr(sc), None,
+                                           _lib.stream_ptr(dev)), "br_tfidf_cosine_topk")
+        return ids, sc
+
+    def rerank_scores_v3(self, queries, cand_ids):
+        """bm25_score (cosine_similarity_bm25_reranking.py:185-195) of every (query, candidate) pair:
+        ``cand_ids`` int32[Q, c] (local ids, -1 = empty) -> float64[Q, c] on the device."""
+        self._require()
+        lib = _lib.load()
+        q_terms, q_off = self._to_device(*self.pack_queries(queries))
+        nq = q_off.numel() - 1
+        dev = self._device
+        cand = torch.as_tensor(cand_ids).to(device=dev, dtype=torch.int32).contiguous()
+        c = cand.shape[1]
+        with torch.cuda.device(dev):
+            off = torch.arange(nq + 1, dtype=torch.int64, device=dev) * c
+            out = torch.empty((nq, c), dtype=torch.float64, device=dev)
+            check(lib.br_rerank_v3_scores(self._h, ptr(q_terms), ptr(q_off), nq, ptr(cand), ptr(off), ptr(out),
+                                          _lib.stream_ptr(dev)), "br_rerank_v3_scores")
+        return out
+
     def retrieve_top_n(self, query, n=10):
         """bm25_ranking.ipynb:206-213 -> np.ndarray[int64] of local doc indices, best first.
         ``n >= N`` returns the full ranking (:208-209).  Ties: doc id ascending."""

@@ -29,6 +29,19 @@ int br_rescore_docs(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_o
                             (cudaStream_t)stream);
 }
 
+int br_index_enable_tfidf(br_index* ix, void* stream) { return br::enable_tfidf(ix, (cudaStream_t)stream); }
+
+int br_tfidf_cosine_topk(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq, int32_t k,
+                         int32_t* out_ids_dev, double* out_scores_dev, int32_t* out_counts_dev, void* stream) {
+    return br::tfidf_topk(ix, q_terms_dev, q_offsets_dev, nq, k, out_ids_dev, out_scores_dev, out_counts_dev,
+                          (cudaStream_t)stream);
+}
+
+int br_rerank_v3_scores(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq,
+                        const int32_t* cand_ids_dev, const int64_t* cand_off_dev, double* out_scores_dev, void* stream) {
+    return br::rerank_v3(ix, q_terms_dev, q_offsets_dev, nq, cand_ids_dev, cand_off_dev, out_scores_dev, (cudaStream_t)stream);
+}
+
 int br_topk_merge(const int64_t* ids_dev, const double* scores_dev, int32_t n_parts, int32_t nq, int32_t k,
                   int64_t* out_ids_dev, double* out_scores_dev, void* stream) {
     return br::topk_merge(ids_dev, scores_dev, n_parts, nq, k, out_ids_dev, out_scores_dev, (cudaStream_t)stream);

@@ -177,7 +177,7 @@ __global__ void k_export(const br_posting* __restrict__ post, const uint16_t* __
 void index_free(br_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
-    cudaFree(ix->row_ptr); cudaFree(ix->post); cudaFree(ix->tf); cudaFree(ix->dl); cudaFree(ix->df);
+    cudaFree(ix->row_ptr); cudaFree(ix->post); cudaFree(ix->post_cos); cudaFree(ix->tf); cudaFree(ix->dl); cudaFree(ix->df);
     cudaFree(ix->idf); cudaFree(ix->hot_slot); cudaFree(ix->skip);
     ix->ws_prep.release(); ix->ws_dense.release(); ix->ws_sel.release(); ix->ws_cand.release();
     ix->ws_misc.release(); ix->ws_tile.release();

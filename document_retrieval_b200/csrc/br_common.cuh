@@ -82,6 +82,7 @@ struct br_index {
     // CSR by term (device)
     int64_t* row_ptr = nullptr;     // [V+1]
     br_posting* post = nullptr;     // [nnz]   doc ids ascending inside a term
+    br_posting* post_cos = nullptr; // [nnz]   optional TF-IDF cosine weights tf*idf^2/||d|| (br_index_enable_tfidf)
     uint16_t* tf = nullptr;         // [nnz]   raw term frequency (for the float64 re-score)
     uint32_t* dl = nullptr;         // [N]
     uint32_t* df = nullptr;         // [V]     shard-local document frequency
@@ -152,6 +153,11 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, i
                cudaStream_t st);
 int rescore_docs(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, int32_t nq, int dedup,
                  const int32_t* cand_ids, const int64_t* cand_off, double* out_scores, cudaStream_t st);
+int enable_tfidf(br_index* ix, cudaStream_t st);
+int tfidf_topk(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, int32_t nq, int32_t k, int32_t* out_ids,
+               double* out_scores, int32_t* out_counts, cudaStream_t st);
+int rerank_v3(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, int32_t nq, const int32_t* cand_ids,
+              const int64_t* cand_off, double* out_scores, cudaStream_t st);
 int topk_merge(const int64_t* ids, const double* scores, int32_t n_parts, int32_t nq, int32_t k,
                int64_t* out_ids, double* out_scores, cudaStream_t st);
 }  // namespace br

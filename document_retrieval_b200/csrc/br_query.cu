@@ -414,6 +414,107 @@ __global__ void __launch_bounds__(FS_T) k_final_select(const IdT* __restrict__ i
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// "V3" re-rank formula: bm25_score, cosine_similarity_bm25_reranking.py:185-195
+//   doc_length = sum of the tf of the query's term occurrences in this doc (:187)
+//   score += idf * ((tf*(k1+1)) / (tf + k1*(1 - b + b*(doc_length/avgdl))))   for every occurrence whose
+//   term is in the corpus (duplicates counted, idf without +1)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t lookup_tf(const RescoreIndex& r, int32_t t, uint32_t doc) {
+    const int64_t base = r.row_ptr[t], end = r.row_ptr[t + 1];
+    int64_t lo = base, hi = end;
+    const int32_t slot = r.skip ? r.hot_slot[t] : -1;
+    if (slot >= 0) {
+        const uint32_t* sk = r.skip + (int64_t)slot * (r.n_sub + 1) + (doc >> r.sub_shift);
+        lo = base + sk[0];
+        hi = base + sk[1];
+    }
+    const int64_t stop = hi;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (r.post[mid].doc < doc) lo = mid + 1; else hi = mid;
+    }
+    return (lo < stop && r.post[lo].doc == doc) ? (int32_t)r.tf[lo] : 0;
+}
+
+__global__ void k_rescore_v3(RescoreIndex r, const int32_t* __restrict__ q_off, PrepView v,
+                             const int64_t* __restrict__ cand_off, int32_t nq, const int32_t* __restrict__ cand,
+                             double* __restrict__ out) {
+    const int64_t c1 = cand_off[nq];
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t doc = cand[c];
+        if (doc < 0) { out[c] = 0.0; continue; }
+        int32_t lo = 0, hi = nq;
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (cand_off[mid] <= c) lo = mid; else hi = mid;
+        }
+        const int32_t q = lo, off = q_off[q], nt = v.o_cnt[q];
+        const int32_t* terms = v.o_terms + off;              // in-corpus terms, query order, duplicates kept
+        int64_t doc_length = 0;
+        for (int32_t i = 0; i < nt; ++i) doc_length += lookup_tf(r, terms[i], (uint32_t)doc);
+        const double norm = __dadd_rn(__dsub_rn(1.0, r.b), __dmul_rn(r.b, __ddiv_rn((double)doc_length, r.avgdl)));
+        const double kn = __dmul_rn(r.k1, norm);
+        double s = 0.0;
+        for (int32_t i = 0; i < nt; ++i) {
+            const int32_t t = terms[i];
+            const double tf = (double)lookup_tf(r, t, (uint32_t)doc);
+            const double num = __dmul_rn(tf, __dadd_rn(r.k1, 1.0));
+            const double den = __dadd_rn(tf, kn);
+            s = __dadd_rn(s, __dmul_rn(r.idf[t], __ddiv_rn(num, den)));
+        }
+        out[c] = s;
+    }
+}
+
+// TF-IDF cosine first stage (cosine_similarity_bm25_reranking.py:72-110,121-126,210-226): doc vector tf*idf,
+// query vector idf per distinct in-corpus term, both L2-normalised.  cos(d,q) = sum_t (tf*idf_t)*idf_t /
+// (||d|| ||q||); ||q|| is constant per query, so ranking needs only w'[d,t] = tf*idf_t^2/||d|| per posting -
+// the same packed-posting layout as BM25, scored by the same kernels.
+__global__ void k_tfidf_norm2(const int64_t* __restrict__ row_ptr, int32_t vocab, int64_t nnz,
+                              const br_posting* __restrict__ post, const uint16_t* __restrict__ tf,
+                              const double* __restrict__ idf, float* __restrict__ norm2) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nnz) return;
+    int32_t lo = 0, hi = vocab;
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (row_ptr[mid] <= j) lo = mid; else hi = mid;
+    }
+    const float e = (float)((double)tf[j] * idf[lo]);        // stored as float32 in the reference's lil_matrix (:88)
+    atomicAdd(norm2 + post[j].doc, e * e);
+}
+__global__ void k_tfidf_weights(const int64_t* __restrict__ row_ptr, int32_t vocab, int64_t nnz,
+                                const br_posting* __restrict__ post, const uint16_t* __restrict__ tf,
+                                const double* __restrict__ idf, const float* __restrict__ norm2,
+                                br_posting* __restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nnz) return;
+    int32_t lo = 0, hi = vocab;
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (row_ptr[mid] <= j) lo = mid; else hi = mid;
+    }
+    const uint32_t d = post[j].doc;
+    const float e = (float)((double)tf[j] * idf[lo]);
+    const float n = sqrtf(norm2[d]);
+    out[j].doc = d;
+    out[j].w = n > 0.f ? e * (float)idf[lo] / n : 0.f;
+}
+__global__ void k_gather_dense(const float* __restrict__ dense, int64_t n_docs, const int64_t* __restrict__ cand_off,
+                               int32_t q_begin, int32_t nq, const int32_t* __restrict__ cand, double* __restrict__ out) {
+    const int64_t c0 = cand_off[q_begin], c1 = cand_off[q_begin + nq];
+    for (int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += (int64_t)gridDim.x * blockDim.x) {
+        int32_t lo = q_begin, hi = q_begin + nq;
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (cand_off[mid] <= c) lo = mid; else hi = mid;
+        }
+        out[c] = (double)dense[(int64_t)(lo - q_begin) * n_docs + cand[c]];
+    }
+}
+
 __global__ void k_scatter_rows(const int32_t* __restrict__ rows, int32_t ns, int32_t k, const int32_t* __restrict__ ids,
                                const double* __restrict__ sc, const int32_t* __restrict__ cnt, int32_t* __restrict__ out_ids,
                                double* __restrict__ out_sc, int32_t* __restrict__ out_cnt) {
@@ -502,7 +603,11 @@ int score_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int3
 // Dense path for queries [q_begin, q_begin + nq) of a prepared batch; results into out_* rows.
 static int topk_dense(br_index* ix, const int32_t* q_off, const PrepView& pv, const int64_t* chunk_start,
                       int32_t q_begin, int32_t nq, int32_t k, int dedup, int positive_only, int32_t* out_ids,
-                      double* out_scores, int32_t* out_counts, cudaStream_t st) {
+                      double* out_scores, int32_t* out_counts, cudaStream_t st, const br_posting* post_table = nullptr) {
+    // post_table != nullptr: score with that weight table and rank by the fp32 dense scores themselves
+    // (TF-IDF cosine stage); otherwise BM25 weights + exact float64 re-score of the candidate band.
+    const bool fp32_rank = post_table != nullptr;
+    const br_posting* post = fp32_rank ? post_table : ix->post;
     const int64_t N = ix->n_docs;
     // queries per pass: dense fp32 rows within ~1 GiB
     int32_t qb = (int32_t)std::max<int64_t>(1, std::min<int64_t>(nq, (1LL << 30) / (4 * N)));
@@ -522,7 +627,7 @@ static int topk_dense(br_index* ix, const int32_t* q_off, const PrepView& pv, co
         const int32_t b0 = q_begin + s, bn = std::min(qb, nq - s);
         BR_CUDA(cudaMemsetAsync(dense, 0, sizeof(float) * (size_t)bn * (size_t)N, st));
         ix->prof_begin(st);
-        k_score_dense<<<kNumSMs * 8, 256, 0, st>>>(ix->post, ix->row_ptr, q_off, pv, chunk_start, b0, bn, dense, N);
+        k_score_dense<<<kNumSMs * 8, 256, 0, st>>>(post, ix->row_ptr, q_off, pv, chunk_start, b0, bn, dense, N);
         BR_CUDA(cudaGetLastError());
         ix->prof_end(st);
         k_select_radix<<<bn, SEL_T, 0, st>>>(dense, N, k, positive_only, sv, b0);
@@ -538,7 +643,13 @@ static int topk_dense(br_index* ix, const int32_t* q_off, const PrepView& pv, co
         double* cand_sc = (double*)(ix->ws_cand.as<char>() + (((size_t)(total + 1) * sizeof(int32_t) + 255) & ~(size_t)255));
         k_emit_cands<<<bn, SEL_T, 0, st>>>(dense, N, positive_only, sv, b0, cand_off, cand);
         BR_CUDA(cudaGetLastError());
-        if (total > 0) BR_TRY(launch_rescore(ix, q_off, pv, dedup, cand_off, b0, bn, cand, cand_sc, total, st));
+        if (total > 0 && fp32_rank) {
+            k_gather_dense<<<(unsigned)std::min<int64_t>((total + 255) / 256, kNumSMs * 16), 256, 0, st>>>(dense, N, cand_off, b0, bn,
+                                                                                                     cand, cand_sc);
+            BR_CUDA(cudaGetLastError());
+        } else if (total > 0) {
+            BR_TRY(launch_rescore(ix, q_off, pv, dedup, cand_off, b0, bn, cand, cand_sc, total, st));
+        }
         BR_TRY(launch_final_select(cand, cand_sc, cand_off, b0, bn, k, positive_only, out_ids, out_scores, out_counts, st));
         // cand_off/h_off are reused by the next pass
         BR_CUDA(cudaStreamSynchronize(st));
@@ -629,6 +740,62 @@ int rescore_docs(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int
     int32_t T;
     BR_TRY(prep_queries(ix, q_terms, q_off, nq, dedup, st, &pv, &chunk_start, &T));
     k_rescore<<<kNumSMs * 16, 128, 0, st>>>(rescore_view(ix), q_off, pv, dedup, cand_off, 0, nq, cand_ids, out_scores);
+    BR_CUDA(cudaGetLastError());
+    return BR_OK;
+}
+
+int enable_tfidf(br_index* ix, cudaStream_t st) {
+    BR_REQUIRE(ix && ix->finalized, BR_ERR_STATE, "br_index_enable_tfidf: call br_index_finalize first");
+    if (ix->post_cos) return BR_OK;
+    BR_CUDA(cudaSetDevice(ix->device));
+    float* norm2 = nullptr;
+    BR_CUDA(cudaMalloc(&norm2, sizeof(float) * (size_t)ix->n_docs));
+    if (cudaMalloc(&ix->post_cos, sizeof(br_posting) * (size_t)std::max<int64_t>(ix->nnz, 1)) != cudaSuccess) {
+        cudaFree(norm2);
+        set_error("br_index_enable_tfidf: out of device memory");
+        return BR_ERR_CUDA;
+    }
+    cudaMemsetAsync(norm2, 0, sizeof(float) * (size_t)ix->n_docs, st);
+    if (ix->nnz > 0) {
+        k_tfidf_norm2<<<blocks_for(ix->nnz, 256), 256, 0, st>>>(ix->row_ptr, ix->vocab, ix->nnz, ix->post, ix->tf, ix->idf, norm2);
+        k_tfidf_weights<<<blocks_for(ix->nnz, 256), 256, 0, st>>>(ix->row_ptr, ix->vocab, ix->nnz, ix->post, ix->tf, ix->idf, norm2,
+                                                                  ix->post_cos);
+    }
+    const cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(norm2);
+    BR_CUDA(e);
+    BR_CUDA(cudaGetLastError());
+    return BR_OK;
+}
+
+int tfidf_topk(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, int32_t k, int32_t* out_ids,
+               double* out_scores, int32_t* out_counts, cudaStream_t st) {
+    BR_REQUIRE(ix && q_terms && q_off && out_ids && out_scores, BR_ERR_INVALID, "br_tfidf_cosine_topk: null pointer");
+    BR_REQUIRE(k >= 1 && k <= BR_MAX_K && nq >= 0, BR_ERR_INVALID, "br_tfidf_cosine_topk: bad sizes");
+    BR_TRY(enable_tfidf(ix, st));
+    if (nq == 0) return BR_OK;
+    ix->stats = br_query_stats{};
+    PrepView pv;
+    int64_t* chunk_start;
+    int32_t T;
+    BR_TRY(prep_queries(ix, q_terms, q_off, nq, 1 /* binary query tf: generate_query_embedding sets, not adds */, st, &pv,
+                        &chunk_start, &T));
+    BR_TRY(topk_dense(ix, q_off, pv, chunk_start, 0, nq, k, 1, 0, out_ids, out_scores, out_counts, st, ix->post_cos));
+    ix->prof_collect();
+    return BR_OK;
+}
+
+int rerank_v3(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, const int32_t* cand_ids,
+              const int64_t* cand_off, double* out_scores, cudaStream_t st) {
+    BR_REQUIRE(ix && q_terms && q_off && cand_ids && cand_off && out_scores, BR_ERR_INVALID, "br_rerank_v3_scores: null pointer");
+    BR_REQUIRE(ix->finalized, BR_ERR_STATE, "br_rerank_v3_scores: call br_index_finalize first");
+    if (nq <= 0) return BR_OK;
+    BR_CUDA(cudaSetDevice(ix->device));
+    PrepView pv;
+    int64_t* chunk_start;
+    int32_t T;
+    BR_TRY(prep_queries(ix, q_terms, q_off, nq, 0, st, &pv, &chunk_start, &T));
+    k_rescore_v3<<<kNumSMs * 16, 128, 0, st>>>(rescore_view(ix), q_off, pv, cand_off, nq, cand_ids, out_scores);
     BR_CUDA(cudaGetLastError());
     return BR_OK;
 }

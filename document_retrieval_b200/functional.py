@@ -10,13 +10,32 @@ import numpy as np
 from .bm25 import BM25
 
 
+# tf_dict (by identity) -> (GPU model, docid list): lets the dict-signature functions of the reference
+# (bm25_score, rank_documents_with_cosine_similarity_and_bm25) find the index their dicts came from.
+_models_by_tf_dict = {}
+
+
+def _model_for(tf_dict, corpus=None):
+    hit = _models_by_tf_dict.get(id(tf_dict))
+    if hit is not None and hit[2] is tf_dict:
+        return hit[0], hit[1]
+    if corpus is None:
+        raise RuntimeError("this tf_dict did not come from compute_tf_df_and_avgdl of this package; pass the corpus "
+                           "DataFrame (rank_documents_with_cosine_similarity_and_bm25) or rebuild it with compute_tf_df_and_avgdl")
+    docs = [str(t).split() for t in corpus["preprocessed_text"]]
+    model = BM25(docs, variant="okapi_no_plus1", dedup_query=False)
+    doc_ids = list(corpus["docid"])
+    _models_by_tf_dict[id(tf_dict)] = (model, doc_ids, tf_dict)
+    return model, doc_ids
+
+
 def compute_tf_df_and_avgdl(corpus_df, path_to_saved_file=None, device=None, return_model=False):
     """cosine_similarity_bm25_reranking.py:129-172 -> ``(tf_dict, df_dict, avgdl, num_docs)`` with
     term-major ``tf_dict = {term: {docid: tf}}``; the four pickles are written as a side effect when
     ``path_to_saved_file`` is given (:163-170).  tf / df / avgdl come from the GPU index build."""
     doc_ids = list(corpus_df["docid"])
     docs = [str(t).split() for t in corpus_df["preprocessed_text"]]
-    model = BM25(docs, variant="okapi_no_plus1", device=device)
+    model = BM25(docs, variant="okapi_no_plus1", dedup_query=False, device=device)
     c = model._export_csr()
     rp = c["row_ptr"]
     tf_dict = {}
@@ -31,9 +50,53 @@ def compute_tf_df_and_avgdl(corpus_df, path_to_saved_file=None, device=None, ret
         for name, obj in (("tf_dict", tf_dict), ("df_dict", df_dict), ("avgdl", avgdl), ("num_docs", num_docs)):
             with open(path_to_saved_file + name + ".pkl", "wb") as f:
                 pickle.dump(obj, f)
+    _models_by_tf_dict.clear()                      # one live corpus at a time, like the reference script
+    _models_by_tf_dict[id(tf_dict)] = (model, doc_ids, tf_dict)
     if return_model:
         return tf_dict, df_dict, avgdl, num_docs, model
     return tf_dict, df_dict, avgdl, num_docs
+
+
+def bm25_score(query_terms, doc_id, tf_dict, idf_dict, avgdl, k1=1.5, b=0.75):
+    """cosine_similarity_bm25_reranking.py:185-195 for one (query, doc) pair -> float.  ``doc_length``
+    is the sum of the query terms' tf in the doc (:187); idf without +1; duplicates counted.  The pair
+    is scored by the CUDA re-rank kernel on the index ``tf_dict`` was derived from (idf_dict / avgdl
+    are that index's own statistics)."""
+    model, doc_ids = _model_for(tf_dict)
+    if (k1, b) != (model.k1, model.b):
+        raise ValueError("k1/b differ from the index the dicts came from")
+    pos = getattr(model, "_docid_pos", None)
+    if pos is None:
+        pos = model._docid_pos = {d: i for i, d in enumerate(doc_ids)}
+    local = pos.get(doc_id, -1)
+    if local < 0:
+        return 0
+    out = model.rerank_scores_v3([list(query_terms)], [[local]])
+    return float(out[0, 0].item())
+
+
+def rank_documents_with_cosine_similarity_and_bm25(corpus, train_query, tf_dict, idf_dict, avgdl, batch_size=400,
+                                                   n_candidates=200, k=10):
+    """cosine_similarity_bm25_reranking.py:198-238 -> ``{query_id: [docid] * 10}``: sparse TF-IDF cosine
+    over the whole corpus -> top-200 (:229) -> bm25_score of the 200 (:232-233) -> stable sort
+    descending, first 10 (:234; ties keep the cosine order).  All three stages run on the GPU; only the
+    final [Q, 200] stable sort uses torch.sort."""
+    import torch
+    model, doc_ids = _model_for(tf_dict, corpus)
+    q_ids = list(train_query["id"])
+    queries = [str(t).split() for t in train_query["preprocessed_query"]]
+    out = {}
+    n_cand = min(n_candidates, model.corpus_size)
+    for s in range(0, len(queries), batch_size):
+        qs = queries[s:s + batch_size]
+        cand, _ = model.tfidf_cosine_top_n_batch(qs, n_cand)
+        v3 = model.rerank_scores_v3(qs, cand)
+        v3 = torch.where(cand >= 0, v3, torch.full_like(v3, float("-inf")))
+        order = torch.sort(v3, dim=1, descending=True, stable=True).indices[:, :k]
+        top = torch.gather(cand, 1, order).cpu().numpy()
+        for qid, row in zip(q_ids[s:s + batch_size], top):
+            out[qid] = [doc_ids[int(d)] for d in row if d >= 0]
+    return out
 
 
 def compute_idf(df_dict, num_docs):

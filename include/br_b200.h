@@ -126,6 +126,28 @@ int br_rescore_docs(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_o
                     int dedup, const int32_t* cand_ids_dev, const int64_t* cand_off_dev,
                     double* out_scores_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Sparse TF-IDF cosine -> BM25 re-rank (implementation 2 of the reference,
+ * cosine_similarity_bm25_reranking.py:198-238).  Needs an index finalised with BR_OKAPI_NO_PLUS1
+ * (compute_idf has no +1, :179).
+ * ------------------------------------------------------------------------------------------- */
+/* Build the second weight table w' = tf*idf^2/||d||, ||d|| = L2 norm of the doc's tf*idf vector
+ * (create_tfidf_embedding :72-110, doc_norms :210-211).  Idempotent. */
+int br_index_enable_tfidf(br_index* ix, void* stream);
+/* First stage: top-k docs by TF-IDF cosine against the query vector "idf per distinct in-corpus term"
+ * (generate_query_embedding :121-126).  out_scores_dev double[nq,k] = fp32 sum_t w'[d,t]
+ * (= cosine * ||q||); order (score desc, doc id asc); zero-score docs fill a short tail in doc order
+ * like the full argsort (:229).  Synchronises `stream`. */
+int br_tfidf_cosine_topk(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq,
+                         int32_t k, int32_t* out_ids_dev, double* out_scores_dev, int32_t* out_counts_dev,
+                         void* stream);
+/* bm25_score (cosine_similarity_bm25_reranking.py:185-195) for explicit (query, doc) pairs, float64:
+ * doc_length = sum of the query terms' tf in the doc (:187), duplicates counted, idf from the index.
+ * Same candidate layout as br_rescore_docs. */
+int br_rerank_v3_scores(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq,
+                        const int32_t* cand_ids_dev, const int64_t* cand_off_dev, double* out_scores_dev,
+                        void* stream);
+
 /* Merge of per-shard top-k lists after the all-gather (no reference analogue: the reference is
  * single-process).  ids_dev int64[n_parts, nq, k] (global ids, -1 = padding), scores_dev
  * double[n_parts, nq, k]; outputs [nq, k] ordered by (score desc, id asc). */

@@ -252,3 +252,51 @@ def test_fused_path_single_query_and_small_batches():
     for nq in (2, 3, 5):
         ids, sc = m.retrieve_top_n_batch((c["q_terms"][:c["q_offsets"][nq]], c["q_offsets"][:nq + 1]), 10)
         assert np.array_equal(ids.cpu().numpy(), oi[:nq]) and np.array_equal(sc.cpu().numpy(), os_[:nq])
+
+
+def test_rerank_v3_and_tfidf_pipeline_match_reference_golden(golden, tmp_path):
+    """bm25_score + rank_documents_with_cosine_similarity_and_bm25 against the fixture made from the
+    unmodified reference (cosine_similarity_bm25_reranking.py:129-238)."""
+    import pandas as pd
+    from document_retrieval_b200 import (bm25_score, compute_idf, compute_tf_df_and_avgdl,
+                                         rank_documents_with_cosine_similarity_and_bm25)
+    g, r = golden("nb_small"), golden("rerank_v3")
+    vocab = int(g["vocab"])
+    docs = synth.to_strings(g["doc_offsets"], g["token_ids"])
+    qs = synth.queries_to_strings(g["q_offsets"], g["q_terms"], vocab)
+    corpus = pd.DataFrame({"docid": [f"d{i}" for i in range(len(docs))], "preprocessed_text": [" ".join(d) for d in docs]})
+    queries = pd.DataFrame({"id": list(range(len(qs))), "preprocessed_query": [" ".join(q) for q in qs]})
+    path = str(tmp_path) + "/"
+    tf_dict, df_dict, avgdl, num_docs, model = compute_tf_df_and_avgdl(corpus, path, return_model=True)
+    import os
+    assert sorted(os.listdir(tmp_path)) == ["avgdl.pkl", "df_dict.pkl", "num_docs.pkl", "tf_dict.pkl"]
+    assert avgdl == float(r["avgdl"]) and num_docs == int(r["num_docs"])
+    for w, v in df_dict.items():
+        assert v == r["df"][int(w[1:])]
+    assert tf_dict[docs[0][0]]["d0"] == docs[0].count(docs[0][0])
+    idf_dict = compute_idf(df_dict, num_docs)
+    for w, v in list(idf_dict.items())[:50]:
+        assert v == r["idf"][int(w[1:])]                       # np.log, same ufunc as the reference
+    # bm25_score on explicit pairs (batched through the same kernel)
+    nq = len(qs)
+    got = model.rerank_scores_v3(qs, r["pair_docs"].astype(np.int32)).cpu().numpy()
+    np.testing.assert_allclose(got, r["pair_scores"], rtol=1e-12, atol=1e-15)
+    one = bm25_score(qs[0], f"d{int(r['pair_docs'][0, 0])}", tf_dict, idf_dict, avgdl)
+    np.testing.assert_allclose(one, r["pair_scores"][0, 0], rtol=1e-12, atol=1e-15)
+    # full pipeline: compare the ranks whose order is defined in the reference (strictly positive,
+    # pairwise distinct re-rank scores; the rest depends on argsort's order among equal cosines)
+    ranked = rank_documents_with_cosine_similarity_and_bm25(corpus, queries, tf_dict, idf_dict, avgdl, batch_size=16)
+    ix = orc.build_index(g["doc_offsets"], g["token_ids"], vocab)
+    checked = 0
+    for i in range(nq):
+        ref = [int(d) for d in r["top10"][i] if d >= 0]
+        mine = [int(d[1:]) for d in ranked[i]]
+        sc = [orc.bm25_score_rerank(ix, g["q_terms"][g["q_offsets"][i]:g["q_offsets"][i + 1]], d, r["idf"], float(r["avgdl"]))
+              for d in ref]
+        for j, d in enumerate(ref):
+            well_defined = sc[j] > 1e-9 and all(abs(sc[j] - s2) > 1e-9 * abs(sc[j]) for jj, s2 in enumerate(sc) if jj != j)
+            if not well_defined:
+                break
+            assert mine[j] == d, (i, j, mine, ref)
+            checked += 1
+    assert checked > 100
