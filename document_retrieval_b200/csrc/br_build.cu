@@ -15,6 +15,8 @@
 //   k_skip           per hot term: offset of the first posting of every 2^sub_shift-doc sub-range
 #include <math.h>
 
+#include <algorithm>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "br_common.cuh"
@@ -178,7 +180,7 @@ void index_free(br_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     cudaFree(ix->row_ptr); cudaFree(ix->post); cudaFree(ix->post_cos); cudaFree(ix->tf); cudaFree(ix->dl); cudaFree(ix->df);
-    cudaFree(ix->idf); cudaFree(ix->hot_slot); cudaFree(ix->skip);
+    cudaFree(ix->idf); cudaFree(ix->hot_slot); cudaFree(ix->skip); cudaFree(ix->sig_bit);
     ix->ws_prep.release(); ix->ws_dense.release(); ix->ws_sel.release(); ix->ws_cand.release();
     ix->ws_misc.release(); ix->ws_tile.release();
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
@@ -399,6 +401,21 @@ int index_finalize(br_index* ix, double k1, double b, int variant, double n_stat
             BR_CUDA(cudaStreamSynchronize(st));
             cudaFree(d_hot);
         }
+    }
+    if (!ix->sig_bit) {
+        // the 32 most frequent terms: queries are grouped by which of them they contain (br_tile.cu)
+        std::vector<int32_t> order(V);
+        for (size_t t = 0; t < V; ++t) order[t] = (int32_t)t;
+        const size_t top = std::min<size_t>(32, V);
+        std::partial_sort(order.begin(), order.begin() + top, order.end(), [&](int32_t x, int32_t y) {
+            return ix->h_df[(size_t)x] != ix->h_df[(size_t)y] ? ix->h_df[(size_t)x] > ix->h_df[(size_t)y] : x < y;
+        });
+        std::vector<int8_t> bit(V, (int8_t)-1);
+        for (size_t r = 0; r < top; ++r)
+            if (ix->h_df[(size_t)order[r]] > 0) bit[(size_t)order[r]] = (int8_t)r;
+        BR_CUDA(cudaMalloc(&ix->sig_bit, V));
+        BR_CUDA(cudaMemcpyAsync(ix->sig_bit, bit.data(), V, cudaMemcpyHostToDevice, st));
+        BR_CUDA(cudaStreamSynchronize(st));
     }
     BR_CUDA(cudaStreamSynchronize(st));
     ix->finalized = true;

@@ -95,6 +95,7 @@ struct br_index {
     int32_t n_sub = 0, n_hot = 0;
     int32_t* hot_slot = nullptr;    // [V]
     uint32_t* skip = nullptr;       // [n_hot, n_sub+1]
+    int8_t* sig_bit = nullptr;      // [V] rank (0 = largest df) among the 32 most frequent terms, -1 otherwise
 
     // host mirrors
     std::vector<uint32_t> h_df;     // shard-local

@@ -29,7 +29,8 @@ namespace br {
 constexpr int SCORE_CHUNK = 8192;
 
 __global__ void k_prep_queries(const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_off, int32_t nq,
-                               int32_t vocab, const int64_t* __restrict__ row_ptr, int dedup, PrepView v) {
+                               int32_t vocab, const int64_t* __restrict__ row_ptr, const int8_t* __restrict__ sig_bit, int dedup,
+                               PrepView v) {
     const int lane = threadIdx.x & 31;
     const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (q >= nq) return;
@@ -64,11 +65,14 @@ __global__ void k_prep_queries(const int32_t* __restrict__ q_terms, const int32_
     __syncwarp();
     // phase 3: rank among the distinct terms -> ascending unique list
     int32_t n_uniq = 0;
+    uint32_t sig = 0;
     for (int32_t base = 0; base < n_valid; base += 32) {
         const int32_t i = base + lane;
         const bool first = i < n_valid && v.tmp[off + i] > 0;
         if (first) {
             const int32_t t = v.o_terms[off + i];
+            const int sb = sig_bit ? sig_bit[t] : -1;
+            if (sb >= 0) sig |= 1u << (31 - sb);
             int32_t rank = 0;
             for (int32_t j = 0; j < n_valid; ++j) rank += (v.tmp[off + j] > 0 && v.o_terms[off + j] < t) ? 1 : 0;
             v.u_terms[off + rank] = t;
@@ -77,7 +81,9 @@ __global__ void k_prep_queries(const int32_t* __restrict__ q_terms, const int32_
         n_uniq += __popc(__ballot_sync(0xffffffffu, first));
     }
     __syncwarp();
+    for (int o = 16; o > 0; o >>= 1) sig |= __shfl_xor_sync(0xffffffffu, sig, o);
     if (lane == 0) {
+        v.sig[q] = sig;
         int64_t cum = 0;
         for (int32_t i = 0; i < n_uniq; ++i) {
             const int32_t t = v.u_terms[off + i];
@@ -565,14 +571,14 @@ static int prep_queries(br_index* ix, const int32_t* q_terms, const int32_t* q_o
     auto carve = [&](size_t n) { size_t o = bytes; bytes += (n + 255) & ~(size_t)255; return o; };
     const size_t o_ut = carve(Tn * 4), o_um = carve(Tn * 4), o_uc = carve(Tn * 8), o_un = carve(Q * 4),
                  o_ot = carve(Tn * 4), o_on = carve(Q * 4), o_P = carve(Q * 8), o_nc = carve(Q * 4),
-                 o_tmp = carve(Tn * 4), o_cs = carve(Q * 8);
+                 o_tmp = carve(Tn * 4), o_cs = carve(Q * 8), o_sig = carve(Q * 4);
     BR_TRY(ix->ws_prep.reserve(bytes));
     char* p = ix->ws_prep.as<char>();
     pv->u_terms = (int32_t*)(p + o_ut); pv->u_mult = (int32_t*)(p + o_um); pv->u_cum = (int64_t*)(p + o_uc);
     pv->u_cnt = (int32_t*)(p + o_un); pv->o_terms = (int32_t*)(p + o_ot); pv->o_cnt = (int32_t*)(p + o_on);
-    pv->P = (int64_t*)(p + o_P); pv->n_chunks = (uint32_t*)(p + o_nc); pv->tmp = (int32_t*)(p + o_tmp);
+    pv->P = (int64_t*)(p + o_P); pv->n_chunks = (uint32_t*)(p + o_nc); pv->tmp = (int32_t*)(p + o_tmp); pv->sig = (uint32_t*)(p + o_sig);
     *chunk_start = (int64_t*)(p + o_cs);
-    k_prep_queries<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(q_terms, q_off, nq, ix->vocab, ix->row_ptr, dedup, *pv);
+    k_prep_queries<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(q_terms, q_off, nq, ix->vocab, ix->row_ptr, ix->sig_bit, dedup, *pv);
     BR_CUDA(cudaGetLastError());
     k_exscan<uint32_t><<<1, 1024, 0, st>>>(pv->n_chunks, nq, *chunk_start);
     BR_CUDA(cudaGetLastError());

@@ -15,6 +15,7 @@ struct PrepView {
     int64_t* P;         // [nq] total postings of the unique terms
     uint32_t* n_chunks; // [nq]
     int32_t* tmp;       // [T]
+    uint32_t* sig;      // [nq] bit (31 - r) set when the query contains the r-th most frequent term
 };
 
 

@@ -28,6 +28,8 @@
 #include <stdio.h>
 #include <time.h>
 
+#include <algorithm>
+
 #include "br_common.cuh"
 #include "br_kernels.cuh"
 #include "br_query.cuh"
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
                                                    const int64_t* __restrict__ row_ptr, int32_t nq, int G, int umax,
                                                    TileEntry* __restrict__ entries, int32_t* __restrict__ n_entries,
                                                    int32_t* __restrict__ elig, unsigned long long* __restrict__ cold_total,
-                                                   int64_t dense_df_min) {
+                                                   int64_t dense_df_min, const int32_t* __restrict__ perm) {
     __shared__ int32_t s_term[4][256];
     __shared__ uint8_t s_q[4][256], s_m[4][256];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
@@ -73,8 +75,8 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
     int n = 0;
     unsigned long long cold_sum = 0;
     for (int i = 0; i < G; ++i) {
-        const int q = g * G + i;
-        if (q >= nq) break;
+        if (g * G + i >= nq) break;
+        const int q = perm[g * G + i];
         const int32_t off = q_off[q], nu = pv.u_cnt[q];
         int hot = 0, bad = 0;
         unsigned long long cold = 0;
@@ -147,14 +149,15 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
 template <bool SCATTER>
 __global__ void k_cold_pass(PrepView pv, const int32_t* __restrict__ q_off, const int32_t* __restrict__ hot_slot,
                             const int64_t* __restrict__ row_ptr, const br_posting* __restrict__ post, int32_t nq, int G,
-                            int n_groups, const int32_t* __restrict__ elig, uint32_t* __restrict__ counter,
-                            ColdEntry* __restrict__ out) {
+                            int n_groups, const int32_t* __restrict__ elig, const int32_t* __restrict__ inv_perm,
+                            uint32_t* __restrict__ counter, ColdEntry* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (q >= nq || !elig[q]) return;
     const int32_t off = q_off[q], nu = pv.u_cnt[q];
-    const int g = q / G;
-    const uint32_t slot = (uint32_t)(q - g * G);
+    const int pos = inv_perm[q];
+    const int g = pos / G;
+    const uint32_t slot = (uint32_t)(pos - g * G);
     for (int j = 0; j < nu; ++j) {
         const int32_t t = pv.u_terms[off + j];
         if (hot_slot[t] >= 0) continue;
@@ -286,6 +289,7 @@ struct TileArgs {
     int K;
     int tile0;
     int has_mult;                 // 0: every multiplicity is 1 (set(query) semantics)
+    const int32_t* perm;          // group g, slot i -> query perm[g*G+i] (queries sorted by frequent-term signature)
 };
 
 template <int G>
@@ -495,8 +499,9 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
     const uint32_t n_valid = (uint32_t)min((int64_t)TILE_S, a.n_docs - (int64_t)doc0);
 #pragma unroll 1
     for (int q = 0; q < G; ++q) {
-        const int qi = g * G + q;
-        if (qi >= a.nq || !a.elig[qi]) continue;
+        if (g * G + q >= a.nq) continue;
+        const int qi = a.perm[g * G + q];
+        if (!a.elig[qi]) continue;
         float v[TILE_S / 32];
         float mx = 0.f;
 #pragma unroll
@@ -692,7 +697,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
                  o_cur = carve(4 * (size_t)(n_buckets + 1)), o_part = carve(4 * (size_t)(n_scan_blocks + 1)),
                  o_poff = carve(8 * (size_t)(n_scan_blocks + 2)),
                  o_cand = carve(4 * (size_t)nq * TILE_CAP), o_ch = carve(4 * (size_t)nq * TILE_CAP),
-                 o_cs = carve(8 * (size_t)nq * TILE_CAP);
+                 o_cs = carve(8 * (size_t)nq * TILE_CAP), o_perm = carve(4 * Q), o_inv = carve(4 * Q);
     BR_TRY(ix->ws_tile.reserve(bytes));
     char* p = ix->ws_tile.as<char>();
     TileEntry* entries = (TileEntry*)(p + o_ent);
@@ -714,13 +719,25 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     int32_t* cand = (int32_t*)(p + o_cand);
     float* cand_h = (float*)(p + o_ch);
     double* cand_sc = (double*)(p + o_cs);
+    int32_t* perm = (int32_t*)(p + o_perm);
+    int32_t* inv_perm = (int32_t*)(p + o_inv);
 
+    // group queries that share the most frequent terms: sort by signature (bit 31 = most frequent term)
+    std::vector<uint32_t> h_sig((size_t)nq);
+    BR_CUDA(cudaMemcpyAsync(h_sig.data(), pv.sig, 4 * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaStreamSynchronize(st));
+    std::vector<int32_t> h_perm((size_t)nq), h_inv((size_t)nq);
+    for (int32_t q = 0; q < nq; ++q) h_perm[(size_t)q] = q;
+    std::stable_sort(h_perm.begin(), h_perm.end(), [&](int32_t x, int32_t y) { return h_sig[(size_t)x] > h_sig[(size_t)y]; });
+    for (int32_t i = 0; i < nq; ++i) h_inv[(size_t)h_perm[(size_t)i]] = i;
+    BR_CUDA(cudaMemcpyAsync(perm, h_perm.data(), 4 * (size_t)nq, cudaMemcpyHostToDevice, st));
+    BR_CUDA(cudaMemcpyAsync(inv_perm, h_inv.data(), 4 * (size_t)nq, cudaMemcpyHostToDevice, st));
     // one memset covers thr / cand_cnt / prev_cnt / overflow (contiguous carve)
     BR_CUDA(cudaMemsetAsync(p + o_thr, 0, o_off - o_thr, st));
     BR_CUDA(cudaMemsetAsync(cold_total, 0, 16, st));
     BR_CUDA(cudaMemsetAsync(cand, 0xFF, 4 * (size_t)nq * TILE_CAP, st));
     k_tile_prep<<<(n_groups + 3) / 4, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, nq, G, umax, entries, n_entries,
-                                                    elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)TILE_DENSE_MIN) >> TILE_SHIFT));
+                                                    elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)TILE_DENSE_MIN) >> TILE_SHIFT), perm);
     BR_CUDA(cudaGetLastError());
     k_fill_offsets<<<blocks_for(nq + 1, 256), 256, 0, st>>>(cand_off, nq, TILE_CAP);
     BR_CUDA(cudaGetLastError());
@@ -738,8 +755,8 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
         ColdEntry* d_cold = ix->ws_misc.as<ColdEntry>();
         BR_CUDA(cudaMemsetAsync(b_cnt, 0, 4 * (size_t)(n_buckets + 1), st));
         const unsigned qb = blocks_for((int64_t)nq * 32, 128);
-        k_cold_pass<false><<<qb, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, ix->post, nq, G, n_groups, elig, b_cnt,
-                                              nullptr);
+        k_cold_pass<false><<<qb, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, ix->post, nq, G, n_groups, elig, inv_perm,
+                                              b_cnt, nullptr);
         BR_CUDA(cudaGetLastError());
         k_scan_reduce<<<(unsigned)n_scan_blocks, SCAN_T, 0, st>>>(b_cnt, n_buckets, part);
         BR_CUDA(cudaGetLastError());
@@ -747,8 +764,8 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
         BR_CUDA(cudaGetLastError());
         k_scan_apply<<<(unsigned)n_scan_blocks, SCAN_T, 0, st>>>(b_cnt, n_buckets, part_off, b_off, b_cur);
         BR_CUDA(cudaGetLastError());
-        k_cold_pass<true><<<qb, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, ix->post, nq, G, n_groups, elig, b_cur,
-                                             d_cold);
+        k_cold_pass<true><<<qb, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, ix->post, nq, G, n_groups, elig, inv_perm,
+                                             b_cur, d_cold);
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 5;
         cold = d_cold;
@@ -757,7 +774,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
 
     stage_mark("cold_sort", st);
     TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
-               cold_off, cold, thr, cand_cnt, cand, cand_h, (int)k, 0, dedup ? 0 : 1};
+               cold_off, cold, thr, cand_cnt, cand, cand_h, (int)k, 0, dedup ? 0 : 1, perm};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
                                                                             sizeof(uint32_t) * (TILE_W + 1) + sizeof(float4));
     switch (G) {
