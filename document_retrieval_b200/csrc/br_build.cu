@@ -153,6 +153,18 @@ __global__ void k_skip(const int64_t* __restrict__ row_ptr, const br_posting* __
     skip[i] = lo;
 }
 
+__global__ void k_rows_fill(const int64_t* __restrict__ row_ptr, const br_posting* __restrict__ post,
+                            const int32_t* __restrict__ row_terms, int32_t n_rows, int64_t n_pad, float* __restrict__ rows) {
+    const int r = blockIdx.y;
+    if (r >= n_rows) return;
+    const int32_t t = row_terms[r];
+    const int64_t lo = row_ptr[t], n = row_ptr[t + 1] - lo;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const br_posting p = post[lo + i];
+        rows[(int64_t)r * n_pad + p.doc] = p.w;
+    }
+}
+
 __global__ void k_import(const int32_t* __restrict__ doc, const int32_t* __restrict__ tf_in, int64_t nnz,
                          br_posting* __restrict__ post, uint16_t* __restrict__ tf, int* __restrict__ bad) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -180,7 +192,7 @@ void index_free(br_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     cudaFree(ix->row_ptr); cudaFree(ix->post); cudaFree(ix->post_cos); cudaFree(ix->tf); cudaFree(ix->dl); cudaFree(ix->df);
-    cudaFree(ix->idf); cudaFree(ix->hot_slot); cudaFree(ix->skip); cudaFree(ix->sig_bit);
+    cudaFree(ix->idf); cudaFree(ix->hot_slot); cudaFree(ix->skip); cudaFree(ix->sig_bit); cudaFree(ix->dense_rows); cudaFree(ix->row_slot);
     ix->ws_prep.release(); ix->ws_dense.release(); ix->ws_sel.release(); ix->ws_cand.release();
     ix->ws_misc.release(); ix->ws_tile.release();
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
@@ -401,6 +413,35 @@ int index_finalize(br_index* ix, double k1, double b, int variant, double n_stat
             BR_CUDA(cudaStreamSynchronize(st));
             cudaFree(d_hot);
         }
+    }
+    {   // dense rows (rebuilt at every finalize: they hold the weights)
+        double frac = 0.2;
+        if (const char* e = getenv("BR_ROW_FRAC")) { double v = atof(e); if (v > 0) frac = v; }
+        std::vector<int32_t> cand_terms;
+        for (size_t t = 0; t < V; ++t)
+            if (ix->n_hot > 0 && (double)ix->h_df[t] >= frac * (double)ix->n_docs && ix->h_df[t] > 0) cand_terms.push_back((int32_t)t);
+        std::sort(cand_terms.begin(), cand_terms.end(), [&](int32_t x, int32_t y) { return ix->h_df[(size_t)x] > ix->h_df[(size_t)y]; });
+        if (cand_terms.size() > 32) cand_terms.resize(32);
+        cudaFree(ix->dense_rows); ix->dense_rows = nullptr;
+        ix->n_rows = (int32_t)cand_terms.size();
+        ix->n_pad = ((ix->n_docs + 4095) / 4096) * 4096;
+        std::vector<int8_t> slot(V, (int8_t)-1);
+        for (size_t r = 0; r < cand_terms.size(); ++r) slot[(size_t)cand_terms[r]] = (int8_t)r;
+        if (!ix->row_slot) BR_CUDA(cudaMalloc(&ix->row_slot, V));
+        BR_CUDA(cudaMemcpyAsync(ix->row_slot, slot.data(), V, cudaMemcpyHostToDevice, st));
+        if (ix->n_rows > 0) {
+            int32_t* d_terms = nullptr;
+            BR_CUDA(cudaMalloc(&ix->dense_rows, sizeof(float) * (size_t)ix->n_rows * (size_t)ix->n_pad));
+            BR_CUDA(cudaMalloc(&d_terms, sizeof(int32_t) * (size_t)ix->n_rows));
+            BR_CUDA(cudaMemsetAsync(ix->dense_rows, 0, sizeof(float) * (size_t)ix->n_rows * (size_t)ix->n_pad, st));
+            BR_CUDA(cudaMemcpyAsync(d_terms, cand_terms.data(), sizeof(int32_t) * (size_t)ix->n_rows, cudaMemcpyHostToDevice, st));
+            k_rows_fill<<<dim3(kNumSMs * 4, (unsigned)ix->n_rows), 256, 0, st>>>(ix->row_ptr, ix->post, d_terms, ix->n_rows, ix->n_pad,
+                                                                              ix->dense_rows);
+            BR_CUDA(cudaGetLastError());
+            BR_CUDA(cudaStreamSynchronize(st));
+            cudaFree(d_terms);
+        }
+        BR_CUDA(cudaStreamSynchronize(st));
     }
     if (!ix->sig_bit) {
         // the 32 most frequent terms: queries are grouped by which of them they contain (br_tile.cu)

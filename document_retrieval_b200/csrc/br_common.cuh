@@ -95,6 +95,12 @@ struct br_index {
     int32_t n_sub = 0, n_hot = 0;
     int32_t* hot_slot = nullptr;    // [V]
     uint32_t* skip = nullptr;       // [n_hot, n_sub+1]
+    // dense rows: for the few terms present in >= ~20% of the docs, w[row][doc] as plain fp32 rows (0 where the doc
+    // lacks the term); the tiled scorer initialises its accumulators from them instead of walking their postings
+    float* dense_rows = nullptr;    // [n_rows, n_pad]
+    int8_t* row_slot = nullptr;     // [V] row index or -1
+    int32_t n_rows = 0;
+    int64_t n_pad = 0;
     int8_t* sig_bit = nullptr;      // [V] rank (0 = largest df) among the 32 most frequent terms, -1 otherwise
 
     // host mirrors

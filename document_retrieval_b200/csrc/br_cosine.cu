@@ -352,43 +352,62 @@ __global__ void k_cos_output(const int32_t* __restrict__ cand, const float* __re
 // ------------------------------------------------------------------------------------------
 // candidate re-rank: query q against its own candidate rows
 // ------------------------------------------------------------------------------------------
+// One CTA per query: each warp keeps the query row in registers (d <= 1024: 4 x 16 B per lane) and walks the
+// candidates warp, warp+8, ... four at a time (12-16 independent 128-bit loads in flight per lane).
+template <int NV>   // 16-byte vectors per lane = ceil(d / 256)
 __global__ void __launch_bounds__(256) k_cosine_rerank(const __nv_bfloat16* __restrict__ docs,
                                                        const float* __restrict__ inv_nd, int64_t n_docs, int32_t d,
                                                        const __nv_bfloat16* __restrict__ queries,
                                                        const float* __restrict__ inv_nq, const int32_t* __restrict__ cand,
-                                                       int64_t n_pairs, int32_t c, float* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t pair = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (pair >= n_pairs) return;
-    const int32_t q = (int32_t)(pair / c);
-    const int32_t doc = cand[pair];
-    if (doc < 0 || doc >= n_docs) {
-        if (lane == 0) out[pair] = -CUDART_INF_F;
-        return;
-    }
-    const uint4* pd = reinterpret_cast<const uint4*>(docs + (int64_t)doc * d);
+                                                       int32_t c, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x;
+    const int nvec = d / 8;
     const uint4* pq = reinterpret_cast<const uint4*>(queries + (int64_t)q * d);
-    float s = 0.f, nn = 0.f;
-    for (int i = lane; i < d / 8; i += 32) {
-        const uint4 a = __ldg(pd + i), b = __ldg(pq + i);
-        const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+    uint4 qv[NV];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float a0 = __uint_as_float(wa[j] << 16), a1 = __uint_as_float(wa[j] & 0xffff0000u);
-            const float b0 = __uint_as_float(wb[j] << 16), b1 = __uint_as_float(wb[j] & 0xffff0000u);
-            s = fmaf(a0, b0, s);
-            s = fmaf(a1, b1, s);
-            nn = fmaf(a0, a0, nn);
-            nn = fmaf(a1, a1, nn);
+    for (int i = 0; i < NV; ++i) qv[i] = lane + 32 * i < nvec ? __ldg(pq + lane + 32 * i) : make_uint4(0, 0, 0, 0);
+    const float iq = inv_nq[q];
+    const int32_t* cq = cand + (int64_t)q * c;
+    for (int j0 = warp * 4; j0 < c; j0 += 32) {
+        int32_t doc[4];
+        uint4 dv[4][NV];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            doc[x] = j0 + x < c ? cq[j0 + x] : -1;
+            const bool ok = doc[x] >= 0 && doc[x] < n_docs;
+            const uint4* pd = reinterpret_cast<const uint4*>(docs + (int64_t)(ok ? doc[x] : 0) * d);
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                dv[x][i] = ok && lane + 32 * i < nvec ? __ldg(pd + lane + 32 * i) : make_uint4(0, 0, 0, 0);
         }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        nn += __shfl_xor_sync(0xffffffffu, nn, o);
-    }
-    if (lane == 0) {
-        const float id = inv_nd ? inv_nd[doc] : 1.0f / (sqrtf(nn) + COS_EPS);
-        out[pair] = s * id * inv_nq[q];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            float s = 0.f, nn = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const uint32_t wa[4] = {dv[x][i].x, dv[x][i].y, dv[x][i].z, dv[x][i].w};
+                const uint32_t wb[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float a0 = __uint_as_float(wa[e] << 16), a1 = __uint_as_float(wa[e] & 0xffff0000u);
+                    const float b0 = __uint_as_float(wb[e] << 16), b1 = __uint_as_float(wb[e] & 0xffff0000u);
+                    s = fmaf(a0, b0, s);
+                    s = fmaf(a1, b1, s);
+                    nn = fmaf(a0, a0, nn);
+                    nn = fmaf(a1, a1, nn);
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                nn += __shfl_xor_sync(0xffffffffu, nn, o);
+            }
+            if (lane == 0 && j0 + x < c) {
+                const bool ok = doc[x] >= 0 && doc[x] < n_docs;
+                const float id = !ok ? 0.f : (inv_nd ? inv_nd[doc[x]] : 1.0f / (sqrtf(nn) + COS_EPS));
+                out[(int64_t)q * c + j0 + x] = ok ? s * id * iq : -CUDART_INF_F;
+            }
+        }
     }
 }
 
@@ -509,9 +528,16 @@ int cosine_rerank(const void* docs, const float* inv_nd, int64_t n_docs, int32_t
     BR_TRY(b_inq.alloc(4 * (size_t)nq)); BR_TRY(b_s.alloc(4 * (size_t)n_pairs)); BR_TRY(b_s64.alloc(8 * (size_t)n_pairs));
     BR_TRY(b_off.alloc(8 * ((size_t)nq + 1))); BR_TRY(b_o64.alloc(8 * (size_t)nq * k));
     BR_TRY(row_inv_norms(queries, nq, d, (float*)b_inq.p, st));
-    k_cosine_rerank<<<blocks_for(n_pairs * 32, 256), 256, 0, st>>>((const __nv_bfloat16*)docs, inv_nd, n_docs, d,
-                                                                   (const __nv_bfloat16*)queries, (const float*)b_inq.p, cand,
-                                                                   n_pairs, c, (float*)b_s.p);
+    BR_REQUIRE(d <= 1024, BR_ERR_UNSUPPORTED, "br_cosine_rerank: embedding dim > 1024");
+    const int nv = (d / 8 + 31) / 32;
+    auto launch = [&](auto kern) {
+        kern<<<nq, 256, 0, st>>>((const __nv_bfloat16*)docs, inv_nd, n_docs, d, (const __nv_bfloat16*)queries,
+                                 (const float*)b_inq.p, cand, c, (float*)b_s.p);
+    };
+    if (nv <= 1) launch(k_cosine_rerank<1>);
+    else if (nv == 2) launch(k_cosine_rerank<2>);
+    else if (nv == 3) launch(k_cosine_rerank<3>);
+    else launch(k_cosine_rerank<4>);
     BR_CUDA(cudaGetLastError());
     k_f32_to_f64<<<blocks_for(n_pairs, 256), 256, 0, st>>>((const float*)b_s.p, n_pairs, (double*)b_s64.p);
     BR_CUDA(cudaGetLastError());

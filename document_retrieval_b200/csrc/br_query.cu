@@ -332,11 +332,11 @@ __device__ __forceinline__ bool fs_before(const FsKey& a, const FsKey& b) {
     return a.s > b.s || (a.s == b.s && a.id < b.id);
 }
 
-__device__ void fs_sort(FsKey* keys) {  // bitonic, FS_N elements, "before" order ascending in index
-    for (int size = 2; size <= FS_N; size <<= 1) {
+__device__ void fs_sort(FsKey* keys, int n) {  // bitonic over keys[0, n), n a power of two <= FS_N
+    for (int size = 2; size <= n; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
-            for (int i = threadIdx.x; i < FS_N / 2; i += FS_T) {
+            for (int i = threadIdx.x; i < n / 2; i += FS_T) {
                 const int a = 2 * i - (i & (stride - 1));
                 const int b = a + stride;
                 const bool up = (a & size) == 0;
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(FS_T) k_final_select(const IdT* __restrict__ i
                                                        int32_t n_parts, int64_t part_stride, int32_t fixed_cnt,
                                                        int32_t k, int64_t id_base, int positive_only,
                                                        IdT* __restrict__ out_ids, double* __restrict__ out_sc,
-                                                       int32_t* __restrict__ out_cnt) {
+                                                       int32_t* __restrict__ out_cnt, const int32_t* __restrict__ cnt_hint) {
     __shared__ FsKey keys[FS_N];
     __shared__ uint32_t s_flag[FS_N];
     const int q = q_begin + blockIdx.x;
@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(FS_T) k_final_select(const IdT* __restrict__ i
         __syncthreads();
         while (filled < FS_N && part < n_parts) {
             const int64_t base = cand_off ? cand_off[q] : (int64_t)part * part_stride + (int64_t)q * fixed_cnt;
-            const int64_t cnt = cand_off ? cand_off[q + 1] - cand_off[q] : fixed_cnt;
+            int64_t cnt = cand_off ? cand_off[q + 1] - cand_off[q] : fixed_cnt;
+            if (cnt_hint) cnt = min(cnt, (int64_t)max(cnt_hint[q], 0));      // only the head of the region is in use
             const int64_t take = min((int64_t)(FS_N - filled), cnt - pos);
             for (int64_t i = threadIdx.x; i < take; i += FS_T) {
                 const IdT id = ids[base + pos + i];
@@ -383,8 +384,10 @@ __global__ void __launch_bounds__(FS_T) k_final_select(const IdT* __restrict__ i
             if (pos >= cnt) { ++part; pos = 0; }
         }
         done = part >= n_parts;
+        int n_sort = 64;                                   // smallest power of two covering the filled part
+        while (n_sort < filled) n_sort <<= 1;
         for (int i = filled + threadIdx.x; i < FS_N; i += FS_T) keys[i] = pad;
-        fs_sort(keys);
+        fs_sort(keys, n_sort);
         // unique-compact the head into keys[0, k)
         for (int i = threadIdx.x; i < FS_N; i += FS_T)
             s_flag[i] = (keys[i].id != INT64_MAX && (i == 0 || keys[i].id != keys[i - 1].id ||
@@ -521,6 +524,22 @@ __global__ void k_gather_dense(const float* __restrict__ dense, int64_t n_docs, 
     }
 }
 
+// fused path: query q owns the fixed-stride region [q*stride, (q+1)*stride), only its first cnt[q] slots are live
+__global__ void __launch_bounds__(64) k_rescore_heads(RescoreIndex r, const int32_t* __restrict__ q_off, PrepView v, int dedup,
+                                                      int32_t stride, const int32_t* __restrict__ cnt,
+                                                      const int32_t* __restrict__ cand, double* __restrict__ cand_score) {
+    const int q = blockIdx.x;
+    const int n = min(cnt[q], stride);
+    const int32_t off = q_off[q];
+    const int32_t* terms = dedup ? v.u_terms + off : v.o_terms + off;
+    const int32_t nt = dedup ? v.u_cnt[q] : v.o_cnt[q];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int64_t c = (int64_t)q * stride + i;
+        const int32_t doc = cand[c];
+        if (doc >= 0) cand_score[c] = rescore_one(r, terms, nt, (uint32_t)doc);
+    }
+}
+
 __global__ void k_scatter_rows(const int32_t* __restrict__ rows, int32_t ns, int32_t k, const int32_t* __restrict__ ids,
                                const double* __restrict__ sc, const int32_t* __restrict__ cnt, int32_t* __restrict__ out_ids,
                                double* __restrict__ out_sc, int32_t* __restrict__ out_cnt) {
@@ -550,11 +569,18 @@ int launch_rescore(br_index* ix, const int32_t* q_off, const PrepView& pv, int d
     return BR_OK;
 }
 
+int launch_rescore_heads(br_index* ix, const int32_t* q_off, const PrepView& pv, int dedup, int32_t nq, int32_t stride,
+                         const int32_t* cnt, const int32_t* cand, double* cand_score, cudaStream_t st) {
+    k_rescore_heads<<<nq, 64, 0, st>>>(rescore_view(ix), q_off, pv, dedup, stride, cnt, cand, cand_score);
+    BR_CUDA(cudaGetLastError());
+    return BR_OK;
+}
+
 int launch_final_select(const int32_t* cand, const double* cand_score, const int64_t* cand_off, int32_t q_begin,
                         int32_t nq, int32_t k, int positive_only, int32_t* out_ids, double* out_scores,
-                        int32_t* out_counts, cudaStream_t st) {
+                        int32_t* out_counts, cudaStream_t st, const int32_t* cnt_hint) {
     k_final_select<int32_t><<<nq, FS_T, 0, st>>>(cand, cand_score, cand_off, q_begin, 1, 0, 0, k, 0, positive_only, out_ids,
-                                                 out_scores, out_counts);
+                                                 out_scores, out_counts, cnt_hint);
     BR_CUDA(cudaGetLastError());
     return BR_OK;
 }
@@ -678,7 +704,9 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
     PrepView pv;
     int64_t* chunk_start;
     int32_t T;
+    stage_mark("batch_enter", st);
     BR_TRY(prep_queries(ix, q_terms, q_off, nq, dedup, st, &pv, &chunk_start, &T));
+    stage_mark("prep", st);
     // algorithmic bytes of this batch: 8 B per posting of every distinct in-vocab query term
     std::vector<int64_t> hP((size_t)nq);
     BR_CUDA(cudaMemcpyAsync(hP.data(), pv.P, sizeof(int64_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
@@ -732,6 +760,7 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
     for (int64_t v : hP) sum += v;
     ix->stats.postings_bytes = 8 * sum;
     ix->prof_collect();
+    stage_mark("batch_exit", st);
     return BR_OK;
 }
 
@@ -812,7 +841,7 @@ int topk_merge(const int64_t* ids, const double* scores, int32_t n_parts, int32_
     BR_REQUIRE(n_parts >= 1 && nq >= 0 && k >= 1 && k <= BR_MAX_K, BR_ERR_INVALID, "br_topk_merge: bad sizes");
     if (nq == 0) return BR_OK;
     k_final_select<int64_t><<<nq, FS_T, 0, st>>>(ids, scores, nullptr, 0, n_parts, (int64_t)nq * k, k, k, 0, 0, out_ids,
-                                                 out_scores, nullptr);
+                                                 out_scores, nullptr, nullptr);
     BR_CUDA(cudaGetLastError());
     return BR_OK;
 }

@@ -21,9 +21,12 @@ struct PrepView {
 
 int launch_rescore(br_index* ix, const int32_t* q_off, const PrepView& pv, int dedup, const int64_t* cand_off,
                    int32_t q_begin, int32_t nq, const int32_t* cand, double* cand_score, int64_t total, cudaStream_t st);
+int launch_rescore_heads(br_index* ix, const int32_t* q_off, const PrepView& pv, int dedup, int32_t nq, int32_t stride,
+                         const int32_t* cnt, const int32_t* cand, double* cand_score, cudaStream_t st);
 int launch_final_select(const int32_t* cand, const double* cand_score, const int64_t* cand_off, int32_t q_begin,
                         int32_t nq, int32_t k, int positive_only, int32_t* out_ids, double* out_scores,
-                        int32_t* out_counts, cudaStream_t st);
+                        int32_t* out_counts, cudaStream_t st, const int32_t* cnt_hint = nullptr);
+void stage_mark(const char* name, cudaStream_t st);
 bool fused_supported(const br_index* ix, int32_t k);
 int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t nq, int32_t k, int dedup,
                int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st,

@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
                                                    const int64_t* __restrict__ row_ptr, int32_t nq, int G, int umax,
                                                    TileEntry* __restrict__ entries, int32_t* __restrict__ n_entries,
                                                    int32_t* __restrict__ elig, unsigned long long* __restrict__ cold_total,
-                                                   int64_t dense_df_min, const int32_t* __restrict__ perm) {
+                                                   int64_t dense_df_min, const int32_t* __restrict__ perm,
+                                                   const int8_t* __restrict__ row_slot) {
     __shared__ int32_t s_term[4][256];
     __shared__ uint8_t s_q[4][256], s_m[4][256];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
@@ -110,15 +111,17 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
     }
     __syncwarp();
     // union of the group's hot terms, terms that are dense everywhere (df >= dense_df_min) first
-    int U = 0, Ud = 0;
-    for (int pass = 0; pass < 2; ++pass) {
+    int U = 0, Ud = 0, Ur = 0;
+    for (int pass = -1; pass < 2; ++pass) {
         for (int base = 0; base < n; base += 32) {
             const int i = base + lane;
             bool first = i < n;
             if (first) {
                 const int32_t t = s_term[wl][i];
+                const bool is_row = row_slot[t] >= 0;
                 const bool dense = row_ptr[t + 1] - row_ptr[t] >= dense_df_min;
-                if (dense != (pass == 0)) first = false;
+                const int cls = is_row ? -1 : (dense ? 0 : 1);          // rows first, then dense postings, then sparse
+                if (cls != pass) first = false;
                 for (int j = 0; first && j < i; ++j)
                     if (s_term[wl][j] == t) first = false;
             }
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
             if (first) {
                 TileEntry e;
                 e.term = s_term[wl][i];
-                e.slot = hot_slot[e.term];
+                e.slot = pass < 0 ? (int32_t)row_slot[e.term] : hot_slot[e.term];
 #pragma unroll
                 for (int x = 0; x < 8; ++x) e.mult[x] = 0;
                 for (int j = i; j < n; ++j)
@@ -135,10 +138,11 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
             }
             U += __popc(m);
         }
+        if (pass < 0) Ur = U;
         if (pass == 0) Ud = U;
     }
     if (lane == 0) {
-        n_entries[g] = U | (Ud << 16);
+        n_entries[g] = U | (Ud << 10) | (Ur << 20);
         if (cold_sum) atomicAdd(cold_total, cold_sum);
     }
 }
@@ -282,6 +286,8 @@ struct TileArgs {
     const int32_t* elig;
     const uint32_t* cold_off;     // [n_tiles * n_groups + 1] or null
     const ColdEntry* cold;
+    const float* rows;            // dense rows [n_rows, n_pad]
+    int64_t n_pad;
     float* thr;
     int32_t* cand_cnt;
     int32_t* cand;                // [nq, TILE_CAP]
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
 
     const int g = blockIdx.x, tile = a.tile0 + blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int U = a.n_entries[g] & 0xffff, Ud = a.n_entries[g] >> 16;
+    const int U = a.n_entries[g] & 0x3ff, Ud = (a.n_entries[g] >> 10) & 0x3ff, Ur = a.n_entries[g] >> 20;
     const int sub0 = tile * TILE_W;
 
     for (int u = threadIdx.x; u < U; u += TILE_W * 32) {
@@ -316,15 +322,38 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
         const int u = i / (TILE_W + 1), j = i - u * (TILE_W + 1);
         const int32_t slot = a.entries[(int64_t)g * a.umax + u].slot;
         const int sub = min(sub0 + j, a.n_sub);
-        s_bnd[i] = a.skip[(int64_t)slot * (a.n_sub + 1) + sub];
-    }
-    {   // each warp zeroes its own accumulator rows
-        float4* z = reinterpret_cast<float4*>(acc);
-#pragma unroll
-        for (int q = 0; q < G; ++q)
-            for (int i = lane; i < TILE_S / 4; i += 32) z[((q * TILE_W + w) * TILE_S) / 4 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        s_bnd[i] = u < Ur ? 0u : a.skip[(int64_t)slot * (a.n_sub + 1) + sub];
     }
     __syncthreads();
+    {   // each warp initialises its own accumulator rows: zero + the weights of the dense-row terms of each
+        // query (terms present in >= ~20% of the docs are stored as plain fp32 rows, 0 where absent), 4 docs per lane
+        const uint32_t d0 = (uint32_t)(sub0 + w) << TILE_SHIFT;
+#pragma unroll 1
+        for (int s4 = 0; s4 < TILE_S / 128; ++s4) {
+            float4 v[G];
+#pragma unroll
+            for (int q = 0; q < G; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int64_t off = (int64_t)d0 + s4 * 128 + lane * 4;
+            if (sub0 + w < a.n_sub) {
+                for (int u = 0; u < Ur; ++u) {
+                    const float4 d = __ldg(reinterpret_cast<const float4*>(a.rows + (int64_t)ent[u].slot * a.n_pad + off));
+                    const float4 f4 = s_fm[u];
+                    const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+                    for (int q = 0; q < G; ++q) {
+                        if (ff[q] != 0.f) {                     // warp-uniform
+                            v[q].x = fmaf(d.x, ff[q], v[q].x); v[q].y = fmaf(d.y, ff[q], v[q].y);
+                            v[q].z = fmaf(d.z, ff[q], v[q].z); v[q].w = fmaf(d.w, ff[q], v[q].w);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < G; ++q)
+                reinterpret_cast<float4*>(acc + (q * TILE_W + w) * TILE_S)[s4 * 32 + lane] = v[q];
+        }
+    }
+    __syncwarp();
     const int sub = sub0 + w;
     if (sub >= a.n_sub) return;
     const uint32_t doc0 = (uint32_t)sub << TILE_SHIFT;
@@ -408,8 +437,7 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
         return u;
     };
     const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
-    int u = next_dense(0);
-    const int U_all = U; (void)U_all;
+    int u = next_dense(Ur);
     uint32_t start = 0, hi = 0;                     // current chunk = postings [start, min(start+128, hi)) of term u
     const uint2* p = reinterpret_cast<const uint2*>(a.post);
     uint2 cur[4];
@@ -575,15 +603,17 @@ __global__ void __launch_bounds__(TG_T) k_tighten(float* __restrict__ thr, int32
     }
     int32_t* ids = cand + (int64_t)q * TILE_CAP;
     float* hs = cand_h + (int64_t)q * TILE_CAP;
-    for (int i = threadIdx.x; i < TILE_CAP; i += TG_T) {
+    int n_sort = 32;                                   // smallest power of two covering the list
+    while (n_sort < n) n_sort <<= 1;
+    for (int i = threadIdx.x; i < n_sort; i += TG_T) {
         s_h[i] = i < n ? hs[i] : -1.f;
         s_id[i] = i < n ? ids[i] : -1;
     }
     if (threadIdx.x == 0) s_keep = 0;
-    for (int size = 2; size <= TILE_CAP; size <<= 1) {
+    for (int size = 2; size <= n_sort; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
-            for (int i = threadIdx.x; i < TILE_CAP / 2; i += TG_T) {
+            for (int i = threadIdx.x; i < n_sort / 2; i += TG_T) {
                 const int x = 2 * i - (i & (stride - 1)), y = x + stride;
                 const bool up = (x & size) == 0;
                 const float hx = s_h[x], hy = s_h[y];
@@ -663,7 +693,7 @@ bool fused_supported(const br_index* ix, int32_t k) {
 
 // Fused path over the whole prepared batch.  h_flags[q] != 0 afterwards -> query q must be served by
 // the dense path (not eligible, candidate overflow, or fewer than k docs with a positive score).
-static void stage_mark(const char* name, cudaStream_t st) {     // BR_TIMELINE=1: wall-clock per stage (debug)
+void stage_mark(const char* name, cudaStream_t st) {     // BR_TIMELINE=1: wall-clock per stage (debug)
     static const bool on = getenv("BR_TIMELINE") != nullptr;
     static double last = 0;
     if (!on) return;
@@ -737,7 +767,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     BR_CUDA(cudaMemsetAsync(cold_total, 0, 16, st));
     BR_CUDA(cudaMemsetAsync(cand, 0xFF, 4 * (size_t)nq * TILE_CAP, st));
     k_tile_prep<<<(n_groups + 3) / 4, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, nq, G, umax, entries, n_entries,
-                                                    elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)TILE_DENSE_MIN) >> TILE_SHIFT), perm);
+                                                    elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)TILE_DENSE_MIN) >> TILE_SHIFT), perm, ix->row_slot);
     BR_CUDA(cudaGetLastError());
     k_fill_offsets<<<blocks_for(nq + 1, 256), 256, 0, st>>>(cand_off, nq, TILE_CAP);
     BR_CUDA(cudaGetLastError());
@@ -774,7 +804,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
 
     stage_mark("cold_sort", st);
     TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
-               cold_off, cold, thr, cand_cnt, cand, cand_h, (int)k, 0, dedup ? 0 : 1, perm};
+               cold_off, cold, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, (int)k, 0, dedup ? 0 : 1, perm};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
                                                                             sizeof(uint32_t) * (TILE_W + 1) + sizeof(float4));
     switch (G) {
@@ -785,8 +815,8 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     }
     stage_mark("tiles", st);
     const int64_t total = (int64_t)nq * TILE_CAP;
-    BR_TRY(launch_rescore(ix, q_off, pv, dedup, cand_off, 0, nq, cand, cand_sc, total, st));
-    BR_TRY(launch_final_select(cand, cand_sc, cand_off, 0, nq, k, positive_only, out_ids, out_scores, cnt_tmp, st));
+    BR_TRY(launch_rescore_heads(ix, q_off, pv, dedup, nq, TILE_CAP, cand_cnt, cand, cand_sc, st));
+    BR_TRY(launch_final_select(cand, cand_sc, cand_off, 0, nq, k, positive_only, out_ids, out_scores, cnt_tmp, st, cand_cnt));
     const int32_t need = (int32_t)std::min<int64_t>(k, ix->n_docs);
     k_fused_flags<<<blocks_for(nq, 256), 256, 0, st>>>(elig, overflow, cnt_tmp, nq, need, positive_only, flags);
     BR_CUDA(cudaGetLastError());
