@@ -306,12 +306,18 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
     int64_t* s_base = reinterpret_cast<int64_t*>(ent + a.umax);                          // [umax]
     uint32_t* s_bnd = reinterpret_cast<uint32_t*>(s_base + a.umax);                      // [umax][W+1]
     float4* s_fm = reinterpret_cast<float4*>(s_bnd + a.umax * (TILE_W + 1));             // [umax] multiplicities as floats
+    __shared__ int s_qi[8];                                                              // query of each group slot (-1: none)
 
     const int g = blockIdx.x, tile = a.tile0 + blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int U = a.n_entries[g] & 0x3ff, Ud = (a.n_entries[g] >> 10) & 0x3ff, Ur = a.n_entries[g] >> 20;
     const int sub0 = tile * TILE_W;
 
+    if (threadIdx.x < G) {
+        const int pos = g * G + threadIdx.x;
+        const int qi = pos < a.nq ? a.perm[pos] : -1;
+        s_qi[threadIdx.x] = (qi >= 0 && a.elig[qi]) ? qi : -1;
+    }
     for (int u = threadIdx.x; u < U; u += TILE_W * 32) {
         const TileEntry e = a.entries[(int64_t)g * a.umax + u];
         ent[u] = e;
@@ -329,28 +335,46 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
         // query (terms present in >= ~20% of the docs are stored as plain fp32 rows, 0 where absent), 4 docs per lane
         const uint32_t d0 = (uint32_t)(sub0 + w) << TILE_SHIFT;
 #pragma unroll 1
-        for (int s4 = 0; s4 < TILE_S / 128; ++s4) {
-            float4 v[G];
+        for (int half = 0; half < 2; ++half) {                  // 256 docs per pass: 2 x (4 docs per lane)
+            float4 v[G][2];
 #pragma unroll
-            for (int q = 0; q < G; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int64_t off = (int64_t)d0 + s4 * 128 + lane * 4;
+            for (int q = 0; q < G; ++q) v[q][0] = v[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int64_t off = (int64_t)d0 + half * 256 + lane * 4;
             if (sub0 + w < a.n_sub) {
-                for (int u = 0; u < Ur; ++u) {
-                    const float4 d = __ldg(reinterpret_cast<const float4*>(a.rows + (int64_t)ent[u].slot * a.n_pad + off));
-                    const float4 f4 = s_fm[u];
-                    const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
+                for (int u0 = 0; u0 < Ur; u0 += 2) {             // two rows x two segments = 4 loads in flight
+                    float4 d[2][2];
+                    float ff[2][4];
 #pragma unroll
-                    for (int q = 0; q < G; ++q) {
-                        if (ff[q] != 0.f) {                     // warp-uniform
-                            v[q].x = fmaf(d.x, ff[q], v[q].x); v[q].y = fmaf(d.y, ff[q], v[q].y);
-                            v[q].z = fmaf(d.z, ff[q], v[q].z); v[q].w = fmaf(d.w, ff[q], v[q].w);
-                        }
+                    for (int k = 0; k < 2; ++k) {
+                        const int u = min(u0 + k, Ur - 1);
+                        const float* row = a.rows + (int64_t)ent[u].slot * a.n_pad + off;
+                        d[k][0] = __ldg(reinterpret_cast<const float4*>(row));
+                        d[k][1] = __ldg(reinterpret_cast<const float4*>(row + 128));
+                        const float4 f4 = u0 + k < Ur ? s_fm[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        ff[k][0] = f4.x; ff[k][1] = f4.y; ff[k][2] = f4.z; ff[k][3] = f4.w;
                     }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+#pragma unroll
+                        for (int q = 0; q < G; ++q) {
+                            if (ff[k][q] != 0.f) {               // warp-uniform
+#pragma unroll
+                                for (int s = 0; s < 2; ++s) {
+                                    v[q][s].x = fmaf(d[k][s].x, ff[k][q], v[q][s].x);
+                                    v[q][s].y = fmaf(d[k][s].y, ff[k][q], v[q][s].y);
+                                    v[q][s].z = fmaf(d[k][s].z, ff[k][q], v[q][s].z);
+                                    v[q][s].w = fmaf(d[k][s].w, ff[k][q], v[q][s].w);
+                                }
+                            }
+                        }
                 }
             }
 #pragma unroll
-            for (int q = 0; q < G; ++q)
-                reinterpret_cast<float4*>(acc + (q * TILE_W + w) * TILE_S)[s4 * 32 + lane] = v[q];
+            for (int q = 0; q < G; ++q) {
+                float4* dst = reinterpret_cast<float4*>(acc + (q * TILE_W + w) * TILE_S + half * 256);
+                dst[lane] = v[q][0];
+                dst[32 + lane] = v[q][1];
+            }
         }
     }
     __syncwarp();
@@ -525,11 +549,13 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
 
     // epilogue: threshold filter per query of the group
     const uint32_t n_valid = (uint32_t)min((int64_t)TILE_S, a.n_docs - (int64_t)doc0);
+    float thq[G];
+#pragma unroll
+    for (int q = 0; q < G; ++q) thq[q] = s_qi[q] >= 0 ? __ldcg(a.thr + s_qi[q]) : 0.f;     // all thresholds in flight at once
 #pragma unroll 1
     for (int q = 0; q < G; ++q) {
-        if (g * G + q >= a.nq) continue;
-        const int qi = a.perm[g * G + q];
-        if (!a.elig[qi]) continue;
+        const int qi = s_qi[q];
+        if (qi < 0) continue;
         float v[TILE_S / 32];
         float mx = 0.f;
 #pragma unroll
@@ -538,7 +564,7 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
             if ((uint32_t)(j * 32 + lane) >= n_valid) v[j] = 0.f;
             mx = fmaxf(mx, v[j]);
         }
-        float th = __ldcg(a.thr + qi);
+        float th = thq[q];
         float lo_thr = th * (1.f - kBandRel);
         if (!__any_sync(0xffffffffu, mx >= lo_thr && mx > 0.f)) continue;     // nothing above the threshold here
         int c = 0;
