@@ -294,12 +294,14 @@ struct TileArgs {
     float* cand_h;                // [nq, TILE_CAP]
     int K;
     int tile0;
+    int tile_end;                 // tiles [tile0, tile_end) in this launch
+    int tpb;                      // consecutive tiles per CTA
     int has_mult;                 // 0: every multiplicity is 1 (set(query) semantics)
     const int32_t* perm;          // group g, slot i -> query perm[g*G+i] (queries sorted by frequent-term signature)
 };
 
 template <int G>
-__global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(TileArgs a) {
+__global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* acc = reinterpret_cast<float*>(smem_raw);                                     // [G][W][S]
     TileEntry* ent = reinterpret_cast<TileEntry*>(smem_raw + sizeof(float) * G * TILE_W * TILE_S);
@@ -308,10 +310,11 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
     float4* s_fm = reinterpret_cast<float4*>(s_bnd + a.umax * (TILE_W + 1));             // [umax] multiplicities as floats
     __shared__ int s_qi[8];                                                              // query of each group slot (-1: none)
 
-    const int g = blockIdx.x, tile = a.tile0 + blockIdx.y;
+    const int g = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int U = a.n_entries[g] & 0x3ff, Ud = (a.n_entries[g] >> 10) & 0x3ff, Ur = a.n_entries[g] >> 20;
-    const int sub0 = tile * TILE_W;
+    const int tile_first = a.tile0 + blockIdx.y * a.tpb;
+    const int tile_last = min(tile_first + a.tpb, a.tile_end);          // exclusive
 
     if (threadIdx.x < G) {
         const int pos = g * G + threadIdx.x;
@@ -324,13 +327,37 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
         s_base[u] = a.row_ptr[e.term];
         s_fm[u] = make_float4((float)e.mult[0], (float)e.mult[1], (float)e.mult[2], (float)e.mult[3]);
     }
-    for (int i = threadIdx.x; i < U * (TILE_W + 1); i += TILE_W * 32) {
-        const int u = i / (TILE_W + 1), j = i - u * (TILE_W + 1);
-        const int32_t slot = a.entries[(int64_t)g * a.umax + u].slot;
-        const int sub = min(sub0 + j, a.n_sub);
-        s_bnd[i] = u < Ur ? 0u : a.skip[(int64_t)slot * (a.n_sub + 1) + sub];
-    }
+    // slice bounds of the first tile; the bounds of tile t+1 are fetched into registers while tile t is processed
+    constexpr int NB = (TILE_QT * G * (TILE_W + 1) + TILE_W * 32 - 1) / (TILE_W * 32);
+    uint32_t nb[NB];
+    auto load_bounds = [&](int tile) {
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            const int i = threadIdx.x + k * TILE_W * 32;
+            nb[k] = 0;
+            if (i < U * (TILE_W + 1)) {
+                const int u = i / (TILE_W + 1), j = i - u * (TILE_W + 1);
+                if (u >= Ur) {
+                    const int32_t slot = a.entries[(int64_t)g * a.umax + u].slot;
+                    nb[k] = a.skip[(int64_t)slot * (a.n_sub + 1) + min(tile * TILE_W + j, a.n_sub)];
+                }
+            }
+        }
+    };
+    auto store_bounds = [&]() {
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            const int i = threadIdx.x + k * TILE_W * 32;
+            if (i < U * (TILE_W + 1)) s_bnd[i] = nb[k];
+        }
+    };
+    load_bounds(tile_first);
+    store_bounds();
     __syncthreads();
+#pragma unroll 1
+    for (int tile = tile_first; tile < tile_last; ++tile) {
+    const int sub0 = tile * TILE_W;
+    if (tile + 1 < tile_last) load_bounds(tile + 1);                  // in flight during this tile
     {   // each warp initialises its own accumulator rows: zero + the weights of the dense-row terms of each
         // query (terms present in >= ~20% of the docs are stored as plain fp32 rows, 0 where absent), 4 docs per lane
         const uint32_t d0 = (uint32_t)(sub0 + w) << TILE_SHIFT;
@@ -379,7 +406,7 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
     }
     __syncwarp();
     const int sub = sub0 + w;
-    if (sub >= a.n_sub) return;
+    if (sub < a.n_sub) {
     const uint32_t doc0 = (uint32_t)sub << TILE_SHIFT;
     float* my = acc + w * TILE_S;                       // + q * TILE_W * TILE_S per query
 
@@ -548,7 +575,6 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
     }
 
     // epilogue: threshold filter per query of the group
-    const uint32_t n_valid = (uint32_t)min((int64_t)TILE_S, a.n_docs - (int64_t)doc0);
     float thq[G];
 #pragma unroll
     for (int q = 0; q < G; ++q) thq[q] = s_qi[q] >= 0 ? __ldcg(a.thr + s_qi[q]) : 0.f;     // all thresholds in flight at once
@@ -561,7 +587,6 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
 #pragma unroll
         for (int j = 0; j < TILE_S / 32; ++j) {
             v[j] = my[q * TILE_W * TILE_S + j * 32 + lane];
-            if ((uint32_t)(j * 32 + lane) >= n_valid) v[j] = 0.f;
             mx = fmaxf(mx, v[j]);
         }
         float th = thq[q];
@@ -609,6 +634,13 @@ __global__ void __launch_bounds__(TILE_W * 32, G >= 4 ? 2 : 3) k_tile_score(Tile
             }
         }
     }
+    }   // sub < n_sub
+    if (tile + 1 < tile_last) {
+        __syncthreads();                                              // every warp is done with this tile's bounds
+        store_bounds();
+        __syncthreads();
+    }
+    }   // tile loop
 }
 
 // Between chunks: thr[q] = max(thr[q], K-th best fp32 score emitted so far); keep only the candidates
@@ -698,8 +730,11 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
         const int ny = std::min(std::min(chunk, n_tiles - t0), 32768);
         TileArgs a = a0;
         a.tile0 = t0;
+        a.tile_end = t0 + ny;
+        static const int tpb_env = getenv("BR_TILE_TPB") ? atoi(getenv("BR_TILE_TPB")) : 4;
+        a.tpb = ny >= 2 * tpb_env ? std::max(1, tpb_env) : 1;
         ix->prof_begin(st);
-        k_tile_score<G><<<dim3((unsigned)n_groups, (unsigned)ny), TILE_W * 32, smem, st>>>(a);
+        k_tile_score<G><<<dim3((unsigned)n_groups, (unsigned)((ny + a.tpb - 1) / a.tpb)), TILE_W * 32, smem, st>>>(a);
         BR_CUDA(cudaGetLastError());
         ix->prof_end(st);
         k_tighten<<<a0.nq, TG_T, 0, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, overflow);
@@ -830,7 +865,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
 
     stage_mark("cold_sort", st);
     TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
-               cold_off, cold, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, (int)k, 0, dedup ? 0 : 1, perm};
+               cold_off, cold, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, (int)k, 0, 0, 1, dedup ? 0 : 1, perm};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
                                                                             sizeof(uint32_t) * (TILE_W + 1) + sizeof(float4));
     switch (G) {
