@@ -2,12 +2,12 @@
 //   e_hat = e / (||e|| + 1e-10) on both sides, sims = E_hat . q_hat, top-k per query.
 //
 //   k_row_inv_norm      1/(||x||_2 + 1e-10) per row, fp32                        (HBM-bound, one pass)
-//   k_cosine_gemm       brute force: bf16 tcgen05 (UMMA) GEMM  docs[128-row tile] x queries[256-col tile],
-//                       TMA (128B swizzle) -> 4-stage smem ring -> tcgen05.mma, fp32 accumulators in TMEM
-//                       (2 x 256 columns, double buffered); epilogue warps read TMEM with tcgen05.ld,
+//   k_cosine_gemm       brute force: bf16 tcgen05 (UMMA) GEMM  docs[256-row tile] x queries[256-col tile],
+//                       TMA (128B swizzle) -> 3-stage smem ring -> tcgen05.mma, fp32 accumulators in TMEM
+//                       (2 x 256 columns: two 128-row UMMAs share each query tile); epilogue warps read TMEM with tcgen05.ld,
 //                       apply 1/(||d||+eps) * 1/(||q||+eps) and keep only scores above the query's running
 //                       threshold - the [Q, N] score matrix is never written.  Persistent, warp-specialised
-//                       (warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue).        (tensor-bound)
+//                       (warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-9 epilogue).        (tensor-bound)
 //   k_tighten_cos       between doc chunks of doubling size: threshold := k-th best so far, compact list
 //   k_cosine_rerank     per query its own c candidate rows (BM25 top-1000 -> cosine): one warp per
 //                       (query, candidate) dot product with 128-bit loads              (gather / HBM-bound)
@@ -124,13 +124,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 // ------------------------------------------------------------------------------------------
 // the GEMM + threshold-filter kernel
 // ------------------------------------------------------------------------------------------
-constexpr int CG_BM = 128, CG_BN = 256, CG_BK = 64, CG_STAGES = 4;
+constexpr int CG_BM = 256, CG_BN = 256, CG_BK = 64, CG_STAGES = 3;   // BM = 2 x 128-row UMMAs sharing the B (query) tile
 constexpr int CG_A_BYTES = CG_BM * CG_BK * 2, CG_B_BYTES = CG_BN * CG_BK * 2;
 constexpr int CG_STAGE_BYTES = CG_A_BYTES + CG_B_BYTES;
-constexpr int CG_THREADS = 192;
-constexpr size_t CG_SMEM = 1024 /*align slack*/ + (size_t)CG_STAGES * CG_STAGE_BYTES + 2 * CG_BN * sizeof(float) * 2 + 256;
+constexpr int CG_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of rows 0-127, warps 6-9 of rows 128-255
+constexpr size_t CG_SMEM = 1024 /*align slack*/ + (size_t)CG_STAGES * CG_STAGE_BYTES + 2 * CG_BN * sizeof(float) + 256;
 // instruction descriptor: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), A,B K-major, N=256 (>>3 at bit 17), M=128 (>>4 at bit 24)
-constexpr uint32_t CG_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CG_BN >> 3) << 17) | ((uint32_t)(CG_BM >> 4) << 24);
+constexpr uint32_t CG_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CG_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 struct CosArgs {
     const float* inv_nd;      // [n_docs]
@@ -151,9 +151,9 @@ __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_cons
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;             // 128B swizzle needs 1024-byte alignment
     unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t s_tiles = base;
-    float* s_thr = reinterpret_cast<float*>(gen + CG_STAGES * CG_STAGE_BYTES);          // [2][CG_BN] scaled thresholds
-    float* s_inq = s_thr + 2 * CG_BN;                                                    // [2][CG_BN] 1/(||q||+eps)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_inq + 2 * CG_BN);                    // full[4] empty[4] tfull[2] tempty[2]
+    float* s_thr = reinterpret_cast<float*>(gen + CG_STAGES * CG_STAGE_BYTES);          // [CG_BN] scaled thresholds
+    float* s_inq = s_thr + CG_BN;                                                        // [CG_BN] 1/(||q||+eps)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_inq + CG_BN);                        // full[S] empty[S] tfull[2] tempty[2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_cons
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), CG_STAGE_BYTES);
                     const uint32_t sa = s_tiles + stage * CG_STAGE_BYTES;
-                    tma_load_2d(sa, &map_docs, full_bar(stage), kb * CG_BK, dt * CG_BM);
+                    tma_load_2d(sa, &map_docs, full_bar(stage), kb * CG_BK, dt * CG_BM);          // 256 doc rows
                     tma_load_2d(sa + CG_A_BYTES, &map_q, full_bar(stage), kb * CG_BK, qt * CG_BN);
                     if (++stage == CG_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -201,39 +201,42 @@ __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_cons
         // ===== MMA issuer (one elected lane) =====
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0, acc_phase[2] = {0, 0};
-            int it = 0;
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-                const int buf = it & 1;
-                mbar_wait(tempty_bar(buf), acc_phase[buf] ^ 1);
-                acc_phase[buf] ^= 1;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                // both accumulator halves (TMEM columns [0,256) and [256,512)) must have been drained
+                mbar_wait(tempty_bar(0), acc_phase ^ 1);
+                mbar_wait(tempty_bar(1), acc_phase ^ 1);
+                acc_phase ^= 1;
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)buf * CG_BN;
                 for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = s_tiles + stage * CG_STAGE_BYTES;
-                    const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + CG_A_BYTES);
+                    const uint64_t da0 = umma_desc_sw128(sa), da1 = umma_desc_sw128(sa + CG_A_BYTES / 2);
+                    const uint64_t db = umma_desc_sw128(sa + CG_A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < CG_BK / 16; ++k)          // UMMA_K = 16 bf16 = 32 bytes: +2 in the >>4 address field
-                        tc_mma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), CG_IDESC, (kb | k) != 0);
+                    for (int k = 0; k < CG_BK / 16; ++k) {        // UMMA_K = 16 bf16 = 32 bytes: +2 in the >>4 address field
+                        tc_mma_bf16(tmem_base, da0 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), CG_IDESC, (kb | k) != 0);
+                        tc_mma_bf16(tmem_base + CG_BN, da1 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), CG_IDESC, (kb | k) != 0);
+                    }
                     tc_commit(empty_bar(stage));                    // smem slot free once these MMAs retire
                     if (++stage == CG_STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tfull_bar(buf));                          // accumulator ready for the epilogue
+                tc_commit(tfull_bar(0));                            // accumulators ready for the epilogue warps
+                tc_commit(tfull_bar(1));
             }
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lanes [32*(warp%4), +32) =====
-        const int quarter = warp & 3;
-        const int et = (int)threadIdx.x - 64;                       // 0..127
-        uint32_t acc_phase[2] = {0, 0};
-        int it = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            const int buf = it & 1;
+        // ===== epilogue warps: half h = (warp-2)/4 owns doc rows [128h, 128h+128) = TMEM columns [256h, 256h+256);
+        //       a warp reads TMEM lanes [32*(warp%4), +32) =====
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const int et = (int)threadIdx.x - 64;                       // 0..255
+        uint32_t acc_phase = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int dt = a.tile_begin + (int)(t / n_qt), qt = (int)(t % n_qt);
-            // scaled thresholds of this query tile (double-buffered: the previous tile may still be read)
-            for (int c = et; c < CG_BN; c += 128) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // previous tile's thresholds no longer in use
+            {
+                const int c = et;
                 const int q = qt * CG_BN + c;
                 float th = CUDART_INF_F, iq = 0.f;
                 if (q < a.nq) {
@@ -241,16 +244,16 @@ __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_cons
                     const float raw = __ldcg(a.thr + q) / iq;          // compare acc*inv_d against thr/inv_q
                     th = raw - fabsf(raw) * 4e-6f;                      // superset: rounding of the division
                 }
-                s_thr[buf * CG_BN + c] = th;
-                s_inq[buf * CG_BN + c] = iq;
+                s_thr[c] = th;
+                s_inq[c] = iq;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");          // epilogue warps only
-            mbar_wait(tfull_bar(buf), acc_phase[buf]);
-            acc_phase[buf] ^= 1;
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // epilogue warps only
+            mbar_wait(tfull_bar(half), acc_phase);
+            acc_phase ^= 1;
             tc_fence_after();
-            const int64_t doc = (int64_t)dt * CG_BM + quarter * 32 + lane;
+            const int64_t doc = (int64_t)dt * CG_BM + half * 128 + quarter * 32 + lane;
             const float inv_d = doc < a.n_docs ? a.inv_nd[doc] : 0.f;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * CG_BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)half * CG_BN;
             for (int c0 = 0; c0 < CG_BN; c0 += 32) {
                 uint32_t v[32];
                 tc_ld_32x32(taddr + c0, v);
@@ -258,13 +261,13 @@ __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_cons
                 if (doc < a.n_docs) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float s = __uint_as_float(v[j]) * inv_d;
-                        if (s >= s_thr[buf * CG_BN + c0 + j]) {
+                        const float sc = __uint_as_float(v[j]) * inv_d;
+                        if (sc >= s_thr[c0 + j]) {
                             const int q = qt * CG_BN + c0 + j;
                             const int pos = atomicAdd(a.cand_cnt + q, 1);
                             if (pos < COS_CAP) {
                                 a.cand[(int64_t)q * COS_CAP + pos] = (int32_t)doc;
-                                a.cand_h[(int64_t)q * COS_CAP + pos] = s * s_inq[buf * CG_BN + c0 + j];
+                                a.cand_h[(int64_t)q * COS_CAP + pos] = sc * s_inq[c0 + j];
                             }
                         }
                     }
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_cons
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(buf));
+            if (lane == 0) mbar_arrive(tempty_bar(half));
         }
     }
     tc_fence_before();
@@ -300,15 +303,17 @@ __global__ void __launch_bounds__(TC_T) k_tighten_cos(float* __restrict__ thr, i
     }
     int32_t* ids = cand + (int64_t)q * COS_CAP;
     float* hs = cand_h + (int64_t)q * COS_CAP;
-    for (int i = threadIdx.x; i < COS_CAP; i += TC_T) {
+    int n_sort = 32;                                   // smallest power of two covering the list
+    while (n_sort < n) n_sort <<= 1;
+    for (int i = threadIdx.x; i < n_sort; i += TC_T) {
         s_h[i] = i < n ? hs[i] : -CUDART_INF_F;
         s_id[i] = i < n ? ids[i] : 0x7fffffff;
     }
     if (threadIdx.x == 0) s_keep = 0;
-    for (int size = 2; size <= COS_CAP; size <<= 1) {
+    for (int size = 2; size <= n_sort; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
-            for (int i = threadIdx.x; i < COS_CAP / 2; i += TC_T) {
+            for (int i = threadIdx.x; i < n_sort / 2; i += TC_T) {
                 const int x = 2 * i - (i & (stride - 1)), y = x + stride;
                 const bool up = (x & size) == 0;
                 const float hx = s_h[x], hy = s_h[y];
