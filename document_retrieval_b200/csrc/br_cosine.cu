@@ -85,6 +85,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  "l"(map), "r"(bar), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+        "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -286,6 +305,155 @@ __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_cons
     }
 }
 
+// Cluster variant: CTA pairs share every doc (A) tile - rank r loads rows [128r, 128r+128) of it and multicasts them to both
+// CTAs, so the doc operand crosses L2->SM once per pair; each CTA loads its own query (B) tile.  Stage release is cluster-wide
+// (both CTAs' UMMAs arrive on both CTAs' empty barriers).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS, 1) k_cosine_gemm_mc(const __grid_constant__ CUtensorMap map_docs,
+                                                               const __grid_constant__ CUtensorMap map_q, CosArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;             // 128B swizzle needs 1024-byte alignment
+    unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t s_tiles = base;
+    float* s_thr = reinterpret_cast<float*>(gen + CG_STAGES * CG_STAGE_BYTES);          // [CG_BN] scaled thresholds
+    float* s_inq = s_thr + CG_BN;                                                        // [CG_BN] 1/(||q||+eps)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_inq + CG_BN);                        // full[S] empty[S] tfull[2] tempty[2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (CG_STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * CG_STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * CG_STAGES + 2 + b); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_rank();
+    const int n_qt = ((a.nq + CG_BN - 1) / CG_BN + 1) / 2;          // query-tile PAIRS
+    const int64_t n_tiles = (int64_t)(a.tile_end - a.tile_begin) * n_qt;
+    const int64_t t_first = blockIdx.x >> 1, t_step = gridDim.x >> 1;
+    const int n_kb = (a.d + CG_BK - 1) / CG_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 2); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                   // peers' barriers are initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = t_first; t < n_tiles; t += t_step) {
+                const int dt = a.tile_begin + (int)(t / n_qt), qt = 2 * (int)(t % n_qt) + (int)crank;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), CG_STAGE_BYTES);
+                    const uint32_t sa = s_tiles + stage * CG_STAGE_BYTES;
+                    tma_load_2d_mc(sa + crank * (CG_A_BYTES / 2), &map_docs, full_bar(stage), kb * CG_BK,
+                                   dt * CG_BM + (int)crank * 128, (uint16_t)3);       // my 128 doc rows -> both CTAs
+                    tma_load_2d(sa + CG_A_BYTES, &map_q, full_bar(stage), kb * CG_BK, qt * CG_BN);
+                    if (++stage == CG_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int64_t t = t_first; t < n_tiles; t += t_step) {
+                // both accumulator halves (TMEM columns [0,256) and [256,512)) must have been drained
+                mbar_wait(tempty_bar(0), acc_phase ^ 1);
+                mbar_wait(tempty_bar(1), acc_phase ^ 1);
+                acc_phase ^= 1;
+                tc_fence_after();
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = s_tiles + stage * CG_STAGE_BYTES;
+                    const uint64_t da0 = umma_desc_sw128(sa), da1 = umma_desc_sw128(sa + CG_A_BYTES / 2);
+                    const uint64_t db = umma_desc_sw128(sa + CG_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < CG_BK / 16; ++k) {        // UMMA_K = 16 bf16 = 32 bytes: +2 in the >>4 address field
+                        tc_mma_bf16(tmem_base, da0 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), CG_IDESC, (kb | k) != 0);
+                        tc_mma_bf16(tmem_base + CG_BN, da1 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), CG_IDESC, (kb | k) != 0);
+                    }
+                    tc_commit_mc(empty_bar(stage), (uint16_t)3);    // slot free in BOTH CTAs once these MMAs retire
+                    if (++stage == CG_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(0));                            // accumulators ready for the epilogue warps
+                tc_commit(tfull_bar(1));
+            }
+        }
+    } else {
+        // ===== epilogue warps: half h = (warp-2)/4 owns doc rows [128h, 128h+128) = TMEM columns [256h, 256h+256);
+        //       a warp reads TMEM lanes [32*(warp%4), +32) =====
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const int et = (int)threadIdx.x - 64;                       // 0..255
+        uint32_t acc_phase = 0;
+        for (int64_t t = t_first; t < n_tiles; t += t_step) {
+            const int dt = a.tile_begin + (int)(t / n_qt), qt = 2 * (int)(t % n_qt) + (int)crank;
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // previous tile's thresholds no longer in use
+            {
+                const int c = et;
+                const int q = qt * CG_BN + c;
+                float th = CUDART_INF_F, iq = 0.f;
+                if (q < a.nq) {
+                    iq = a.inv_nq[q];
+                    const float raw = __ldcg(a.thr + q) / iq;          // compare acc*inv_d against thr/inv_q
+                    th = raw - fabsf(raw) * 4e-6f;                      // superset: rounding of the division
+                }
+                s_thr[c] = th;
+                s_inq[c] = iq;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // epilogue warps only
+            mbar_wait(tfull_bar(half), acc_phase);
+            acc_phase ^= 1;
+            tc_fence_after();
+            const int64_t doc = (int64_t)dt * CG_BM + half * 128 + quarter * 32 + lane;
+            const float inv_d = doc < a.n_docs ? a.inv_nd[doc] : 0.f;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)half * CG_BN;
+            for (int c0 = 0; c0 < CG_BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld_32x32(taddr + c0, v);
+                tc_wait_ld();
+                if (doc < a.n_docs) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = __uint_as_float(v[j]) * inv_d;
+                        if (sc >= s_thr[c0 + j]) {
+                            const int q = qt * CG_BN + c0 + j;
+                            const int pos = atomicAdd(a.cand_cnt + q, 1);
+                            if (pos < COS_CAP) {
+                                a.cand[(int64_t)q * COS_CAP + pos] = (int32_t)doc;
+                                a.cand_h[(int64_t)q * COS_CAP + pos] = sc * s_inq[c0 + j];
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(half));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                   // no CTA exits while its peer can still write into it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // threshold := k-th best candidate so far; keep the candidates >= threshold, sorted (score desc, id asc)
 constexpr int TC_T = 256;
 __global__ void __launch_bounds__(TC_T) k_tighten_cos(float* __restrict__ thr, int32_t* __restrict__ cand_cnt,
@@ -477,12 +645,14 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     BR_REQUIRE(k >= 1 && k <= 256, BR_ERR_INVALID, "br_cosine_topk: k must be in [1, 256]");
     BR_REQUIRE(((uintptr_t)docs & 15) == 0 && ((uintptr_t)queries & 15) == 0, BR_ERR_INVALID, "br_cosine_topk: 16-byte alignment required");
     if (nq == 0) return BR_OK;
+    static const bool use_mc = getenv("BR_COS_NO_MULTICAST") == nullptr;
     CUtensorMap map_d, map_q;
-    BR_TRY(make_map(&map_d, docs, n_docs, d, CG_BM));
+    BR_TRY(make_map(&map_d, docs, n_docs, d, use_mc ? 128 : CG_BM));
     BR_TRY(make_map(&map_q, queries, nq, d, CG_BN));
     static bool attr = false;
     if (!attr) {
         BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));
+        BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));
         attr = true;
     }
     const size_t Q = (size_t)nq;
@@ -502,8 +672,13 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     while (t0 < n_dt) {
         const int nt = std::min(chunk, n_dt - t0);
         CosArgs a{inv_nd, inv_nq, thr, (int32_t*)b_cnt.p, (int32_t*)b_cand.p, (float*)b_h.p, n_docs, nq, d, t0, t0 + nt};
-        const int grid = (int)std::min<int64_t>((int64_t)nt * n_qt, kNumSMs);
-        k_cosine_gemm<<<grid, CG_THREADS, CG_SMEM, st>>>(map_d, map_q, a);
+        if (use_mc) {
+            const int grid = 2 * (int)std::min<int64_t>((int64_t)nt * ((n_qt + 1) / 2), kNumSMs / 2);
+            k_cosine_gemm_mc<<<grid, CG_THREADS, CG_SMEM, st>>>(map_d, map_q, a);
+        } else {
+            const int grid = (int)std::min<int64_t>((int64_t)nt * n_qt, kNumSMs);
+            k_cosine_gemm<<<grid, CG_THREADS, CG_SMEM, st>>>(map_d, map_q, a);
+        }
         BR_CUDA(cudaGetLastError());
         k_tighten_cos<<<nq, TC_T, 0, st>>>(thr, (int32_t*)b_cnt.p, (int32_t*)b_prev.p, (int32_t*)b_cand.p, (float*)b_h.p, k,
                                            (int32_t*)b_ovf.p);
