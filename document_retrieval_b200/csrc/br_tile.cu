@@ -421,23 +421,25 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
 #pragma unroll 1
     for (int r0 = Ud; r0 < U; r0 += 32) {
         const int u = r0 + lane;
-        uint32_t lo = 0, n = 0;
+        uint32_t lo = 0, n = 0, qmask = 0;
         if (u < U) {
             lo = s_bnd[u * (TILE_W + 1) + w];
             n = s_bnd[u * (TILE_W + 1) + w + 1] - lo;
+            const float4 f4 = s_fm[u];
+            qmask = (f4.x != 0.f ? 1u : 0u) | (f4.y != 0.f ? 2u : 0u) | (f4.z != 0.f ? 4u : 0u) | (f4.w != 0.f ? 8u : 0u);
         }
-        const uint32_t ns = n;
+        const uint32_t pc = __popc(qmask);
+        const uint32_t ns = n * pc;                            // one element per (posting, query of the group that has the term)
         uint32_t incl = ns;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const uint32_t t2 = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t2;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         for (uint32_t j0 = 0; j0 < total; j0 += 32) {
             const uint32_t j = j0 + lane;
-            // owner = first lane whose inclusive prefix exceeds j
-            int own = 0;
+            int own = 0;                                        // owner = first lane whose inclusive prefix exceeds j
 #pragma unroll
             for (int step = 16; step > 0; step >>= 1) {
                 const uint32_t v = __shfl_sync(0xffffffffu, incl, own + step - 1);
@@ -446,35 +448,36 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
             const bool valid = j < total;
             own = valid ? own : 0;
             const uint32_t o_incl = __shfl_sync(0xffffffffu, incl, own);
-            const uint32_t o_n = __shfl_sync(0xffffffffu, ns, own);
+            const uint32_t o_ns = __shfl_sync(0xffffffffu, ns, own);
             const uint32_t o_lo = __shfl_sync(0xffffffffu, lo, own);
+            const uint32_t o_pc = __shfl_sync(0xffffffffu, pc, own);
+            uint32_t o_mask = __shfl_sync(0xffffffffu, qmask, own);
             const int ou = r0 + own;
-            uint32_t l = 0;
+            uint32_t addr = 0;
             float wt = 0.f;
-            unsigned mults = 0;                              // 8 bits per query (G <= 4) / 4 bits (G == 8)
             if (valid) {
-                const uint32_t idx = j - (o_incl - o_n);
+                const uint32_t e = j - (o_incl - o_ns);        // element inside the owner's slice
+                const uint32_t idx = o_pc == 1 ? e : e / o_pc;
+                uint32_t k = o_pc == 1 ? 0u : e - idx * o_pc;   // k-th query of the term
+                while (k--) o_mask &= o_mask - 1;
+                const int q = __ffs(o_mask) - 1;
                 const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.post) + s_base[ou] + o_lo + idx);
-                l = v.x - doc0;
-                wt = __uint_as_float(v.y);
+                addr = (uint32_t)q * ROW + (v.x - doc0);
+                wt = __uint_as_float(v.y) * reinterpret_cast<const float*>(s_fm + ou)[q];
             }
-#pragma unroll
-            for (int q = 0; q < G; ++q) {
-                const float m = valid ? reinterpret_cast<const float*>(s_fm + ou)[q] : 0.f;
-                bool todo = m != 0.f;
-                (void)mults;
-                while (true) {
-                    const unsigned pend = __ballot_sync(0xffffffffu, todo);
-                    if (!pend) break;
-                    if (todo) {
-                        const unsigned peers = __match_any_sync(pend, l);
-                        if ((peers & ((1u << lane) - 1)) == 0) {
-                            my[q * ROW + l] = fmaf(wt, m, my[q * ROW + l]);
-                            todo = false;
-                        }
+            // lanes that target the same accumulator (same doc and query through different terms) take turns
+            bool todo = valid;
+            while (true) {
+                const unsigned pend = __ballot_sync(0xffffffffu, todo);
+                if (!pend) break;
+                if (todo) {
+                    const unsigned peers = __match_any_sync(pend, addr);
+                    if ((peers & ((1u << lane) - 1)) == 0) {
+                        my[addr] += wt;
+                        todo = false;
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
             }
         }
     }
@@ -582,12 +585,13 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
     for (int q = 0; q < G; ++q) {
         const int qi = s_qi[q];
         if (qi < 0) continue;
-        float v[TILE_S / 32];
+        float v[TILE_S / 32];                                   // v[4*s + e] = doc s*128 + lane*4 + e
         float mx = 0.f;
 #pragma unroll
-        for (int j = 0; j < TILE_S / 32; ++j) {
-            v[j] = my[q * TILE_W * TILE_S + j * 32 + lane];
-            mx = fmaxf(mx, v[j]);
+        for (int s = 0; s < TILE_S / 128; ++s) {
+            const float4 f = reinterpret_cast<const float4*>(my + q * TILE_W * TILE_S)[s * 32 + lane];
+            v[4 * s + 0] = f.x; v[4 * s + 1] = f.y; v[4 * s + 2] = f.z; v[4 * s + 3] = f.w;
+            mx = fmaxf(fmaxf(mx, fmaxf(f.x, f.y)), fmaxf(f.z, f.w));
         }
         float th = thq[q];
         float lo_thr = th * (1.f - kBandRel);
@@ -629,7 +633,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
 #pragma unroll
         for (int j = 0; j < TILE_S / 32; ++j) {
             if (v[j] >= lo_thr && v[j] > 0.f) {
-                if (pos < TILE_CAP) { out[pos] = (int32_t)(doc0 + j * 32 + lane); out_h[pos] = v[j]; }
+                if (pos < TILE_CAP) { out[pos] = (int32_t)(doc0 + (j >> 2) * 128 + lane * 4 + (j & 3)); out_h[pos] = v[j]; }
                 ++pos;
             }
         }
