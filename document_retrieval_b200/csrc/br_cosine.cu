@@ -649,12 +649,8 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     CUtensorMap map_d, map_q;
     BR_TRY(make_map(&map_d, docs, n_docs, d, use_mc ? 128 : CG_BM));
     BR_TRY(make_map(&map_q, queries, nq, d, CG_BN));
-    static bool attr = false;
-    if (!attr) {
-        BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));
-        BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));
-        attr = true;
-    }
+    BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));      // per device
+    BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));
     const size_t Q = (size_t)nq;
     AsyncBuf b_inq(st), b_thr(st), b_cnt(st), b_prev(st), b_ovf(st), b_cand(st), b_h(st);
     BR_TRY(b_inq.alloc(4 * Q)); BR_TRY(b_thr.alloc(4 * Q)); BR_TRY(b_cnt.alloc(4 * Q)); BR_TRY(b_prev.alloc(4 * Q));

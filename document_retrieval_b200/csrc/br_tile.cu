@@ -723,11 +723,7 @@ __global__ void k_fill_offsets(int64_t* __restrict__ off, int32_t nq, int64_t st
 template <int G>
 static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t smem, cudaStream_t st, br_index* ix,
                         int32_t* prev_cnt, int32_t* overflow) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        BR_CUDA(cudaFuncSetAttribute(k_tile_score<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    BR_CUDA(cudaFuncSetAttribute(k_tile_score<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device
     // chunks of doubling size: thresholds learnt on the first 2^c tiles filter the next 2^c
     int t0 = 0, chunk = 1;
     while (t0 < n_tiles) {
