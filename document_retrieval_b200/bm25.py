@@ -362,6 +362,34 @@ class BM25:
         """{doc id: token count} (final_implementation.py:121-122)."""
         return dict(enumerate(self._export_csr()["dl"].tolist()))
 
+    # ------------------------------------------------------------------ native (de)serialisation
+    def save(self, path):
+        """Flat CSR file (numpy .npz, uncompressed): row_ptr / doc / tf / dl + vocabulary + statistics.
+        Replaces the joblib/pickle model files whose loading dominated the reference's run time
+        (bm25_ranking.ipynb:222-251, final_implementation.py:187-287): the arrays are memcpy'd to the GPU
+        and the weights / skip tables are rebuilt there."""
+        st = self.__getstate__()
+        c = st.pop("csr")
+        stat = st.pop("stat")
+        terms = st.pop("terms")
+        np.savez(path, row_ptr=c["row_ptr"], doc=c["doc"], tf=c["tf"], dl=c["dl"], df_stat=stat["df"],
+                 avgdl=np.float64(stat["avgdl"]), terms=np.asarray(terms if terms is not None else [], dtype=object),
+                 has_terms=np.bool_(terms is not None),
+                 meta=np.asarray([repr({k: st[k] for k in ("k1", "b", "variant", "dedup_query", "vocab_size",
+                                                           "corpus_size", "doc_base")})], dtype=object))
+
+    @classmethod
+    def load(cls, path, device=None):
+        import ast
+        with np.load(path if str(path).endswith(".npz") else str(path) + ".npz", allow_pickle=True) as z:
+            meta = ast.literal_eval(str(z["meta"][0]))
+            st = dict(meta, terms=[str(t) for t in z["terms"]] if bool(z["has_terms"]) else None,
+                      csr=dict(row_ptr=z["row_ptr"], doc=z["doc"], tf=z["tf"], dl=z["dl"]),
+                      stat=dict(avgdl=float(z["avgdl"]), df=z["df_stat"]))
+        self = cls.__new__(cls)
+        self.__setstate__(st)
+        return self
+
     # ------------------------------------------------------------------ pickling (joblib.dump, :312)
     def __getstate__(self):
         st = dict(k1=self.k1, b=self.b, variant=self.variant, dedup_query=self.dedup_query, terms=self.terms,

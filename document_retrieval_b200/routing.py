@@ -106,3 +106,40 @@ def retrieve_top_n_batch(args):
         return [bm25_model.retrieve_top_n(q, n=k) for q in tokenized_query_batch]
     ids, _ = bm25_model.retrieve_top_n_batch(tokenized_query_batch, k)
     return [r.astype(np.int64) for r in ids.cpu().numpy()]
+
+
+def dedupe_sentences_to_docs(sentence_ids, sentence_to_doc, k=10):
+    """team_run1.py:286-294: walk the ranked sentences, keep the first occurrence of every parent doc, stop
+    at ``k`` docs.  ``sentence_ids`` [Q, n] (best first, -1 pads; numpy or torch), ``sentence_to_doc`` maps a
+    sentence index to its doc index -> int64[Q, k] (-1 pads).  Vectorised on the device the ids live on."""
+    import torch
+    s = torch.as_tensor(sentence_ids)
+    m = torch.as_tensor(sentence_to_doc).to(s.device)
+    valid = s >= 0
+    docs = torch.where(valid, m[s.clamp(min=0).long()], torch.full_like(s, -1, dtype=m.dtype)).long()
+    # first occurrence: no equal doc earlier in the row
+    eq = docs[:, :, None] == docs[:, None, :]
+    earlier = torch.tril(torch.ones(s.shape[1], s.shape[1], dtype=torch.bool, device=s.device), diagonal=-1)
+    first = valid & ~(eq & earlier[None]).any(dim=2)
+    rank = torch.cumsum(first.long(), dim=1) - 1
+    out = torch.full((s.shape[0], k), -1, dtype=torch.long, device=s.device)
+    keep = first & (rank < k)
+    rows = torch.arange(s.shape[0], device=s.device)[:, None].expand_as(s)
+    out[rows[keep], rank[keep]] = docs[keep]
+    return out
+
+
+def mrr_recall_at_k(ranked_docs, relevant_docs, k_values=(1, 5, 10)):
+    """team_run1.py:297-325: mean MRR@k and Recall@k.  ``ranked_docs`` list of ranked id lists,
+    ``relevant_docs`` list of (lists of) relevant ids -> {k: (mrr, recall)}."""
+    out = {}
+    for k in k_values:
+        mrr, rec = [], []
+        for ranked, rel in zip(ranked_docs, relevant_docs):
+            rel = [rel] if isinstance(rel, (str, int, np.integer)) else list(rel)
+            top = [d for d in list(ranked)[:k]]
+            r = next((i + 1 for i, d in enumerate(top) if d in rel), None)
+            mrr.append(1 / r if r else 0)
+            rec.append(len(set(rel) & set(top)) / len(rel) if rel else 0)
+        out[k] = (float(np.mean(mrr)) if mrr else 0.0, float(np.mean(rec)) if rec else 0.0)
+    return out

@@ -1,0 +1,113 @@
+"""GPU: the BASELINE.json configurations at (close to) full size against the plain-C oracle.
+C2: 7 per-language indexes (268,022 docs), 2,000 mixed-language queries, Recall@10 - ids bit-exact.
+C3: BM25 top-1000 -> cosine re-rank (768-d bf16) on the C2 'en' corpus, query subsample.
+C4: size-independent properties on a 1M-doc slice (sharded == single, fused == dense)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bm25_oracle as orc
+from oracle.c_oracle import COracle
+from document_retrieval_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2():
+    return synth.make_c2(scale=1.0)
+
+
+def test_c2_full_recall_and_ids(c2):
+    from document_retrieval_b200 import BM25, evaluate_recall_at_k, retrieve_test_queries
+    langs, queries = c2
+    assert sum(c["n_docs"] for c in langs.values()) == 268_022 and len(queries) == 2_000
+    models, maps, oracles = {}, {}, {}
+    for lang, c in langs.items():
+        models[lang] = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"])
+        maps[lang] = np.arange(c["n_docs"]) + 1_000_000 * (1 + list(langs).index(lang))
+        oracles[lang] = COracle(c["doc_offsets"], c["token_ids"], c["vocab"])
+        assert models[lang].avgdl == oracles[lang].avgdl
+    rows = [dict(query=q["terms"], lang=q["lang"], positive_docs=int(maps[q["lang"]][q["qrel"]]), query_id=i)
+            for i, q in enumerate(queries)]
+    want = [None] * len(rows)
+    for lang in langs:
+        idx = [i for i, r in enumerate(rows) if r["lang"] == lang]
+        terms = np.concatenate([rows[i]["query"] for i in idx]).astype(np.int32)
+        offs = np.cumsum([0] + [rows[i]["query"].size for i in idx]).astype(np.int32)
+        oi, _, _ = oracles[lang].topk_batch(terms, offs, 10)
+        for j, i in enumerate(idx):
+            want[i] = [int(maps[lang][d]) for d in oi[j]]
+    got = retrieve_test_queries(models, maps, rows, k=10)
+    assert [[int(x) for x in g] for g in got] == want                 # every top-10 list identical
+    rec = evaluate_recall_at_k(models, maps, rows, k=10)
+    assert rec == orc.recall_at_k(want, [r["positive_docs"] for r in rows]) and rec > 0.9
+
+
+def test_c3_bm25_top1000_then_cosine(c2):
+    from document_retrieval_b200 import BM25
+    from document_retrieval_b200.cosine import CosineIndex, rerank_bm25_with_cosine
+    c = c2[0]["en"]
+    m = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"])
+    qo, qt, _ = synth.make_queries(c["doc_offsets"], c["token_ids"], 512, c["vocab"], (3, 3))
+    g = torch.Generator(device="cuda").manual_seed(synth.ROOT_SEED + 3)
+    emb = torch.randn(c["n_docs"], 768, generator=g, device="cuda").to(torch.bfloat16)
+    qe = torch.randn(512, 768, generator=g, device="cuda").to(torch.bfloat16)
+    ix = CosineIndex(emb)
+    ids, sims = rerank_bm25_with_cosine(m, ix, (qt, qo), qe, n_candidates=1000, k=10)
+    # BM25 candidates: identical to the oracle's top-1000
+    co = COracle(c["doc_offsets"], c["token_ids"], c["vocab"])
+    oi, _, _ = co.topk_batch(qt, qo, 1000)
+    cand, _ = m.retrieve_top_n_batch((qt, qo), 1000)
+    assert np.array_equal(cand.cpu().numpy(), oi)
+    # cosine over those candidates: fp32 torch restatement of team_run1.py:270-282
+    e32, q32 = emb.float(), qe.float()
+    for i in range(0, 512, 37):
+        cc = torch.from_numpy(oi[i].astype(np.int64)).cuda()
+        d = e32[cc]
+        d = d / (d.norm(dim=1, keepdim=True) + 1e-10)
+        q = q32[i] / (q32[i].norm() + 1e-10)
+        s = d @ q
+        top = torch.topk(s, 10)
+        np.testing.assert_allclose(sims[i].cpu().numpy(), top.values.cpu().numpy(), rtol=1e-5, atol=2e-6)
+        assert set(ids[i].cpu().tolist()) <= set(oi[i].tolist())
+
+
+def test_c4_slice_properties():
+    """1M-doc slice of the C4 shape: fused == dense, 4 fake shards == single index, save/load round trip."""
+    import os
+    import tempfile
+    from document_retrieval_b200 import BM25
+    from document_retrieval_b200.sharded import merge_topk_cuda, shard_bounds
+    do, tk = synth.make_corpus_torch(1_000_000, 1_000_000, 60, "cuda", seed=5)
+    qo, qt, _ = synth.make_queries_torch(do, tk, 2_000, 1_000_000, seed=6)
+    q = (qt, qo)
+    m = BM25.from_token_ids(do, tk, 1_000_000)
+    ids_f, sc_f = m.retrieve_top_n_batch(q, 10)
+    assert m.query_stats()["queries_fused"] > 1900
+    m.set_option("fused", 0)
+    ids_d, sc_d = m.retrieve_top_n_batch(q, 10)
+    m.set_option("fused", 1)
+    assert torch.equal(ids_f, ids_d) and torch.equal(sc_f, sc_d)
+    shards = []
+    for lo, hi in shard_bounds(1_000_000, 4):
+        o = do[lo:hi + 1] - do[lo]
+        t = tk[int(do[lo]):int(do[hi])]
+        shards.append(BM25.from_token_ids(o, t, 1_000_000, doc_base=lo, finalize=False))
+    df = sum(s.local_df_tensor().to(torch.int64) for s in shards).cpu().numpy()
+    n = sum(s.stats()["n_docs"] for s in shards)
+    sdl = sum(s.stats()["sum_dl"] for s in shards)
+    parts = []
+    for s in shards:
+        s.finalize(n, sdl, df)
+        i, sc = s.retrieve_top_n_batch(q, 10)
+        parts.append((torch.where(i >= 0, i.long() + s.doc_base, torch.full_like(i, -1, dtype=torch.long)), sc))
+    ids_m, sc_m = merge_topk_cuda(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), 10)
+    assert torch.equal(ids_m, ids_f.long()) and torch.equal(sc_m, sc_f)
+    del shards
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "index.npz")
+        m.save(path)
+        m2 = BM25.load(path)
+        i2, s2 = m2.retrieve_top_n_batch(q, 10)
+        assert torch.equal(i2, ids_f) and torch.equal(s2, sc_f)

@@ -1,0 +1,42 @@
+"""CPU: host-side helpers that need no GPU (sentence -> doc dedupe, MRR/Recall, compute_idf)."""
+import numpy as np
+
+from oracle import bm25_oracle as orc
+from document_retrieval_b200 import compute_idf, dedupe_sentences_to_docs, mrr_recall_at_k
+
+
+def test_dedupe_sentences_to_docs_matches_reference_loop():
+    rng = np.random.default_rng(3)
+    s2d = rng.integers(0, 40, size=500)
+    ranked = np.stack([rng.permutation(500)[:100] for _ in range(16)])
+    ranked[3, 50:] = -1
+    got = dedupe_sentences_to_docs(ranked, s2d, k=10).numpy()
+    for i in range(16):
+        seen, want = set(), []
+        for s in ranked[i]:                      # team_run1.py:286-294
+            if s < 0:
+                continue
+            d = int(s2d[s])
+            if d not in seen:
+                want.append(d)
+                seen.add(d)
+            if len(want) >= 10:
+                break
+        assert got[i][got[i] >= 0].tolist() == want
+
+
+def test_mrr_recall_matches_oracle():
+    ranked = [[3, 1, 2], [9, 8, 7], [5]]
+    rel = [1, [7, 6], 4]
+    out = mrr_recall_at_k(ranked, rel, (1, 2, 3))
+    for k in (1, 2, 3):
+        m = [orc.mrr_recall_at_k(r, [x] if isinstance(x, int) else x, k) for r, x in zip(ranked, rel)]
+        assert abs(out[k][0] - np.mean([a for a, _ in m])) < 1e-15 and abs(out[k][1] - np.mean([b for _, b in m])) < 1e-15
+
+
+def test_compute_idf_is_the_reference_expression():
+    df = {"a": 1, "b": 50, "c": 99}
+    idf = compute_idf(df, 100)
+    for t, d in df.items():
+        assert idf[t] == float(np.log((100 - d + 0.5) / (d + 0.5)))     # cosine_similarity_bm25_reranking.py:179
+    assert idf["c"] < 0
