@@ -826,7 +826,6 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     // one memset covers thr / cand_cnt / prev_cnt / overflow (contiguous carve)
     BR_CUDA(cudaMemsetAsync(p + o_thr, 0, o_off - o_thr, st));
     BR_CUDA(cudaMemsetAsync(cold_total, 0, 16, st));
-    BR_CUDA(cudaMemsetAsync(cand, 0xFF, 4 * (size_t)nq * TILE_CAP, st));
     k_tile_prep<<<(n_groups + 3) / 4, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, nq, G, umax, entries, n_entries,
                                                     elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)TILE_DENSE_MIN) >> TILE_SHIFT), perm, ix->row_slot);
     BR_CUDA(cudaGetLastError());
