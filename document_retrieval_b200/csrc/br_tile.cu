@@ -40,7 +40,7 @@ constexpr int TILE_W = 8;            // warps per CTA = sub-ranges per tile
 constexpr int TILE_SHIFT = 9;        // 512 docs per sub-range (must equal br_index::sub_shift)
 constexpr int TILE_S = 1 << TILE_SHIFT;
 constexpr int TILE_DOCS_SHIFT = TILE_SHIFT + 3;   // log2(W * S)
-constexpr int TILE_QT = 32;          // max distinct hot terms of one query on this path
+constexpr int TILE_QT = 20;          // max distinct hot terms of one query on this path (more -> dense path)
 constexpr int TILE_CAP = 1024;       // candidates kept per query between tighten rounds
 constexpr uint32_t TILE_DENSE_MIN = 16;  // postings of a term in a 512-doc sub-range from which the warp works cooperatively
 static_assert((1 << 3) == TILE_W, "TILE_DOCS_SHIFT assumes W == 8");
@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
     int64_t* s_base = reinterpret_cast<int64_t*>(ent + a.umax);                          // [umax]
     uint32_t* s_bnd = reinterpret_cast<uint32_t*>(s_base + a.umax);                      // [umax][W+1]
     float4* s_fm = reinterpret_cast<float4*>(s_bnd + a.umax * (TILE_W + 1));             // [umax] multiplicities as floats
+    uint32_t* s_skiprow = reinterpret_cast<uint32_t*>(s_fm + a.umax);                    // [umax] slot * (n_sub+1)
     __shared__ int s_qi[8];                                                              // query of each group slot (-1: none)
 
     const int g = blockIdx.x;
@@ -326,30 +327,29 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
         ent[u] = e;
         s_base[u] = a.row_ptr[e.term];
         s_fm[u] = make_float4((float)e.mult[0], (float)e.mult[1], (float)e.mult[2], (float)e.mult[3]);
+        s_skiprow[u] = (uint32_t)e.slot * (uint32_t)(a.n_sub + 1);      // row terms: slot = row index (unused here)
     }
     // slice bounds of the first tile; the bounds of tile t+1 are fetched into registers while tile t is processed
     constexpr int NB = (TILE_QT * G * (TILE_W + 1) + TILE_W * 32 - 1) / (TILE_W * 32);
-    uint32_t nb[NB];
+    uint32_t nb[NB], bsel[NB];                       // bsel: bit 31 valid | j << 16 | u  (which bound this thread fetches)
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        const int i = threadIdx.x + k * TILE_W * 32;
+        const int u = i / (TILE_W + 1), j = i - u * (TILE_W + 1);
+        bsel[k] = (i < U * (TILE_W + 1) && u >= Ur) ? (0x80000000u | ((uint32_t)j << 16) | (uint32_t)u) : 0u;
+        if (i < U * (TILE_W + 1)) s_bnd[i] = 0;      // row terms keep empty slices
+    }
+    __syncthreads();                                 // s_skiprow is complete
     auto load_bounds = [&](int tile) {
 #pragma unroll
-        for (int k = 0; k < NB; ++k) {
-            const int i = threadIdx.x + k * TILE_W * 32;
-            nb[k] = 0;
-            if (i < U * (TILE_W + 1)) {
-                const int u = i / (TILE_W + 1), j = i - u * (TILE_W + 1);
-                if (u >= Ur) {
-                    const int32_t slot = a.entries[(int64_t)g * a.umax + u].slot;
-                    nb[k] = a.skip[(int64_t)slot * (a.n_sub + 1) + min(tile * TILE_W + j, a.n_sub)];
-                }
-            }
-        }
+        for (int k = 0; k < NB; ++k)
+            if (bsel[k] >> 31)
+                nb[k] = __ldg(a.skip + s_skiprow[bsel[k] & 0xffffu] + min(tile * TILE_W + (int)((bsel[k] >> 16) & 0xfu), a.n_sub));
     };
     auto store_bounds = [&]() {
 #pragma unroll
-        for (int k = 0; k < NB; ++k) {
-            const int i = threadIdx.x + k * TILE_W * 32;
-            if (i < U * (TILE_W + 1)) s_bnd[i] = nb[k];
-        }
+        for (int k = 0; k < NB; ++k)
+            if (bsel[k] >> 31) s_bnd[threadIdx.x + k * TILE_W * 32] = nb[k];
     };
     load_bounds(tile_first);
     store_bounds();
@@ -866,7 +866,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
                cold_off, cold, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, (int)k, 0, 0, 1, dedup ? 0 : 1, perm};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
-                                                                            sizeof(uint32_t) * (TILE_W + 1) + sizeof(float4));
+                                                                            sizeof(uint32_t) * (TILE_W + 1) + sizeof(float4) + sizeof(uint32_t));
     switch (G) {
         case 1: BR_TRY(launch_tiles<1>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
         case 2: BR_TRY(launch_tiles<2>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
