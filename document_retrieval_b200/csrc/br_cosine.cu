@@ -161,7 +161,8 @@ struct CosArgs {
     int64_t n_docs;
     int32_t nq;
     int32_t d;
-    int32_t tile_begin, tile_end;   // doc tiles [tile_begin, tile_end) of 128 rows
+    int32_t tile_begin, tile_end;   // doc tiles [tile_begin, tile_end) of CG_BM rows
+    int32_t debug_skip_epilogue;    // measurement aid (BR_COS_DEBUG_NOEPI): epilogue warps only hand the accumulators back
 };
 
 __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_constant__ CUtensorMap map_docs,
@@ -273,20 +274,37 @@ __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_cons
             const int64_t doc = (int64_t)dt * CG_BM + half * 128 + quarter * 32 + lane;
             const float inv_d = doc < a.n_docs ? a.inv_nd[doc] : 0.f;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)half * CG_BN;
-            for (int c0 = 0; c0 < CG_BN; c0 += 32) {
-                uint32_t v[32];
-                tc_ld_32x32(taddr + c0, v);
+            // Common case (nothing passes) is branch-free: m = max_j (acc_j * inv_d - thr_j) over 32 columns with the
+            // thresholds read as float4; the next 32 columns are already on their way from TMEM.  Only when m >= 0
+            // are the 32 columns rescanned and emitted.
+            uint32_t v[2][32];
+            if (!a.debug_skip_epilogue) tc_ld_32x32(taddr, v[0]);
+#pragma unroll
+            for (int b = 0; b < (CG_BN / 32); ++b) {
+                if (a.debug_skip_epilogue) break;
                 tc_wait_ld();
-                if (doc < a.n_docs) {
+                if (b + 1 < CG_BN / 32) tc_ld_32x32(taddr + (b + 1) * 32, v[(b + 1) & 1]);
+                const uint32_t (&cur)[32] = v[b & 1];
+                const float4* t4 = reinterpret_cast<const float4*>(s_thr + b * 32);
+                float m = -CUDART_INF_F;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 th = t4[j4];
+                    m = fmaxf(m, fmaf(__uint_as_float(cur[4 * j4 + 0]), inv_d, -th.x));
+                    m = fmaxf(m, fmaf(__uint_as_float(cur[4 * j4 + 1]), inv_d, -th.y));
+                    m = fmaxf(m, fmaf(__uint_as_float(cur[4 * j4 + 2]), inv_d, -th.z));
+                    m = fmaxf(m, fmaf(__uint_as_float(cur[4 * j4 + 3]), inv_d, -th.w));
+                }
+                if (m >= 0.f && doc < a.n_docs) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float sc = __uint_as_float(v[j]) * inv_d;
-                        if (sc >= s_thr[c0 + j]) {
-                            const int q = qt * CG_BN + c0 + j;
+                        const float sc = __uint_as_float(cur[j]) * inv_d;
+                        if (sc >= s_thr[b * 32 + j]) {
+                            const int q = qt * CG_BN + b * 32 + j;
                             const int pos = atomicAdd(a.cand_cnt + q, 1);
                             if (pos < COS_CAP) {
                                 a.cand[(int64_t)q * COS_CAP + pos] = (int32_t)doc;
-                                a.cand_h[(int64_t)q * COS_CAP + pos] = sc * s_inq[c0 + j];
+                                a.cand_h[(int64_t)q * COS_CAP + pos] = sc * s_inq[b * 32 + j];
                             }
                         }
                     }
@@ -421,20 +439,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS, 1) k_cos
             const int64_t doc = (int64_t)dt * CG_BM + half * 128 + quarter * 32 + lane;
             const float inv_d = doc < a.n_docs ? a.inv_nd[doc] : 0.f;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)half * CG_BN;
-            for (int c0 = 0; c0 < CG_BN; c0 += 32) {
-                uint32_t v[32];
-                tc_ld_32x32(taddr + c0, v);
+            // Common case (nothing passes) is branch-free: m = max_j (acc_j * inv_d - thr_j) over 32 columns with the
+            // thresholds read as float4; the next 32 columns are already on their way from TMEM.  Only when m >= 0
+            // are the 32 columns rescanned and emitted.
+            uint32_t v[2][32];
+            if (!a.debug_skip_epilogue) tc_ld_32x32(taddr, v[0]);
+#pragma unroll
+            for (int b = 0; b < (CG_BN / 32); ++b) {
+                if (a.debug_skip_epilogue) break;
                 tc_wait_ld();
-                if (doc < a.n_docs) {
+                if (b + 1 < CG_BN / 32) tc_ld_32x32(taddr + (b + 1) * 32, v[(b + 1) & 1]);
+                const uint32_t (&cur)[32] = v[b & 1];
+                const float4* t4 = reinterpret_cast<const float4*>(s_thr + b * 32);
+                float m = -CUDART_INF_F;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 th = t4[j4];
+                    m = fmaxf(m, fmaf(__uint_as_float(cur[4 * j4 + 0]), inv_d, -th.x));
+                    m = fmaxf(m, fmaf(__uint_as_float(cur[4 * j4 + 1]), inv_d, -th.y));
+                    m = fmaxf(m, fmaf(__uint_as_float(cur[4 * j4 + 2]), inv_d, -th.z));
+                    m = fmaxf(m, fmaf(__uint_as_float(cur[4 * j4 + 3]), inv_d, -th.w));
+                }
+                if (m >= 0.f && doc < a.n_docs) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float sc = __uint_as_float(v[j]) * inv_d;
-                        if (sc >= s_thr[c0 + j]) {
-                            const int q = qt * CG_BN + c0 + j;
+                        const float sc = __uint_as_float(cur[j]) * inv_d;
+                        if (sc >= s_thr[b * 32 + j]) {
+                            const int q = qt * CG_BN + b * 32 + j;
                             const int pos = atomicAdd(a.cand_cnt + q, 1);
                             if (pos < COS_CAP) {
                                 a.cand[(int64_t)q * COS_CAP + pos] = (int32_t)doc;
-                                a.cand_h[(int64_t)q * COS_CAP + pos] = sc * s_inq[c0 + j];
+                                a.cand_h[(int64_t)q * COS_CAP + pos] = sc * s_inq[b * 32 + j];
                             }
                         }
                     }
@@ -667,7 +702,8 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     int t0 = 0, chunk = 1;
     while (t0 < n_dt) {
         const int nt = std::min(chunk, n_dt - t0);
-        CosArgs a{inv_nd, inv_nq, thr, (int32_t*)b_cnt.p, (int32_t*)b_cand.p, (float*)b_h.p, n_docs, nq, d, t0, t0 + nt};
+        CosArgs a{inv_nd, inv_nq, thr, (int32_t*)b_cnt.p, (int32_t*)b_cand.p, (float*)b_h.p, n_docs, nq, d, t0, t0 + nt,
+                  getenv("BR_COS_DEBUG_NOEPI") ? 1 : 0};
         if (use_mc) {
             const int grid = 2 * (int)std::min<int64_t>((int64_t)nt * ((n_qt + 1) / 2), kNumSMs / 2);
             k_cosine_gemm_mc<<<grid, CG_THREADS, CG_SMEM, st>>>(map_d, map_q, a);

@@ -153,7 +153,8 @@ struct SelView {
 constexpr int SEL_T = 1024;
 
 __global__ void __launch_bounds__(SEL_T) k_select_radix(const float* __restrict__ scores, int64_t n_docs, int32_t k,
-                                                        int positive_only, SelView sv, int32_t q_begin) {
+                                                        int positive_only, SelView sv, int32_t q_begin,
+                                                        const int32_t* __restrict__ n_terms) {
     __shared__ uint32_t hist[2048];
     __shared__ uint32_t s_bin, s_above;
     __shared__ unsigned long long s_cnt[2];
@@ -195,7 +196,9 @@ __global__ void __launch_bounds__(SEL_T) k_select_radix(const float* __restrict_
     } else {
         const float kth = key_score(kth_key);
         if (!positive_only && kth == 0.0f) mode = 1; // fewer than k positive docs: zero tail in doc order
-        lo = kth - kBandRel * fabsf(kth);
+        // fp32 error of an n-term sum grows with n: widen the band for unusually long queries
+        const float band = kBandRel * (float)max(1, (n_terms[q] + 31) / 32);
+        lo = kth - band * fabsf(kth);
     }
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -662,7 +665,7 @@ static int topk_dense(br_index* ix, const int32_t* q_off, const PrepView& pv, co
         k_score_dense<<<kNumSMs * 8, 256, 0, st>>>(post, ix->row_ptr, q_off, pv, chunk_start, b0, bn, dense, N);
         BR_CUDA(cudaGetLastError());
         ix->prof_end(st);
-        k_select_radix<<<bn, SEL_T, 0, st>>>(dense, N, k, positive_only, sv, b0);
+        k_select_radix<<<bn, SEL_T, 0, st>>>(dense, N, k, positive_only, sv, b0, dedup ? pv.u_cnt : pv.o_cnt);
         BR_CUDA(cudaGetLastError());
         BR_CUDA(cudaMemcpyAsync(h_cnt.data(), sv.cnt + b0, sizeof(int64_t) * (size_t)bn, cudaMemcpyDeviceToHost, st));
         BR_CUDA(cudaStreamSynchronize(st));

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
         }
         for (int o = 16; o > 0; o >>= 1) cold += __shfl_xor_sync(0xffffffffu, cold, o);
         bad = __any_sync(0xffffffffu, bad);
-        const bool ok = hot <= TILE_QT && !bad;
+        const bool ok = hot <= TILE_QT && !bad && pv.o_cnt[q] <= 32;   // longer queries: dense path (wider fp32 band)
         if (lane == 0) elig[q] = ok ? 1 : 0;
         if (!ok) continue;
         cold_sum += cold;
