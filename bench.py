@@ -321,10 +321,12 @@ def main():
     line = {
         "metric": "BM25 top-10 queries/sec", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32 accumulate + f64 re-score", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "sharding": f"docs over {world} GPU(s), NCCL all-gather of [Q,k] + merge",
                    "l2_policy": "inputs (packed postings, %.2f GB per GPU) larger than L2" % (st["nnz"] * 8 / 1e9),
-                   "index_build_s": build_s, "postings_per_gpu": st["nnz"], "recall_at_10_vs_source_doc": recall},
+                   "index_build_s": build_s, "postings_per_gpu": st["nnz"], "recall_at_10_vs_source_doc": recall,
+                   "arithmetic": "fp32 accumulation of precomputed posting weights, float64 re-score of the candidate band "
+                                 "(ids bit-exact against the float64 reference)"},
         "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h_terms.numel() * 4 + h_off.numel() * 4),
                 "d2h_bytes_per_step": int(h_out.numel() * 8)},
         "gpu_launches": int(qstats["kernel_launches"]) * args.steps,
