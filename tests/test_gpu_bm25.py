@@ -300,3 +300,24 @@ def test_rerank_v3_and_tfidf_pipeline_match_reference_golden(golden, tmp_path):
             assert mine[j] == d, (i, j, mine, ref)
             checked += 1
     assert checked > 50
+
+
+def test_long_and_duplicate_heavy_queries():
+    """Queries with more than 32 terms (dense path, wider fp32 band) and heavy duplication."""
+    c = synth.make_config("C1", scale=0.3)
+    from document_retrieval_b200 import BM25
+    rng = np.random.default_rng(11)
+    qs = []
+    for i in range(12):
+        d = int(rng.integers(0, c["n_docs"]))
+        toks = c["token_ids"][c["doc_offsets"][d]:c["doc_offsets"][d + 1]]
+        qs.append(np.concatenate([toks[:60], toks[:5], toks[:5]]).astype(np.int32))   # ~50 distinct terms, duplicates
+    q_off = np.cumsum([0] + [q.size for q in qs]).astype(np.int32)
+    q_terms = np.concatenate(qs)
+    for variant, dedup in (("notebook", True), ("okapi", False)):
+        m = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"], variant=variant, dedup_query=dedup)
+        co = COracle(c["doc_offsets"], c["token_ids"], c["vocab"], variant=variant)
+        oi, os_, _ = co.topk_batch(q_terms, q_off, 10, dedup=dedup)
+        ids, sc = m.retrieve_top_n_batch((q_terms, q_off), 10)
+        assert np.array_equal(ids.cpu().numpy(), oi) and np.array_equal(sc.cpu().numpy(), os_)
+        assert m.query_stats()["queries_dense"] == len(qs)
