@@ -725,7 +725,9 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
                         int32_t* prev_cnt, int32_t* overflow) {
     BR_CUDA(cudaFuncSetAttribute(k_tile_score<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device
     // chunks of doubling size: thresholds learnt on the first 2^c tiles filter the next 2^c
-    int t0 = 0, chunk = 1;
+    // first chunk: as many tiles as the candidate buffer certainly holds with thresholds still at zero
+    // (every sub-range can emit up to ~3k docs before its first tightening)
+    int t0 = 0, chunk = std::max(1, std::min(4, TILE_CAP / (TILE_W * 3 * a0.K)));
     while (t0 < n_tiles) {
         const int ny = std::min(std::min(chunk, n_tiles - t0), 32768);
         TileArgs a = a0;
