@@ -37,7 +37,10 @@
 namespace br {
 
 constexpr int TILE_W = 8;            // warps per CTA = sub-ranges per tile
-constexpr int TILE_SHIFT = 9;        // 512 docs per sub-range (must equal br_index::sub_shift)
+#ifndef BR_TILE_SHIFT
+#define BR_TILE_SHIFT 9
+#endif
+constexpr int TILE_SHIFT = BR_TILE_SHIFT;   // 512 docs per sub-range (must equal br_index::sub_shift)
 constexpr int TILE_S = 1 << TILE_SHIFT;
 constexpr int TILE_DOCS_SHIFT = TILE_SHIFT + 3;   // log2(W * S)
 constexpr int TILE_QT = 20;          // max distinct hot terms of one query on this path (more -> dense path)
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
         // query (terms present in >= ~20% of the docs are stored as plain fp32 rows, 0 where absent), 4 docs per lane
         const uint32_t d0 = (uint32_t)(sub0 + w) << TILE_SHIFT;
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {                  // 256 docs per pass: 2 x (4 docs per lane)
+        for (int half = 0; half < TILE_S / 256; ++half) {       // 256 docs per pass: 2 x (4 docs per lane)
             float4 v[G][2];
 #pragma unroll
             for (int q = 0; q < G; ++q) v[q][0] = v[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
