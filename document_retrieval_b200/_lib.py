@@ -41,6 +41,13 @@ SIGNATURES = {
     "br_last_query_stats": (C.c_int, [_P, _P]),
     "br_set_profiling": (C.c_int, [_P, C.c_int]),
     "br_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "br_tokenize_count": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.POINTER(C.c_int64), _P]),
+    "br_vocab_build": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_int64, _P, _P, C.POINTER(_P)]),
+    "br_vocab_lookup": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P, C.c_int64, _P, _P]),
+    "br_vocab_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "br_vocab_export": (C.c_int, [_P, _P, _P]),
+    "br_vocab_import": (C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(_P)]),
+    "br_vocab_destroy": (None, [_P]),
 }
 
 

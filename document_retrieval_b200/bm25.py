@@ -39,8 +39,9 @@ class BM25:
         self.dedup_query = (variant == "notebook") if dedup_query is None else bool(dedup_query)
         self._device = device
         self._h = None                 # br_index*
-        self.vocab = None              # str -> term id (string API only)
-        self.terms = None              # term id -> str
+        self._vocab = None             # str -> term id (string API only; lazy when built from texts)
+        self._terms = None             # term id -> str
+        self.vocabulary = None         # ingest.Vocabulary (GPU hash table) when built with from_texts
         self.vocab_size = 0
         self.corpus_size = 0
         self.avgdl = 0.0
@@ -64,9 +65,57 @@ class BM25:
         flat = [w for d in tokenized_corpus for w in d]
         codes, uniques = pd.factorize(np.asarray(flat, dtype=object)) if flat else (np.zeros(0, np.int64), [])
         self.terms = [str(u) for u in uniques]
-        self.vocab = {w: i for i, w in enumerate(self.terms)}
+        self.vocabulary = None
         self._build_ids(doc_offsets, codes.astype(np.int32), max(len(self.terms), 1))
         return self
+
+    # term strings: plain attributes for build(list[list[str]]), decoded lazily from the GPU vocabulary's
+    # byte pool for from_texts (only the dict-valued attributes and list[str] queries need them)
+    @property
+    def terms(self):
+        if self._terms is None and self.vocabulary is not None:
+            self._terms = self.vocabulary.terms
+        return self._terms
+
+    @terms.setter
+    def terms(self, v):
+        self._terms, self._vocab = v, None
+
+    @property
+    def vocab(self):
+        if self._vocab is None and self.terms is not None:
+            self._vocab = {w: i for i, w in enumerate(self.terms)}
+        return self._vocab
+
+    @vocab.setter
+    def vocab(self, v):
+        self._vocab = v
+
+    @classmethod
+    def from_texts(cls, texts, k1=1.5, b=0.75, *, bigrams=False, variant="notebook", dedup_query=None, device=None):
+        """Build from preprocessed text instead of token lists: ``BM25([t.split() for t in texts])``
+        (bm25_ranking.ipynb:299,306) with the tokenisation, the first-seen vocabulary and - with
+        ``bigrams=True`` - the 2-gram expansion of bm25_ranking.ipynb:105-107 done on the GPU
+        (ingest.py / csrc/br_ingest.cu).  Query with ``retrieve_top_n_texts`` (texts) or the usual
+        token-list calls."""
+        from .ingest import Vocabulary
+        self = cls(None, k1, b, variant=variant, dedup_query=dedup_query, device=device)
+        voc, doc_off, ids = Vocabulary.from_texts(texts, bigrams=bigrams, device=device)
+        self.vocabulary = voc
+        self._device = voc.device
+        self._build_ids(doc_off, ids, max(len(voc), 1))
+        return self
+
+    def retrieve_top_n_texts(self, query_texts, n=10, **kw):
+        """``retrieve_top_n_batch([q.split() for q in query_texts], n)`` with the queries tokenised and
+        looked up on the GPU (bm25_ranking.ipynb:341-347: ``tokenized_query = preprocessed_query.split()``)."""
+        if self.vocabulary is None:
+            from .ingest import Vocabulary
+            if self.terms is None:
+                raise BRError("retrieve_top_n_texts needs a model with a string vocabulary")
+            self.vocabulary = Vocabulary.from_terms(self.terms, device=self._device)
+        q_terms, q_off = self.vocabulary.encode_texts(query_texts)
+        return self.retrieve_top_n_batch((q_terms, q_off), n, **kw)
 
     @classmethod
     def from_token_ids(cls, doc_offsets, token_ids, vocab_size, k1=1.5, b=0.75, *, variant="notebook",
@@ -405,7 +454,6 @@ class BM25:
     def __setstate__(self, st):
         self.__init__(None, st["k1"], st["b"], variant=st["variant"], dedup_query=st["dedup_query"])
         self.terms = st["terms"]
-        self.vocab = None if self.terms is None else {w: i for i, w in enumerate(self.terms)}
         self.vocab_size, self.corpus_size, self.doc_base = st["vocab_size"], st["corpus_size"], st["doc_base"]
         c = st["csr"]
         if c is None:

@@ -92,3 +92,26 @@ class ShardedBM25:
         if all_ids.shape[0] == 1:
             return gids, sc
         return self.merge(all_ids, all_sc, n)
+
+
+class ShardedCosineIndex:
+    """Row-sharded brute-force cosine top-k (BASELINE config 5: 10 M x 768 bf16 over 8 GPUs; the
+    reference's single-process path is team_run1.py:269-282).  Each rank holds the embedding rows
+    ``[row_base, row_base + n_local)``, queries are replicated (10 k x 768 x 2 B = 15 MB), every rank
+    runs the fused GEMM + top-k on its rows and only the [Q, k] (global row, cosine) candidates are
+    all-gathered and merged - bit-identical to the single-GPU result because top-k over a row
+    partition is exactly decomposable and ties break on the global row id."""
+
+    def __init__(self, local_embeddings, row_base, device=None, group=None, merge=merge_topk_cuda):
+        from .cosine import CosineIndex
+        self.local = CosineIndex(local_embeddings, device=device, doc_base=row_base)
+        self.group, self.merge = group, merge
+
+    def topk(self, query_embeddings, k=10):
+        """-> (global rows int64[Q, k], cosine float64[Q, k] (fp32 values widened)) on every rank."""
+        ids, sims = self.local.topk(query_embeddings, k)
+        sims = sims.to(torch.float64)
+        all_ids, all_sc = gather_candidates(ids, sims, self.group)
+        if all_ids.shape[0] == 1:
+            return ids, sims
+        return self.merge(all_ids, all_sc, k)

@@ -197,6 +197,44 @@ int br_set_profiling(br_index* ix, int on);
  * "tile_g" (queries per group of the tiled kernel: 0 auto, 1, 2, 4 or 8). */
 int br_set_option(br_index* ix, const char* name, int value);
 
+/* ---------------------------------------------------------------------------------------------
+ * Text ingestion: preprocessed text -> term ids (the step right before the index build).
+ * Replaces `lang_tokenized_corpus = [text.split() for text in lang_texts]`
+ * (bm25_ranking.ipynb:299), the first-seen vocabulary that the dict inserts of BM25.build create
+ * (bm25_ranking.ipynb:180-186) and, with bigrams != 0, the 2-gram expansion
+ * `tokens + ['_'.join(gram) for gram in ngrams(tokens, 2)]` (bm25_ranking.ipynb:105-107).
+ *
+ * text_dev is one UTF-8 buffer holding all documents back to back; doc_byte_off_dev int64[n_docs+1]
+ * gives each document's byte range (the Arrow large_string layout).  Tokens are maximal runs of
+ * characters for which Python's str.isspace() is false (str.split() semantics, Unicode whitespace
+ * included); a token never crosses a document boundary.  Term ids are dense, in order of first
+ * occurrence (document order; inside a document unigrams first, then bigrams), i.e. the insertion
+ * order of the reference's dicts.  Terms are matched through a 64-bit hash and every token is
+ * byte-compared with the first occurrence of its term: a hash collision is an error
+ * (BR_ERR_UNSUPPORTED), never a silent merge.
+ *
+ * Call order: br_tokenize_count (fills doc_tok_off_dev int64[n_docs+1] = br_index_build's
+ * doc_offsets, returns the token total) -> caller allocates token_ids_dev int32[n_tokens] ->
+ * br_vocab_build (corpus: creates the vocabulary) or br_vocab_lookup (queries: ids under an
+ * existing vocabulary, -1 = out of vocabulary, which the scoring kernels skip like
+ * `if word not in self.idf: continue`, bm25_ranking.ipynb:195-196).  All three synchronise `stream`. */
+typedef struct br_vocab br_vocab;
+int br_tokenize_count(const uint8_t* text_dev, const int64_t* doc_byte_off_dev, int64_t n_docs, int bigrams,
+                      int64_t* doc_tok_off_dev, int64_t* n_tokens_host, void* stream);
+int br_vocab_build(const uint8_t* text_dev, const int64_t* doc_byte_off_dev, int64_t n_docs, int bigrams,
+                   const int64_t* doc_tok_off_dev, int64_t n_tokens, int32_t* token_ids_dev, void* stream,
+                   br_vocab** out);
+int br_vocab_lookup(const br_vocab* v, const uint8_t* text_dev, const int64_t* doc_byte_off_dev, int64_t n_docs,
+                    int bigrams, const int64_t* doc_tok_off_dev, int64_t n_tokens, int32_t* token_ids_dev,
+                    void* stream);
+int br_vocab_stats(const br_vocab* v, int64_t* n_terms, int64_t* pool_bytes);
+/* Vocabulary strings: term t = pool[pool_off[t] .. pool_off[t+1]) (UTF-8).  Export for the Python
+ * dict attributes (df / idf / inverted_index keys) and for pickling; import rebuilds the hash table. */
+int br_vocab_export(const br_vocab* v, int64_t* pool_off_host, uint8_t* pool_host);
+int br_vocab_import(const int64_t* pool_off_host, const uint8_t* pool_host, int64_t n_terms, void* stream,
+                    br_vocab** out);
+void br_vocab_destroy(br_vocab* v);
+
 #ifdef __cplusplus
 }
 #endif

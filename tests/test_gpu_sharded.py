@@ -41,3 +41,20 @@ def test_fake_shards_equal_single_index(world):
 def test_reduce_stats_single_process():
     df, n, s = reduce_stats(torch.tensor([1, 2, 3], dtype=torch.int32, device="cuda"), 5, 17)
     assert df.tolist() == [1, 2, 3] and (n, s) == (5, 17)
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_fake_cosine_shards_equal_single_index(world):
+    """Row-sharded brute-force cosine (config 5 layout): per-shard br_cosine_topk with doc_base + br_topk_merge
+    equals the single-index call bit for bit."""
+    from document_retrieval_b200.cosine import CosineIndex
+    g = torch.Generator(device="cuda").manual_seed(9)
+    docs = torch.randn(20_000, 256, generator=g, device="cuda").to(torch.bfloat16)
+    docs[777] = docs[12_345]                      # an exact tie across shards -> lower global row first
+    qs = torch.cat([torch.randn(300, 256, generator=g, device="cuda").to(torch.bfloat16), docs[777:778]])
+    ids1, s1 = CosineIndex(docs).topk(qs, 10)
+    parts = [CosineIndex(docs[lo:hi], doc_base=lo).topk(qs, 10) for lo, hi in shard_bounds(docs.shape[0], world)]
+    ids_m, sc_m = merge_topk_cuda(torch.stack([p[0] for p in parts]), torch.stack([p[1].double() for p in parts]), 10)
+    assert torch.equal(ids_m, ids1)
+    assert torch.equal(sc_m, s1.double())
+    assert ids1[-1, :2].tolist() == [777, 12_345]

@@ -40,3 +40,15 @@ def test_compute_idf_is_the_reference_expression():
     for t, d in df.items():
         assert idf[t] == float(np.log((100 - d + 0.5) / (d + 0.5)))     # cosine_similarity_bm25_reranking.py:179
     assert idf["c"] < 0
+
+
+def test_pack_texts_arrow_layout():
+    from document_retrieval_b200.ingest import pack_texts
+    texts = ["a b", "", None, "été  x", 3.5, "한국어"]
+    data, off = pack_texts(texts)
+    clean = [t if isinstance(t, str) else "" for t in texts]        # bm25_ranking.ipynb:85-86
+    enc = [t.encode("utf-8") for t in clean]
+    assert data.tobytes() == b"".join(enc)
+    assert off.tolist() == np.concatenate([[0], np.cumsum([len(e) for e in enc])]).tolist()
+    d0, o0 = pack_texts([])
+    assert d0.size == 0 and o0.tolist() == [0]
