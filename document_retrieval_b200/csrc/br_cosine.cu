@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math_constants.h>
+#include <string.h>
 
 #include "br_common.cuh"
 #include "br_kernels.cuh"
@@ -131,6 +132,15 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tc_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzle operand tile (rows of 64 bf16 = 128 B, 8-row swizzle atoms of 1024 B):
@@ -163,6 +173,7 @@ struct CosArgs {
     int32_t d;
     int32_t tile_begin, tile_end;   // doc tiles [tile_begin, tile_end) of CG_BM rows
     int32_t debug_skip_epilogue;    // measurement aid (BR_COS_DEBUG_NOEPI): epilogue warps only hand the accumulators back
+    int32_t window;                 // query-stationary kernel: doc tiles per L2 window
 };
 
 __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_constant__ CUtensorMap map_docs,
@@ -489,6 +500,305 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS, 1) k_cos
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Query-stationary CTA-pair variant (the default for d <= 768): tcgen05.mma.cta_group::2, M = 256 docs per pair
+// (128 per CTA = its 128 TMEM lanes), N = 224 queries per pair (112 rows of B in each CTA's shared memory).
+//   * the pair's query block stays RESIDENT in shared memory for its whole K extent (12 k-blocks x 14 KB per CTA) while
+//     doc tiles stream past it through a 3-stage ring of 16 KB - operand traffic L2->SM drops from 48 KB to 16 KB per
+//     64-deep k-block per SM, below what the L2 can deliver at full tensor rate;
+//   * the accumulators are double-buffered in TMEM (2 x 224 of the 512 columns), so the epilogue of tile i (tcgen05.ld,
+//     normalise, threshold filter) runs under the MMAs of tile i+1;
+//   * work units (query block, doc tile) are enumerated query-block-major inside windows of QS_WINDOW doc tiles (~50 MB
+//     of embeddings, L2-resident) and split evenly over the pairs, so a pair reloads its query block only once or
+//     twice per window and every doc tile comes from HBM once per launch.
+// Barriers live in the leader CTA (rank 0) where the single MMA-issuing thread waits; the peer's TMA loads complete
+// on the leader's barriers (.cta_group::2), and tcgen05.commit multicasts the "slot free" / "accumulator ready"
+// arrivals to both CTAs.
+// ------------------------------------------------------------------------------------------
+constexpr int QS_NKB = 12;
+constexpr int QS_A_BYTES = 128 * CG_BK * 2;            // 16 KB: this CTA's 128 doc rows of one k-block
+constexpr int QS_THREADS = 320;                        // warp 0 TMA, warp 1 MMA / TMEM alloc, warps 2-9 epilogue
+template <int BN, int STAGES>
+struct QsCfg {
+    static constexpr int BNH = BN / 2;                                  // query rows held by each CTA
+    static constexpr int B_BYTES = BNH * CG_BK * 2;                     // one k-block of them
+    static constexpr size_t SMEM = 1024 + (size_t)QS_NKB * B_BYTES + (size_t)STAGES * QS_A_BYTES + 2 * BN * sizeof(float) + 8 * (2 * STAGES + 6) + 16;
+    // instruction descriptor: D=f32, A=B=bf16 K-major, N=BN (>>3 at bit 17), M=256 (>>4 at bit 24; the pair's M)
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    static_assert(SMEM <= 232448, "query block + doc ring exceed the shared memory of one SM");
+    static_assert(BN % 32 == 0 && BN <= 256, "BN: multiple of 32 (epilogue column chunks), two accumulator stages in 512 TMEM columns");
+};
+
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {   // shared::cta address -> shared::cluster address in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into MY shared memory whose completion bytes are counted on a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+// Work units (query block, doc tile) of one pair.  Doc tiles are taken in windows of `window` tiles (L2-sized); inside a
+// window the n_qb x wl units are enumerated query-block-major and split evenly over the pairs, so that ALL pairs work on
+// the same window at the same time (its doc rows come from HBM once and from L2 for every other query block) and a
+// pair changes its resident query block at most about twice per window.
+struct QsIter {
+    int n_qb, n_dt, window, pair, n_pairs;
+    int w, wl, qb, t;
+    int64_t r, re;
+    bool valid;
+    __device__ __forceinline__ bool open_window() {
+        for (; w * window < n_dt; ++w) {
+            wl = min(window, n_dt - w * window);
+            const int64_t uw = (int64_t)n_qb * wl;
+            r = (int64_t)pair * uw / n_pairs;
+            re = (int64_t)(pair + 1) * uw / n_pairs;
+            if (r < re) {
+                qb = (int)(r / wl);
+                t = (int)(r - (int64_t)qb * wl);
+                return true;
+            }
+        }
+        return false;
+    }
+    __device__ __forceinline__ QsIter(int n_qb_, int n_dt_, int window_, int pair_, int n_pairs_)
+        : n_qb(n_qb_), n_dt(n_dt_), window(window_), pair(pair_), n_pairs(n_pairs_), w(0), wl(0), qb(0), t(0), r(0), re(0) {
+        valid = open_window();
+    }
+    __device__ __forceinline__ int tile() const { return w * window + t; }
+    __device__ __forceinline__ void next() {
+        if (++r == re) {
+            ++w;
+            valid = open_window();
+        } else if (++t == wl) {
+            t = 0;
+            ++qb;
+        }
+    }
+};
+
+template <int QS_BN, int QS_STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QS_THREADS, 1) k_cosine_gemm_qs(const __grid_constant__ CUtensorMap map_docs,
+                                                               const __grid_constant__ CUtensorMap map_q, CosArgs a) {
+    using Cfg = QsCfg<QS_BN, QS_STAGES>;
+    constexpr int QS_BNH = Cfg::BNH, QS_B_BYTES = Cfg::B_BYTES;
+    constexpr uint32_t QS_IDESC = Cfg::IDESC;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;             // 128B swizzle needs 1024-byte alignment
+    unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t s_b = base;                                                // [QS_NKB][112 x 64] resident query block (my half)
+    const uint32_t s_a = base + QS_NKB * QS_B_BYTES;                          // [QS_STAGES][128 x 64] doc ring
+    float* s_thr = reinterpret_cast<float*>(gen + QS_NKB * QS_B_BYTES + QS_STAGES * QS_A_BYTES);   // [QS_BN]
+    float* s_inq = s_thr + QS_BN;                                                                   // [QS_BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_inq + QS_BN);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * QS_STAGES + 6);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };                      // leader: doc stage filled (both CTAs' bytes)
+    auto empty_bar = [&](int s) { return bar0 + 8u * (QS_STAGES + s); };       // each CTA: doc stage consumed
+    const uint32_t bfull_bar = bar0 + 8u * (2 * QS_STAGES);                    // leader: query block resident
+    const uint32_t bempty_bar = bar0 + 8u * (2 * QS_STAGES + 1);               // each CTA: query block no longer read
+    auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * QS_STAGES + 2 + b); };   // each CTA: accumulator stage ready
+    auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * QS_STAGES + 4 + b); };  // leader: accumulator stage drained (16 warps)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_rank();
+    const int n_qb = (a.nq + QS_BN - 1) / QS_BN;
+    const int n_dt = a.tile_end - a.tile_begin;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_kb = (a.d + CG_BK - 1) / CG_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < QS_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(bfull_bar, 1);
+        mbar_init(bempty_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                   // the peer's barriers exist before anything arrives on them
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs: my half of the query block, my 128 rows of every doc tile) =====
+        if (lane == 0) {
+            const uint32_t l_bfull = mapa_rank(bfull_bar, 0);
+            int stage = 0, cur_qb = -1;
+            uint32_t phase = 0, b_phase = 0;
+            for (QsIter it(n_qb, n_dt, a.window, pair, n_pairs); it.valid; it.next()) {
+                struct { int qb, tile; } un{it.qb, it.tile()};
+                if (un.qb != cur_qb) {
+                    cur_qb = un.qb;
+                    mbar_wait(bempty_bar, b_phase ^ 1);             // every MMA that read the previous block has retired
+                    b_phase ^= 1;
+                    if (crank == 0) mbar_expect_tx(bfull_bar, 2u * (uint32_t)n_kb * QS_B_BYTES);
+                    for (int kb = 0; kb < n_kb; ++kb)
+                        tma_load_2d_pair(s_b + kb * QS_B_BYTES, &map_q, l_bfull, kb * CG_BK, un.qb * QS_BN + (int)crank * QS_BNH);
+                }
+                const int row0 = (a.tile_begin + un.tile) * CG_BM + (int)crank * 128;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (crank == 0) mbar_expect_tx(full_bar(stage), 2u * QS_A_BYTES);
+                    tma_load_2d_pair(s_a + stage * QS_A_BYTES, &map_docs, mapa_rank(full_bar(stage), 0), kb * CG_BK, row0);
+                    if (++stage == QS_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
+        if (lane == 0 && crank == 0) {
+            int stage = 0, cur_qb = -1, acc = 0;
+            uint32_t phase = 0, bf_phase = 0, acc_phase[2] = {0, 0};
+            for (QsIter it(n_qb, n_dt, a.window, pair, n_pairs); it.valid; it.next()) {
+                struct { int qb, tile; } un{it.qb, it.tile()};
+                if (un.qb != cur_qb) {
+                    cur_qb = un.qb;
+                    mbar_wait(bfull_bar, bf_phase);
+                    bf_phase ^= 1;
+                }
+                mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1);     // both CTAs' epilogue warps have drained this stage
+                acc_phase[acc] ^= 1;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(s_a + stage * QS_A_BYTES);
+                    const uint64_t db = umma_desc_sw128(s_b + kb * QS_B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < CG_BK / 16; ++k)
+                        tc_mma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), QS_IDESC, (kb | k) != 0);
+                    tc_commit_pair(empty_bar(stage), (uint16_t)3);   // doc slot free in both CTAs once these MMAs retire
+                    if (++stage == QS_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_pair(tfull_bar(acc), (uint16_t)3);         // accumulators ready for both CTAs' epilogue warps
+                QsIter nx = it;
+                nx.next();
+                if (!nx.valid || nx.qb != cur_qb) tc_commit_pair(bempty_bar, (uint16_t)3);   // last tile under this query block
+                acc ^= 1;
+            }
+        }
+    } else {
+        // ===== epilogue warps: warp reads TMEM lanes [32*(warp%4), +32) = doc rows of this CTA's half of the tile; the two
+        //       warps of a lane quarter split the query columns.  A tcgen05.ld queues behind the UMMAs already issued, so
+        //       ALL of a warp's columns are requested up front (NCH x 16 registers) and waited for once. =====
+        constexpr int NCH = QS_BN / 32;                                // 16-column chunks per warp
+        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
+        const int col0 = chalf * (QS_BN / 2);
+        const int et = (int)threadIdx.x - 64;                       // 0..255
+        const uint32_t l_tempty0 = mapa_rank(tempty_bar(0), 0), l_tempty1 = mapa_rank(tempty_bar(1), 0);
+        int cur_qb = -1, acc = 0;
+        uint32_t acc_phase[2] = {0, 0};
+        for (QsIter it(n_qb, n_dt, a.window, pair, n_pairs); it.valid; it.next()) {
+            struct { int qb, tile; } un{it.qb, it.tile()};
+            if (un.qb != cur_qb) {
+                cur_qb = un.qb;
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // previous block's thresholds no longer in use
+                if (et < QS_BN) {
+                    const int q = un.qb * QS_BN + et;
+                    float th = CUDART_INF_F, iq = 0.f;
+                    if (q < a.nq) {
+                        iq = a.inv_nq[q];
+                        const float raw = __ldcg(a.thr + q) / iq;      // compare acc*inv_d against thr/inv_q
+                        th = raw - fabsf(raw) * 4e-6f;                  // superset: rounding of the division
+                    }
+                    s_thr[et] = th;
+                    s_inq[et] = iq;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            const int64_t doc = (int64_t)(a.tile_begin + un.tile) * CG_BM + (int)crank * 128 + quarter * 32 + lane;
+            const float inv_d = doc < a.n_docs ? a.inv_nd[doc] : 0.f;
+            mbar_wait(tfull_bar(acc), acc_phase[acc]);
+            acc_phase[acc] ^= 1;
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)col0;
+            if (!a.debug_skip_epilogue) {
+                // common case (nothing passes) is branch-free: m = max_j (acc_j * inv_d - thr_j) over all my columns
+                float m = -CUDART_INF_F;
+                {
+                    uint32_t v[NCH][16];
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) tc_ld_32x16(taddr + c * 16, v[c]);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const float4* t4 = reinterpret_cast<const float4*>(s_thr + col0 + c * 16);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 th = t4[j4];
+                            m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 0]), inv_d, -th.x));
+                            m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 1]), inv_d, -th.y));
+                            m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 2]), inv_d, -th.z));
+                            m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 3]), inv_d, -th.w));
+                        }
+                    }
+                }
+                // rare: some doc row of this warp has a passing column - read the columns again, 16 at a time (the
+                // tcgen05.ld is warp-collective, so the whole warp takes the branch) and emit
+                if (__any_sync(0xffffffffu, m >= 0.f && doc < a.n_docs)) {
+#pragma unroll 1
+                    for (int c = 0; c < NCH; ++c) {
+                        uint32_t e[16];
+                        tc_ld_32x16(taddr + c * 16, e);
+                        tc_wait_ld();
+                        if (m >= 0.f && doc < a.n_docs) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float sc = __uint_as_float(e[j]) * inv_d;
+                                const int col = col0 + c * 16 + j;
+                                if (sc >= s_thr[col]) {
+                                    const int q = un.qb * QS_BN + col;
+                                    const int pos = atomicAdd(a.cand_cnt + q, 1);
+                                    if (pos < COS_CAP) {
+                                        a.cand[(int64_t)q * COS_CAP + pos] = (int32_t)doc;
+                                        a.cand_h[(int64_t)q * COS_CAP + pos] = sc * s_inq[col];
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc ? l_tempty1 : l_tempty0);
+            acc ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                   // no CTA exits (or frees TMEM) while its peer can still touch it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // threshold := k-th best candidate so far; keep the candidates >= threshold, sorted (score desc, id asc)
 constexpr int TC_T = 256;
 __global__ void __launch_bounds__(TC_T) k_tighten_cos(float* __restrict__ thr, int32_t* __restrict__ cand_cnt,
@@ -680,10 +990,21 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     BR_REQUIRE(k >= 1 && k <= 256, BR_ERR_INVALID, "br_cosine_topk: k must be in [1, 256]");
     BR_REQUIRE(((uintptr_t)docs & 15) == 0 && ((uintptr_t)queries & 15) == 0, BR_ERR_INVALID, "br_cosine_topk: 16-byte alignment required");
     if (nq == 0) return BR_OK;
-    static const bool use_mc = getenv("BR_COS_NO_MULTICAST") == nullptr;
+    // kernel choice: "qs" query-stationary CTA pairs (default when the query block fits: d <= 768), "mc" 2-CTA multicast,
+    // "plain" one CTA per tile (BR_COS_KERNEL overrides)
+    static const char* env_kernel = getenv("BR_COS_KERNEL");
+    static const bool use_mc = getenv("BR_COS_NO_MULTICAST") == nullptr && !(env_kernel && !strcmp(env_kernel, "plain"));
+    const bool use_qs = d <= QS_NKB * CG_BK && (!env_kernel || !strcmp(env_kernel, "qs"));
+    static const int qs_bn = getenv("BR_COS_QS_BN") ? atoi(getenv("BR_COS_QS_BN")) : 224;
+    static const int qs_window = getenv("BR_COS_QS_WINDOW") ? atoi(getenv("BR_COS_QS_WINDOW")) : 64;
+    BR_REQUIRE(qs_bn == 128 || qs_bn == 160 || qs_bn == 192 || qs_bn == 224, BR_ERR_INVALID, "BR_COS_QS_BN must be 128, 160, 192 or 224");
     CUtensorMap map_d, map_q;
-    BR_TRY(make_map(&map_d, docs, n_docs, d, use_mc ? 128 : CG_BM));
-    BR_TRY(make_map(&map_q, queries, nq, d, CG_BN));
+    BR_TRY(make_map(&map_d, docs, n_docs, d, (use_mc || use_qs) ? 128 : CG_BM));
+    BR_TRY(make_map(&map_q, queries, nq, d, use_qs ? qs_bn / 2 : CG_BN));
+    BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_qs<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QsCfg<128, 8>::SMEM));
+    BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_qs<192, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QsCfg<192, 5>::SMEM));
+    BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_qs<224, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QsCfg<224, 3>::SMEM));
+    BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_qs<160, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QsCfg<160, 6>::SMEM));
     BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));      // per device
     BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));
     const size_t Q = (size_t)nq;
@@ -703,8 +1024,15 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     while (t0 < n_dt) {
         const int nt = std::min(chunk, n_dt - t0);
         CosArgs a{inv_nd, inv_nq, thr, (int32_t*)b_cnt.p, (int32_t*)b_cand.p, (float*)b_h.p, n_docs, nq, d, t0, t0 + nt,
-                  getenv("BR_COS_DEBUG_NOEPI") ? 1 : 0};
-        if (use_mc) {
+                  getenv("BR_COS_DEBUG_NOEPI") ? 1 : 0, qs_window};
+        if (use_qs) {
+            const int64_t units = (int64_t)nt * ((nq + qs_bn - 1) / qs_bn);
+            const int grid = 2 * (int)std::min<int64_t>(units, kNumSMs / 2);
+            if (qs_bn == 128) k_cosine_gemm_qs<128, 8><<<grid, QS_THREADS, QsCfg<128, 8>::SMEM, st>>>(map_d, map_q, a);
+            else if (qs_bn == 192) k_cosine_gemm_qs<192, 5><<<grid, QS_THREADS, QsCfg<192, 5>::SMEM, st>>>(map_d, map_q, a);
+            else if (qs_bn == 224) k_cosine_gemm_qs<224, 3><<<grid, QS_THREADS, QsCfg<224, 3>::SMEM, st>>>(map_d, map_q, a);
+            else k_cosine_gemm_qs<160, 6><<<grid, QS_THREADS, QsCfg<160, 6>::SMEM, st>>>(map_d, map_q, a);
+        } else if (use_mc) {
             const int grid = 2 * (int)std::min<int64_t>((int64_t)nt * ((n_qt + 1) / 2), kNumSMs / 2);
             k_cosine_gemm_mc<<<grid, CG_THREADS, CG_SMEM, st>>>(map_d, map_q, a);
         } else {
