@@ -508,7 +508,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS, 1) k_cos
 //     64-deep k-block per SM, below what the L2 can deliver at full tensor rate;
 //   * the accumulators are double-buffered in TMEM (2 x 224 of the 512 columns), so the epilogue of tile i (tcgen05.ld,
 //     normalise, threshold filter) runs under the MMAs of tile i+1;
-//   * work units (query block, doc tile) are enumerated query-block-major inside windows of QS_WINDOW doc tiles (~50 MB
+//   * work units (query block, doc tile) are enumerated query-block-major inside windows of 64 doc tiles (~25 MB
 //     of embeddings, L2-resident) and split evenly over the pairs, so a pair reloads its query block only once or
 //     twice per window and every doc tile comes from HBM once per launch.
 // Barriers live in the leader CTA (rank 0) where the single MMA-issuing thread waits; the peer's TMA loads complete
@@ -535,7 +535,9 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {   
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (release at CTA scope), as CUTLASS ClusterBarrier::arrive does: the consumer only needs the TMEM reads,
+    // which tcgen05.wait::ld + tcgen05.fence::before_thread_sync have already ordered; .release.cluster costs a MEMBAR.ALL.GPU
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into MY shared memory whose completion bytes are counted on a barrier of the pair's leader CTA
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int32_t c0, int32_t c1) {
@@ -992,11 +994,11 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     if (nq == 0) return BR_OK;
     // kernel choice: "qs" query-stationary CTA pairs (default when the query block fits: d <= 768), "mc" 2-CTA multicast,
     // "plain" one CTA per tile (BR_COS_KERNEL overrides)
-    static const char* env_kernel = getenv("BR_COS_KERNEL");
-    static const bool use_mc = getenv("BR_COS_NO_MULTICAST") == nullptr && !(env_kernel && !strcmp(env_kernel, "plain"));
+    const char* env_kernel = getenv("BR_COS_KERNEL");
+    const bool use_mc = getenv("BR_COS_NO_MULTICAST") == nullptr && !(env_kernel && !strcmp(env_kernel, "plain"));
     const bool use_qs = d <= QS_NKB * CG_BK && (!env_kernel || !strcmp(env_kernel, "qs"));
-    static const int qs_bn = getenv("BR_COS_QS_BN") ? atoi(getenv("BR_COS_QS_BN")) : 224;
-    static const int qs_window = getenv("BR_COS_QS_WINDOW") ? atoi(getenv("BR_COS_QS_WINDOW")) : 64;
+    const int qs_bn = getenv("BR_COS_QS_BN") ? atoi(getenv("BR_COS_QS_BN")) : 224;
+    const int qs_window = getenv("BR_COS_QS_WINDOW") ? atoi(getenv("BR_COS_QS_WINDOW")) : 64;
     BR_REQUIRE(qs_bn == 128 || qs_bn == 160 || qs_bn == 192 || qs_bn == 224, BR_ERR_INVALID, "BR_COS_QS_BN must be 128, 160, 192 or 224");
     CUtensorMap map_d, map_q;
     BR_TRY(make_map(&map_d, docs, n_docs, d, (use_mc || use_qs) ? 128 : CG_BM));
