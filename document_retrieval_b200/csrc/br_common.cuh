@@ -109,7 +109,7 @@ struct br_index {
     std::vector<double> h_idf;
 
     // query-time scratch
-    br::DevBuf ws_prep, ws_dense, ws_sel, ws_cand, ws_misc, ws_tile;
+    br::DevBuf ws_prep, ws_dense, ws_sel, ws_cand, ws_misc, ws_tile, ws_sort;
     br_query_stats stats{};
 
     bool allow_fused = true;

@@ -30,6 +30,8 @@
 
 #include <algorithm>
 
+#include <cub/cub.cuh>
+
 #include "br_common.cuh"
 #include "br_kernels.cuh"
 #include "br_query.cuh"
@@ -718,6 +720,17 @@ __global__ void k_fused_flags(const int32_t* __restrict__ elig, const int32_t* _
     flags[q] = (!elig[q] || overflow[q] || (!positive_only && out_cnt[q] < need)) ? 1 : 0;
 }
 
+// signature sort on the device: keys ~sig ascending (= signature descending; the radix sort is stable, so equal
+// signatures keep query order exactly like the host stable_sort it replaces), values = query index
+__global__ void k_sig_keys(const uint32_t* __restrict__ sig, int32_t nq, uint32_t* __restrict__ key, int32_t* __restrict__ val) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) { key[i] = ~sig[i]; val[i] = i; }
+}
+__global__ void k_invert_perm(const int32_t* __restrict__ perm, int32_t nq, int32_t* __restrict__ inv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) inv[perm[i]] = i;
+}
+
 __global__ void k_fill_offsets(int64_t* __restrict__ off, int32_t nq, int64_t stride) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q <= nq) off[q] = (int64_t)q * stride;
@@ -793,7 +806,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
                  o_cur = carve(4 * (size_t)(n_buckets + 1)), o_part = carve(4 * (size_t)(n_scan_blocks + 1)),
                  o_poff = carve(8 * (size_t)(n_scan_blocks + 2)),
                  o_cand = carve(4 * (size_t)nq * TILE_CAP), o_ch = carve(4 * (size_t)nq * TILE_CAP),
-                 o_cs = carve(8 * (size_t)nq * TILE_CAP), o_perm = carve(4 * Q), o_inv = carve(4 * Q);
+                 o_cs = carve(8 * (size_t)nq * TILE_CAP), o_perm = carve(4 * Q), o_inv = carve(4 * Q), o_sk = carve(12 * Q);
     BR_TRY(ix->ws_tile.reserve(bytes));
     char* p = ix->ws_tile.as<char>();
     TileEntry* entries = (TileEntry*)(p + o_ent);
@@ -818,16 +831,21 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     int32_t* perm = (int32_t*)(p + o_perm);
     int32_t* inv_perm = (int32_t*)(p + o_inv);
 
-    // group queries that share the most frequent terms: sort by signature (bit 31 = most frequent term)
-    std::vector<uint32_t> h_sig((size_t)nq);
-    BR_CUDA(cudaMemcpyAsync(h_sig.data(), pv.sig, 4 * (size_t)nq, cudaMemcpyDeviceToHost, st));
-    BR_CUDA(cudaStreamSynchronize(st));
-    std::vector<int32_t> h_perm((size_t)nq), h_inv((size_t)nq);
-    for (int32_t q = 0; q < nq; ++q) h_perm[(size_t)q] = q;
-    std::stable_sort(h_perm.begin(), h_perm.end(), [&](int32_t x, int32_t y) { return h_sig[(size_t)x] > h_sig[(size_t)y]; });
-    for (int32_t i = 0; i < nq; ++i) h_inv[(size_t)h_perm[(size_t)i]] = i;
-    BR_CUDA(cudaMemcpyAsync(perm, h_perm.data(), 4 * (size_t)nq, cudaMemcpyHostToDevice, st));
-    BR_CUDA(cudaMemcpyAsync(inv_perm, h_inv.data(), 4 * (size_t)nq, cudaMemcpyHostToDevice, st));
+    // group queries that share the most frequent terms: sort by signature (bit 31 = most frequent term), on the device
+    {
+        uint32_t* key_in = (uint32_t*)(p + o_sk);
+        uint32_t* key_out = key_in + Q;
+        int32_t* val_in = (int32_t*)(key_out + Q);
+        k_sig_keys<<<blocks_for(nq, 256), 256, 0, st>>>(pv.sig, nq, key_in, val_in);
+        BR_CUDA(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        BR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in, key_out, val_in, perm, nq, 0, 32, st));
+        BR_TRY(ix->ws_sort.reserve(tmp_bytes + 16));
+        BR_CUDA(cub::DeviceRadixSort::SortPairs(ix->ws_sort.p, tmp_bytes, key_in, key_out, val_in, perm, nq, 0, 32, st));
+        k_invert_perm<<<blocks_for(nq, 256), 256, 0, st>>>(perm, nq, inv_perm);
+        BR_CUDA(cudaGetLastError());
+        ix->stats.kernel_launches += 2;
+    }
     // one memset covers thr / cand_cnt / prev_cnt / overflow (contiguous carve)
     BR_CUDA(cudaMemsetAsync(p + o_thr, 0, o_off - o_thr, st));
     BR_CUDA(cudaMemsetAsync(cold_total, 0, 16, st));

@@ -40,7 +40,10 @@ def test_cosine_topk_golden(golden):
     assert np.array_equal(ids, g["top_ids"])
 
 
-@pytest.mark.parametrize("n,d,nq,k", [(5000, 768, 300, 10), (777, 128, 5, 3), (130, 64, 257, 10), (20000, 384, 64, 32)])
+@pytest.mark.parametrize("n,d,nq,k", [(5000, 768, 300, 10), (777, 128, 5, 3), (130, 64, 257, 10), (20000, 384, 64, 32),
+                                      (3000, 200, 500, 10),      # d not a multiple of the 64-wide k-block (TMA zero fill)
+                                      (2000, 1024, 300, 10),     # d > 768: the query block does not fit -> multicast kernel
+                                      (40000, 96, 1000, 5)])     # several L2 windows x several query blocks
 def test_cosine_topk_random(n, d, nq, k):
     from document_retrieval_b200.cosine import CosineIndex
     g = torch.Generator().manual_seed(synth.ROOT_SEED + n)
@@ -50,6 +53,23 @@ def test_cosine_topk_random(n, d, nq, k):
     ix = CosineIndex(docs, doc_base=1000)
     ids, sims = ix.topk(qs, k)
     _check(ids.cpu().numpy() - 1000, sims.cpu().numpy(), docs.float().numpy(), qs.float().numpy(), k)
+
+
+@pytest.mark.parametrize("env", [{"BR_COS_KERNEL": "mc"}, {"BR_COS_KERNEL": "plain"}, {"BR_COS_QS_BN": "128"},
+                                 {"BR_COS_QS_BN": "160"}, {"BR_COS_QS_BN": "192"}, {"BR_COS_QS_WINDOW": "3"}])
+def test_cosine_kernel_variants_agree(env, monkeypatch):
+    """Every GEMM variant (query-stationary CTA pairs at each block width, 2-CTA multicast, one CTA per tile) returns
+    the same ids and bit-identical similarities as the default: same K order of accumulation per element."""
+    from document_retrieval_b200.cosine import CosineIndex
+    g = torch.Generator().manual_seed(99)
+    docs = torch.randn(9000, 320, generator=g).to(torch.bfloat16)
+    qs = torch.randn(700, 320, generator=g).to(torch.bfloat16)
+    ix = CosineIndex(docs)
+    ids0, s0 = ix.topk(qs, 10)
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    ids1, s1 = ix.topk(qs, 10)
+    assert torch.equal(ids0, ids1) and torch.equal(s0, s1)
 
 
 def test_cosine_rerank_of_bm25_candidates():
