@@ -177,7 +177,26 @@ def cpu_oracle_run(args, doc_offsets_h, token_ids_h, q_terms, q_off, n_sample, t
     return n_sample / best, build_s, best, out
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything that libraries print on fd 1 (e.g. NCCL's "NCCL version ..." banner) goes to stderr, so that
+    stdout carries exactly the one JSON line of the contract."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(obj) + "\n").encode())
+
+
 def main():
+    _quiet_stdout()
     args = parse()
     import torch
     import torch.distributed as dist
@@ -213,7 +232,7 @@ def main():
         dt = (time.time() - t0) / args.steps
         qps = n_sample / dt
         sample = f"{n_sample} of {args.queries} queries at full N={args.docs} per step, index resident in host RAM"
-        print(json.dumps({
+        _emit(({
             "impl": "reference", "metric": "BM25 top-10 queries/sec", "value": qps, "unit": "queries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -351,7 +370,7 @@ def main():
                                           f"({cpu_s:.1f} s; host index build {cpu_build_s:.1f} s untimed)",
                                 "top10_ids_identical_to_gpu": same}
     if rank == 0:
-        print(json.dumps(line))
+        _emit(line)
     if dist_on:
         dist.destroy_process_group()
     return 0
