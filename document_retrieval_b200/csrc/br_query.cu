@@ -713,7 +713,7 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
     // algorithmic bytes of this batch: 8 B per posting of every distinct in-vocab query term
     std::vector<int64_t> hP((size_t)nq);
     BR_CUDA(cudaMemcpyAsync(hP.data(), pv.P, sizeof(int64_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
-    if (!fused_supported(ix, k)) {
+    if (!fused_supported(ix, k, nq)) {
         BR_TRY(topk_dense(ix, q_off, pv, chunk_start, 0, nq, k, dedup, positive_only, out_ids, out_scores, out_counts, st));
     } else {
         std::vector<int32_t> flags;

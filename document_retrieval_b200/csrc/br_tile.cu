@@ -46,7 +46,9 @@ constexpr int TILE_SHIFT = BR_TILE_SHIFT;   // 512 docs per sub-range (must equa
 constexpr int TILE_S = 1 << TILE_SHIFT;
 constexpr int TILE_DOCS_SHIFT = TILE_SHIFT + 3;   // log2(W * S)
 constexpr int TILE_QT = 20;          // max distinct hot terms of one query on this path (more -> dense path)
-constexpr int TILE_CAP = 1024;       // candidates kept per query between tighten rounds
+constexpr int TILE_CAP = 1024;       // candidates kept per query between tighten rounds (k <= 32)
+constexpr int TILE_CAP_BIG = 8192;   // the same for 32 < k <= 1024: one tile of 4096 docs may pass entirely before the first
+                                     // threshold exists, later chunks add about k candidates each
 constexpr uint32_t TILE_DENSE_MIN = 16;  // postings of a term in a 512-doc sub-range from which the warp works cooperatively
 static_assert((1 << 3) == TILE_W, "TILE_DOCS_SHIFT assumes W == 8");
 
@@ -295,8 +297,9 @@ struct TileArgs {
     int64_t n_pad;
     float* thr;
     int32_t* cand_cnt;
-    int32_t* cand;                // [nq, TILE_CAP]
-    float* cand_h;                // [nq, TILE_CAP]
+    int32_t* cand;                // [nq, cap]
+    float* cand_h;                // [nq, cap]
+    int cap;                      // candidate slots per query (TILE_CAP for k <= 32, TILE_CAP_BIG above)
     int K;
     int tile0;
     int tile_end;                 // tiles [tile0, tile_end) in this launch
@@ -607,7 +610,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
         int tot = c;
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         if (tot == 0) continue;
-        if (tot >= a.K) {
+        if (tot >= a.K && a.K <= 32) {
             // K distinct docs (one per lane) score >= the K-th largest lane maximum: a valid lower
             // bound of the K-th best score of this query over the whole shard
             const float srt = warp_sort_desc(mx, lane);
@@ -633,12 +636,12 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
         if (lane == 0) base = atomicAdd(a.cand_cnt + qi, total);
         base = __shfl_sync(0xffffffffu, base, 0);
         int pos = base + incl - c;
-        int32_t* out = a.cand + (int64_t)qi * TILE_CAP;
-        float* out_h = a.cand_h + (int64_t)qi * TILE_CAP;
+        int32_t* out = a.cand + (int64_t)qi * a.cap;
+        float* out_h = a.cand_h + (int64_t)qi * a.cap;
 #pragma unroll
         for (int j = 0; j < TILE_S / 32; ++j) {
             if (v[j] >= lo_thr && v[j] > 0.f) {
-                if (pos < TILE_CAP) { out[pos] = (int32_t)(doc0 + (j >> 2) * 128 + lane * 4 + (j & 3)); out_h[pos] = v[j]; }
+                if (pos < a.cap) { out[pos] = (int32_t)(doc0 + (j >> 2) * 128 + lane * 4 + (j & 3)); out_h[pos] = v[j]; }
                 ++pos;
             }
         }
@@ -712,6 +715,92 @@ __global__ void __launch_bounds__(TG_T) k_tighten(float* __restrict__ thr, int32
     }
 }
 
+// The same for long candidate lists (32 < K <= 1024, up to TILE_CAP_BIG entries): the K-th largest score by a 4 x 8-bit
+// radix select over the list in shared memory (scores are positive floats, so their bit patterns order like integers)
+// instead of a sort; survivors (score >= new threshold x (1 - band)) are compacted to the head of the query's region in
+// arbitrary order - every survivor is re-scored in float64 and ordered by k_final_select afterwards.
+__global__ void __launch_bounds__(TG_T) k_tighten_big(float* __restrict__ thr, int32_t* __restrict__ cand_cnt,
+                                                      int32_t* __restrict__ prev_cnt, int32_t* __restrict__ cand,
+                                                      float* __restrict__ cand_h, int K, int cap,
+                                                      int32_t* __restrict__ overflow) {
+    extern __shared__ __align__(16) unsigned char tb_smem[];
+    uint32_t* s_h = reinterpret_cast<uint32_t*>(tb_smem);             // [cap] score bits
+    int32_t* s_id = reinterpret_cast<int32_t*>(s_h + cap);            // [cap]
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_prefix, s_need;
+    const int q = blockIdx.x;
+    int n = cand_cnt[q];
+    if (n == prev_cnt[q]) return;                      // nothing emitted since the last round
+    if (n > cap) {
+        if (threadIdx.x == 0) overflow[q] = 1;
+        n = cap;
+    }
+    int32_t* ids = cand + (int64_t)q * cap;
+    float* hs = cand_h + (int64_t)q * cap;
+    for (int i = threadIdx.x; i < n; i += TG_T) {
+        s_h[i] = __float_as_uint(hs[i]);
+        s_id[i] = ids[i];
+    }
+    float th = thr[q];
+    if (n >= K) {
+        if (threadIdx.x == 0) { s_prefix = 0; s_need = (uint32_t)K; }
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            s_hist[threadIdx.x] = 0;                  // TG_T == 256 bins
+            __syncthreads();
+            const uint32_t prefix = s_prefix, need = s_need;
+            const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+            for (int i = threadIdx.x; i < n; i += TG_T) {
+                const uint32_t b = s_h[i];
+                if ((b & himask) == prefix) atomicAdd(&s_hist[(b >> shift) & 0xff], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {                   // walk the bins from the top until `need` elements are covered
+                uint32_t acc = 0;
+                int b = 255;
+                for (; b > 0; --b) {
+                    if (acc + s_hist[b] >= need) break;
+                    acc += s_hist[b];
+                }
+                s_prefix = prefix | ((uint32_t)b << shift);
+                s_need = need - acc;
+            }
+            __syncthreads();
+        }
+        const float kth = __uint_as_float(s_prefix);  // exactly the K-th largest score of the list
+        if (kth > th) th = kth;
+    }
+    __syncthreads();
+    const uint32_t lo = __float_as_uint(th * (1.f - kBandRel));
+    // stable compaction in rounds of TG_T elements
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += TG_T) {
+        const int i = i0 + threadIdx.x;
+        const bool keep = i < n && s_h[i] >= lo;
+        uint32_t total;
+        const uint32_t ex = block_excl_scan(keep ? 1u : 0u, &total);
+        const int base = s_base;
+        if (keep) {
+            ids[base + ex] = s_id[i];
+            hs[base + ex] = __uint_as_float(s_h[i]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = base + (int)total;
+        __syncthreads();
+    }
+    const int kept = s_base;
+    for (int i = kept + threadIdx.x; i < n; i += TG_T) {
+        ids[i] = -1;
+        hs[i] = 0.f;
+    }
+    if (threadIdx.x == 0) {
+        thr[q] = th;
+        cand_cnt[q] = kept;
+        prev_cnt[q] = kept;
+    }
+}
+
 __global__ void k_fused_flags(const int32_t* __restrict__ elig, const int32_t* __restrict__ overflow,
                               const int32_t* __restrict__ out_cnt, int32_t nq, int32_t need, int positive_only,
                               int32_t* __restrict__ flags) {
@@ -743,7 +832,9 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
     // chunks of doubling size: thresholds learnt on the first 2^c tiles filter the next 2^c
     // first chunk: as many tiles as the candidate buffer certainly holds with thresholds still at zero
     // (every sub-range can emit up to ~3k docs before its first tightening)
-    int t0 = 0, chunk = std::max(1, std::min(4, TILE_CAP / (TILE_W * 3 * a0.K)));
+    const bool big = a0.cap > TILE_CAP;
+    if (big) BR_CUDA(cudaFuncSetAttribute(k_tighten_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TILE_CAP_BIG));
+    int t0 = 0, chunk = big ? 1 : std::max(1, std::min(4, TILE_CAP / (TILE_W * 3 * a0.K)));
     while (t0 < n_tiles) {
         const int ny = std::min(std::min(chunk, n_tiles - t0), 32768);
         TileArgs a = a0;
@@ -755,7 +846,8 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
         k_tile_score<G><<<dim3((unsigned)n_groups, (unsigned)((ny + a.tpb - 1) / a.tpb)), TILE_W * 32, smem, st>>>(a);
         BR_CUDA(cudaGetLastError());
         ix->prof_end(st);
-        k_tighten<<<a0.nq, TG_T, 0, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, overflow);
+        if (big) k_tighten_big<<<a0.nq, TG_T, 8 * (size_t)a0.cap, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, a0.cap, overflow);
+        else k_tighten<<<a0.nq, TG_T, 0, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, overflow);
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 2;
         t0 += ny;
@@ -764,9 +856,12 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
     return BR_OK;
 }
 
-bool fused_supported(const br_index* ix, int32_t k) {
+bool fused_supported(const br_index* ix, int32_t k, int32_t nq) {
     static const bool disabled = getenv("BR_DISABLE_FUSED") != nullptr;
-    return !disabled && ix->allow_fused && k <= 32 && ix->variant != BR_OKAPI_NO_PLUS1 && ix->n_hot > 0 &&
+    static const bool no_big = getenv("BR_DISABLE_FUSED_BIGK") != nullptr;
+    // 32 < k <= 1024: candidate regions of TILE_CAP_BIG slots per query (16 B each) - bounded to 6 GB of scratch
+    const bool k_ok = k <= 32 || (!no_big && k <= 1024 && (int64_t)nq * TILE_CAP_BIG * 16 <= (6LL << 30));
+    return !disabled && ix->allow_fused && k_ok && ix->variant != BR_OKAPI_NO_PLUS1 && ix->n_hot > 0 &&
            ix->sub_shift == TILE_SHIFT && ix->skip != nullptr;
 }
 
@@ -793,6 +888,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     if (ix->tile_g) G = ix->tile_g;
     if (G > 4) G = 4;
     const int n_groups = (nq + G - 1) / G, umax = G * TILE_QT;
+    const int cap = k <= 32 ? TILE_CAP : TILE_CAP_BIG;
     const int n_tiles = (ix->n_sub + TILE_W - 1) / TILE_W;
     const int64_t n_buckets = (int64_t)n_tiles * n_groups;
     const int64_t n_scan_blocks = (n_buckets + SCAN_TILE - 1) / SCAN_TILE;
@@ -805,8 +901,8 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
                  o_bc = carve(4 * (size_t)(n_buckets + 1)), o_bo = carve(4 * (size_t)(n_buckets + 1)),
                  o_cur = carve(4 * (size_t)(n_buckets + 1)), o_part = carve(4 * (size_t)(n_scan_blocks + 1)),
                  o_poff = carve(8 * (size_t)(n_scan_blocks + 2)),
-                 o_cand = carve(4 * (size_t)nq * TILE_CAP), o_ch = carve(4 * (size_t)nq * TILE_CAP),
-                 o_cs = carve(8 * (size_t)nq * TILE_CAP), o_perm = carve(4 * Q), o_inv = carve(4 * Q), o_sk = carve(12 * Q);
+                 o_cand = carve(4 * (size_t)nq * cap), o_ch = carve(4 * (size_t)nq * cap),
+                 o_cs = carve(8 * (size_t)nq * cap), o_perm = carve(4 * Q), o_inv = carve(4 * Q), o_sk = carve(12 * Q);
     BR_TRY(ix->ws_tile.reserve(bytes));
     char* p = ix->ws_tile.as<char>();
     TileEntry* entries = (TileEntry*)(p + o_ent);
@@ -852,7 +948,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     k_tile_prep<<<(n_groups + 3) / 4, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, nq, G, umax, entries, n_entries,
                                                     elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)TILE_DENSE_MIN) >> TILE_SHIFT), perm, ix->row_slot);
     BR_CUDA(cudaGetLastError());
-    k_fill_offsets<<<blocks_for(nq + 1, 256), 256, 0, st>>>(cand_off, nq, TILE_CAP);
+    k_fill_offsets<<<blocks_for(nq + 1, 256), 256, 0, st>>>(cand_off, nq, cap);
     BR_CUDA(cudaGetLastError());
     unsigned long long h_cold = 0;
     BR_CUDA(cudaMemcpyAsync(&h_cold, cold_total, sizeof(h_cold), cudaMemcpyDeviceToHost, st));
@@ -887,7 +983,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
 
     stage_mark("cold_sort", st);
     TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
-               cold_off, cold, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, (int)k, 0, 0, 1, dedup ? 0 : 1, perm};
+               cold_off, cold, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, cap, (int)k, 0, 0, 1, dedup ? 0 : 1, perm};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
                                                                             sizeof(uint32_t) * (TILE_W + 1) + sizeof(float4) + sizeof(uint32_t));
     switch (G) {
@@ -897,8 +993,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
         default: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
     }
     stage_mark("tiles", st);
-    const int64_t total = (int64_t)nq * TILE_CAP;
-    BR_TRY(launch_rescore_heads(ix, q_off, pv, dedup, nq, TILE_CAP, cand_cnt, cand, cand_sc, st));
+    BR_TRY(launch_rescore_heads(ix, q_off, pv, dedup, nq, cap, cand_cnt, cand, cand_sc, st));
     BR_TRY(launch_final_select(cand, cand_sc, cand_off, 0, nq, k, positive_only, out_ids, out_scores, cnt_tmp, st, cand_cnt));
     const int32_t need = (int32_t)std::min<int64_t>(k, ix->n_docs);
     k_fused_flags<<<blocks_for(nq, 256), 256, 0, st>>>(elig, overflow, cnt_tmp, nq, need, positive_only, flags);
