@@ -42,6 +42,7 @@ class BM25:
         self._vocab = None             # str -> term id (string API only; lazy when built from texts)
         self._terms = None             # term id -> str
         self.vocabulary = None         # ingest.Vocabulary (GPU hash table) when built with from_texts
+        self.bigrams = False           # from_texts(bigrams=True): query texts get the same 2-gram expansion
         self.vocab_size = 0
         self.corpus_size = 0
         self.avgdl = 0.0
@@ -102,6 +103,7 @@ class BM25:
         self = cls(None, k1, b, variant=variant, dedup_query=dedup_query, device=device)
         voc, doc_off, ids = Vocabulary.from_texts(texts, bigrams=bigrams, device=device)
         self.vocabulary = voc
+        self.bigrams = bool(bigrams)
         self._device = voc.device
         self._build_ids(doc_off, ids, max(len(voc), 1))
         return self
@@ -113,7 +115,7 @@ class BM25:
             from .ingest import Vocabulary
             if self.terms is None:
                 raise BRError("retrieve_top_n_texts needs a model with a string vocabulary")
-            self.vocabulary = Vocabulary.from_terms(self.terms, device=self._device)
+            self.vocabulary = Vocabulary.from_terms(self.terms, bigrams=self.bigrams, device=self._device)
         q_terms, q_off = self.vocabulary.encode_texts(query_texts)
         return self.retrieve_top_n_batch((q_terms, q_off), n, **kw)
 
@@ -425,7 +427,7 @@ class BM25:
                  avgdl=np.float64(stat["avgdl"]), terms=np.asarray(terms if terms is not None else [], dtype=object),
                  has_terms=np.bool_(terms is not None),
                  meta=np.asarray([repr({k: st[k] for k in ("k1", "b", "variant", "dedup_query", "vocab_size",
-                                                           "corpus_size", "doc_base")})], dtype=object))
+                                                           "corpus_size", "doc_base", "bigrams")})], dtype=object))
 
     @classmethod
     def load(cls, path, device=None):
@@ -443,7 +445,7 @@ class BM25:
     def __getstate__(self):
         st = dict(k1=self.k1, b=self.b, variant=self.variant, dedup_query=self.dedup_query, terms=self.terms,
                   vocab_size=self.vocab_size, corpus_size=self.corpus_size, doc_base=self.doc_base, csr=None,
-                  stat=None)
+                  stat=None, bigrams=self.bigrams)
         if self._h is not None:
             st["csr"] = self._export_csr()
             s = self.stats()
@@ -454,6 +456,7 @@ class BM25:
     def __setstate__(self, st):
         self.__init__(None, st["k1"], st["b"], variant=st["variant"], dedup_query=st["dedup_query"])
         self.terms = st["terms"]
+        self.bigrams = bool(st.get("bigrams", False))
         self.vocab_size, self.corpus_size, self.doc_base = st["vocab_size"], st["corpus_size"], st["doc_base"]
         c = st["csr"]
         if c is None:

@@ -739,9 +739,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QS_THREADS, 1) k_cos
             acc_phase[acc] ^= 1;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)col0;
-            if (!a.debug_skip_epilogue) {
-                // common case (nothing passes) is branch-free: m = max_j (acc_j * inv_d - thr_j) over all my columns
-                float m = -CUDART_INF_F;
+            if (a.debug_skip_epilogue != 1) {
+                // common case (nothing passes) is branch-free: per 16-column chunk mc = max_j (acc_j * inv_d - thr_j)
+                float mc[NCH];
                 {
                     uint32_t v[NCH][16];
 #pragma unroll
@@ -750,36 +750,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QS_THREADS, 1) k_cos
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
                         const float4* t4 = reinterpret_cast<const float4*>(s_thr + col0 + c * 16);
+                        float m = -CUDART_INF_F;
+                        if (a.debug_skip_epilogue != 2) {     // 2: measurement aid, TMEM reads without the filter arithmetic
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 th = t4[j4];
-                            m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 0]), inv_d, -th.x));
-                            m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 1]), inv_d, -th.y));
-                            m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 2]), inv_d, -th.z));
-                            m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 3]), inv_d, -th.w));
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 th = t4[j4];
+                                m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 0]), inv_d, -th.x));
+                                m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 1]), inv_d, -th.y));
+                                m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 2]), inv_d, -th.z));
+                                m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 3]), inv_d, -th.w));
+                            }
                         }
+                        mc[c] = doc < a.n_docs ? m : -CUDART_INF_F;
                     }
                 }
-                // rare: some doc row of this warp has a passing column - read the columns again, 16 at a time (the
-                // tcgen05.ld is warp-collective, so the whole warp takes the branch) and emit
-                if (__any_sync(0xffffffffu, m >= 0.f && doc < a.n_docs)) {
-#pragma unroll 1
-                    for (int c = 0; c < NCH; ++c) {
-                        uint32_t e[16];
-                        tc_ld_32x16(taddr + c * 16, e);
-                        tc_wait_ld();
-                        if (m >= 0.f && doc < a.n_docs) {
+                // rare (about k ln 2 docs per query per launch): a chunk in which some doc row of this warp has a passing
+                // column is read again from TMEM (the tcgen05.ld is warp-collective, so the whole warp takes the branch)
+                // and its passing (doc, query) pairs are appended to the queries' candidate lists
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float sc = __uint_as_float(e[j]) * inv_d;
-                                const int col = col0 + c * 16 + j;
-                                if (sc >= s_thr[col]) {
-                                    const int q = un.qb * QS_BN + col;
-                                    const int pos = atomicAdd(a.cand_cnt + q, 1);
-                                    if (pos < COS_CAP) {
-                                        a.cand[(int64_t)q * COS_CAP + pos] = (int32_t)doc;
-                                        a.cand_h[(int64_t)q * COS_CAP + pos] = sc * s_inq[col];
-                                    }
+                for (int c = 0; c < NCH; ++c) {
+                    if (a.debug_skip_epilogue == 3 || !__any_sync(0xffffffffu, mc[c] >= 0.f)) continue;   // 3: measurement aid
+                    uint32_t e[16];
+                    tc_ld_32x16(taddr + c * 16, e);
+                    tc_wait_ld();
+                    if (mc[c] >= 0.f) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float sc = __uint_as_float(e[j]) * inv_d;
+                            const int col = col0 + c * 16 + j;
+                            if (sc >= s_thr[col]) {
+                                const int q = un.qb * QS_BN + col;
+                                const int pos = atomicAdd(a.cand_cnt + q, 1);
+                                if (pos < COS_CAP) {
+                                    a.cand[(int64_t)q * COS_CAP + pos] = (int32_t)doc;
+                                    a.cand_h[(int64_t)q * COS_CAP + pos] = sc * s_inq[col];
                                 }
                             }
                         }
@@ -1037,11 +1041,16 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     BR_CUDA(cudaMemsetAsync(b_prev.p, 0, 4 * Q, st));
     BR_CUDA(cudaMemsetAsync(b_ovf.p, 0, 4 * Q, st));
     const int n_dt = (int)((n_docs + CG_BM - 1) / CG_BM), n_qt = (nq + CG_BN - 1) / CG_BN;
-    int t0 = 0, chunk = 1;
+    // doc chunks of growing size: thresholds learnt on the docs so far filter the next chunk.  A launch emits about
+    // k (growth - 1) candidates per query whatever its size; measured on the config-5 shard an emission costs ~1.7 ns of
+    // wall time, which makes doubling (13 launches, ~120 emissions per query) faster than 3x / 4x / 8x growth
+    const int chunk0 = getenv("BR_COS_CHUNK0") ? std::max(1, atoi(getenv("BR_COS_CHUNK0"))) : 1;
+    const int growth = getenv("BR_COS_CHUNK_MULT") ? std::max(2, atoi(getenv("BR_COS_CHUNK_MULT"))) : 2;
+    int t0 = 0, chunk = chunk0;
     while (t0 < n_dt) {
         const int nt = std::min(chunk, n_dt - t0);
         CosArgs a{inv_nd, inv_nq, thr, (int32_t*)b_cnt.p, (int32_t*)b_cand.p, (float*)b_h.p, n_docs, nq, d, t0, t0 + nt,
-                  getenv("BR_COS_DEBUG_NOEPI") ? 1 : 0, qs_window};
+                  getenv("BR_COS_DEBUG_NOEPI") ? atoi(getenv("BR_COS_DEBUG_NOEPI")) : 0, qs_window};
         if (use_qs) {
             const int64_t units = (int64_t)nt * ((nq + qs_bn - 1) / qs_bn);
             const int grid = 2 * (int)std::min<int64_t>(units, kNumSMs / 2);
@@ -1061,7 +1070,7 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
                                            (int32_t*)b_ovf.p);
         BR_CUDA(cudaGetLastError());
         t0 += nt;
-        chunk *= 2;
+        chunk *= growth;
     }
     k_cos_output<<<blocks_for((int64_t)nq * k, 256), 256, 0, st>>>((int32_t*)b_cand.p, (float*)b_h.p, (int32_t*)b_cnt.p, nq, k,
                                                                     doc_base, out_ids, out_sims);

@@ -54,11 +54,20 @@ def _batched_top(bm25_models, rows, k, preprocess, batch_size):
         model = bm25_models[lang]
         for s in range(0, len(idxs), batch_size):
             chunk = idxs[s:s + batch_size]
-            toks = [preprocess(rows[i]["query"], lang) for i in chunk]
             kk = min(k, model.corpus_size)
             if kk < 1:
                 continue
-            ids, _ = model.retrieve_top_n_batch(toks, kk)
+            qs = [rows[i]["query"] for i in chunk]
+            if preprocess is _default_preprocess and all(isinstance(q, str) for q in qs) and \
+                    getattr(model, "terms", None) is not None and hasattr(model, "retrieve_top_n_texts"):
+                # already-preprocessed query strings: `preprocessed_query.split()` (bm25_ranking.ipynb:341-347) and the
+                # vocabulary lookup run on the GPU for the whole chunk
+                try:
+                    ids, _ = model.retrieve_top_n_texts(qs, kk)
+                except RuntimeError:                 # e.g. a vocabulary whose str() forms are not distinct
+                    ids, _ = model.retrieve_top_n_batch([preprocess(q, lang) for q in qs], kk)
+            else:
+                ids, _ = model.retrieve_top_n_batch([preprocess(q, lang) for q in qs], kk)
             ids = ids.cpu().numpy()
             for j, i in enumerate(chunk):
                 out[i] = ids[j][ids[j] >= 0]

@@ -156,3 +156,29 @@ def test_large_corpus_matches_factorize():
     assert np.array_equal(d_off.cpu().numpy(), off)
     assert np.array_equal(d_ids.cpu().numpy(), codes.astype(np.int32))
     assert voc.terms == list(uniq)
+
+
+def test_eval_loop_takes_query_strings_through_the_gpu_tokeniser():
+    """evaluate_recall_at_k / retrieve_test_queries with preprocessed query *strings* (bm25_ranking.ipynb:341-347) give the
+    same answers as with token lists; a pickled bigram model still expands query texts."""
+    rng = np.random.default_rng(9)
+    words = [f"k{i}" for i in range(200)]
+    models, id_maps, rows_s, rows_t = dr.LanguageModels(), {}, [], []
+    for lang, n in (("en", 600), ("fr", 300)):
+        texts = [" ".join(rng.choice(words, size=int(rng.integers(4, 30)))) for _ in range(n)]
+        models[lang] = dr.BM25.from_texts(texts) if lang == "en" else dr.BM25([t.split() for t in texts])
+        id_maps[lang] = [f"{lang}-{i}" for i in range(n)]
+        for j in rng.integers(0, n, size=40):
+            q = " ".join(texts[j].split()[:6])
+            rows_s.append({"query": "  " + q + "\t", "lang": lang, "positive_docs": f"{lang}-{j}"})
+            rows_t.append({"query": q.split(), "lang": lang, "positive_docs": f"{lang}-{j}"})
+    rows_s.append({"query": "k1 k2", "lang": "xx", "positive_docs": "none"})
+    rows_t.append({"query": ["k1", "k2"], "lang": "xx", "positive_docs": "none"})
+    assert dr.evaluate_recall_at_k(models, id_maps, rows_s, 10) == dr.evaluate_recall_at_k(models, id_maps, rows_t, 10)
+    assert dr.retrieve_test_queries(models, id_maps, rows_s, 10) == dr.retrieve_test_queries(models, id_maps, rows_t, 10)
+    texts = [" ".join(rng.choice(words[:30], size=int(rng.integers(2, 12)))) for _ in range(300)]
+    b = dr.BM25.from_texts(texts, bigrams=True)
+    b2 = pickle.loads(pickle.dumps(b))
+    ids1, sc1 = b.retrieve_top_n_texts(texts[:50], 10)
+    ids2, sc2 = b2.retrieve_top_n_texts(texts[:50], 10)
+    assert b2.bigrams and np.array_equal(ids1.cpu().numpy(), ids2.cpu().numpy()) and np.array_equal(sc1.cpu().numpy(), sc2.cpu().numpy())
