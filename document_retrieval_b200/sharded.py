@@ -102,10 +102,11 @@ class ShardedCosineIndex:
     all-gathered and merged - bit-identical to the single-GPU result because top-k over a row
     partition is exactly decomposable and ties break on the global row id."""
 
-    def __init__(self, local_embeddings, row_base, device=None, group=None, merge=merge_topk_cuda):
-        from .cosine import CosineIndex
-        self.local = CosineIndex(local_embeddings, device=device, doc_base=row_base)
-        self.group, self.merge = group, merge
+    def __init__(self, local_embeddings, row_base, device=None, group=None, merge=merge_topk_cuda, local=None):
+        if local is None:
+            from .cosine import CosineIndex
+            local = CosineIndex(local_embeddings, device=device, doc_base=row_base)
+        self.local, self.group, self.merge = local, group, merge
 
     def topk(self, query_embeddings, k=10):
         """-> (global rows int64[Q, k], cosine float64[Q, k] (fp32 values widened)) on every rank."""

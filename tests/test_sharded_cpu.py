@@ -91,6 +91,52 @@ def test_two_rank_sharded_equals_single_index():
         assert np.array_equal(ids0[i], a) and np.array_equal(sc0[i], b)     # bit-identical to one index
 
 
+class _OracleCosShard:
+    """Stand-in for CosineIndex on one row shard (oracle-backed, CPU)."""
+
+    def __init__(self, rows, base):
+        self.rows, self.base = rows, base
+
+    def topk(self, q, k):
+        ids, sims = orc.cosine_topk(self.rows, np.asarray(q, np.float32), k)
+        return torch.from_numpy(ids + self.base), torch.from_numpy(sims)
+
+
+def _cos_worker(rank, world, port, ret):
+    from document_retrieval_b200.sharded import ShardedCosineIndex
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(4)
+        docs = rng.standard_normal((3001, 32)).astype(np.float32)
+        docs[2500] = docs[17]                         # exact tie across the two shards
+        qs = np.concatenate([rng.standard_normal((40, 32)).astype(np.float32), docs[17:18]])
+        lo, hi = shard_bounds(docs.shape[0], world)[rank]
+        sh = ShardedCosineIndex(None, lo, local=_OracleCosShard(docs[lo:hi], lo), merge=_merge_cpu)
+        ids, sims = sh.topk(qs, 10)
+        ret[rank] = (ids.numpy(), sims.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_cosine_equals_single_index():
+    """Row-sharded cosine top-k (config 5 layout): global row ids, all-gather, merge by (cosine desc, row asc)."""
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_cos_worker, args=(world, port, ret), nprocs=world, join=True)
+    rng = np.random.default_rng(4)
+    docs = rng.standard_normal((3001, 32)).astype(np.float32)
+    docs[2500] = docs[17]
+    qs = np.concatenate([rng.standard_normal((40, 32)).astype(np.float32), docs[17:18]])
+    ids, sims = orc.cosine_topk(docs, qs, 10)
+    assert np.array_equal(ret[0][0], ret[1][0]) and np.array_equal(ret[0][1], ret[1][1])
+    assert np.array_equal(ret[0][0], ids) and np.array_equal(ret[0][1], sims.astype(np.float64))
+    assert ret[0][0][-1, :2].tolist() == [17, 2500]
+
+
 def test_abi_symbols_exported():
     """The C-ABI library loads and exports every symbol include/br_b200.h declares (no compute)."""
     import re
