@@ -174,6 +174,7 @@ struct CosArgs {
     int32_t tile_begin, tile_end;   // doc tiles [tile_begin, tile_end) of CG_BM rows
     int32_t debug_skip_epilogue;    // measurement aid (BR_COS_DEBUG_NOEPI): epilogue warps only hand the accumulators back
     int32_t window;                 // query-stationary kernel: doc tiles per L2 window
+    int32_t* dbg_dummy;             // [nq] measurement aid (BR_COS_DEBUG_NOEPI=6: one extra atomic round trip per emission)
 };
 
 __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_constant__ CUtensorMap map_docs,
@@ -780,7 +781,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QS_THREADS, 1) k_cos
                             const int col = col0 + c * 16 + j;
                             if (sc >= s_thr[col]) {
                                 const int q = un.qb * QS_BN + col;
-                                const int pos = atomicAdd(a.cand_cnt + q, 1);
+                                int pos = atomicAdd(a.cand_cnt + q, 1);
+                                if (a.debug_skip_epilogue == 6) pos += atomicAdd(a.dbg_dummy + q, 1) & 0;
                                 if (pos < COS_CAP) {
                                     a.cand[(int64_t)q * COS_CAP + pos] = (int32_t)doc;
                                     a.cand_h[(int64_t)q * COS_CAP + pos] = sc * s_inq[col];
@@ -1029,9 +1031,9 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));      // per device
     BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));
     const size_t Q = (size_t)nq;
-    AsyncBuf b_inq(st), b_thr(st), b_cnt(st), b_prev(st), b_ovf(st), b_cand(st), b_h(st);
+    AsyncBuf b_inq(st), b_thr(st), b_cnt(st), b_prev(st), b_ovf(st), b_cand(st), b_h(st), b_dbg(st);
     BR_TRY(b_inq.alloc(4 * Q)); BR_TRY(b_thr.alloc(4 * Q)); BR_TRY(b_cnt.alloc(4 * Q)); BR_TRY(b_prev.alloc(4 * Q));
-    BR_TRY(b_ovf.alloc(4 * Q)); BR_TRY(b_cand.alloc(4 * Q * COS_CAP)); BR_TRY(b_h.alloc(4 * Q * COS_CAP));
+    BR_TRY(b_ovf.alloc(4 * Q)); BR_TRY(b_cand.alloc(4 * Q * COS_CAP)); BR_TRY(b_h.alloc(4 * Q * COS_CAP)); BR_TRY(b_dbg.alloc(4 * Q));
     float* inv_nq = (float*)b_inq.p;
     float* thr = (float*)b_thr.p;
     BR_TRY(row_inv_norms(queries, nq, d, inv_nq, st));
@@ -1050,7 +1052,7 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     while (t0 < n_dt) {
         const int nt = std::min(chunk, n_dt - t0);
         CosArgs a{inv_nd, inv_nq, thr, (int32_t*)b_cnt.p, (int32_t*)b_cand.p, (float*)b_h.p, n_docs, nq, d, t0, t0 + nt,
-                  getenv("BR_COS_DEBUG_NOEPI") ? atoi(getenv("BR_COS_DEBUG_NOEPI")) : 0, qs_window};
+                  getenv("BR_COS_DEBUG_NOEPI") ? atoi(getenv("BR_COS_DEBUG_NOEPI")) : 0, qs_window, (int32_t*)b_dbg.p};
         if (use_qs) {
             const int64_t units = (int64_t)nt * ((nq + qs_bn - 1) / qs_bn);
             const int grid = 2 * (int)std::min<int64_t>(units, kNumSMs / 2);
