@@ -321,3 +321,20 @@ def test_long_and_duplicate_heavy_queries():
         ids, sc = m.retrieve_top_n_batch((q_terms, q_off), 10)
         assert np.array_equal(ids.cpu().numpy(), oi) and np.array_equal(sc.cpu().numpy(), os_)
         assert m.query_stats()["queries_dense"] == len(qs)
+
+
+@pytest.mark.parametrize("k", [33, 100, 257, 1024])
+def test_large_k_fused_path_equals_dense_path(k):
+    """32 < k <= 1024 runs through the tiled path too (radix-select tighten over 8192-slot candidate regions) and must
+    return exactly what the dense radix-select path returns - ids, float64 scores and counts."""
+    c = synth.make_config("C1")
+    from document_retrieval_b200 import BM25
+    q = (c["q_terms"], c["q_offsets"])
+    for kw, call in (({}, {}), ({"variant": "okapi", "dedup_query": False}, {"positive_only": True})):
+        m = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"], **kw)
+        a = m.retrieve_top_n_batch(q, k, return_counts=True, **call)
+        assert m.query_stats()["queries_fused"] > 0.8 * (c["q_offsets"].size - 1)
+        m.set_option("fused", 0)
+        b = m.retrieve_top_n_batch(q, k, return_counts=True, **call)
+        assert m.query_stats()["queries_fused"] == 0
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
