@@ -42,6 +42,22 @@ class LanguageModels(dict):
         return self
 
 
+def build_language_models(preprocessed_corpus, document_langs, document_ids, k1=1.5, b=0.75, **kw):
+    """The per-language build loop of bm25_ranking.ipynb:276-316 in one call: group the preprocessed texts by language,
+    tokenise each group with ``text.split()`` (:299) and build its ``BM25`` (:306) - here through ``BM25.from_texts``, i.e.
+    tokenisation, vocabulary and index build on the GPU.  -> ``LanguageModels`` (``bm25_models`` with ``doc_id_maps``
+    attached, local doc index -> ``docid`` in corpus order like :288)."""
+    from .bm25 import BM25
+    lang_to_idx = defaultdict(list)
+    for idx, lang in enumerate(document_langs):              # :276-280
+        lang_to_idx[lang].append(idx)
+    models = LanguageModels()
+    for lang, idxs in lang_to_idx.items():
+        texts = [preprocessed_corpus[i] for i in idxs]
+        models.add(lang, BM25.from_texts(texts, k1, b, **kw), [document_ids[i] for i in idxs])
+    return models
+
+
 def _batched_top(bm25_models, rows, k, preprocess, batch_size):
     """-> list (aligned with rows) of np.ndarray local ids, or None when the language is unknown."""
     by_lang = defaultdict(list)

@@ -182,3 +182,28 @@ def test_eval_loop_takes_query_strings_through_the_gpu_tokeniser():
     ids1, sc1 = b.retrieve_top_n_texts(texts[:50], 10)
     ids2, sc2 = b2.retrieve_top_n_texts(texts[:50], 10)
     assert b2.bigrams and np.array_equal(ids1.cpu().numpy(), ids2.cpu().numpy()) and np.array_equal(sc1.cpu().numpy(), sc2.cpu().numpy())
+
+
+def test_build_language_models_equals_the_notebook_loop():
+    """bm25_ranking.ipynb:276-316 (group by language, text.split(), BM25 per language) through one call."""
+    rng = np.random.default_rng(12)
+    langs_all = ["en", "fr", "ko"]
+    corpus, langs, docids = [], [], []
+    for i in range(900):
+        lang = langs_all[int(rng.integers(0, 3))]
+        corpus.append(" ".join(f"{lang}{int(t)}" for t in rng.zipf(1.3, size=int(rng.integers(3, 40))) if t < 500))
+        langs.append(lang)
+        docids.append(f"doc-{i}")
+    models = dr.build_language_models(corpus, langs, docids)
+    for lang in langs_all:
+        idx = [i for i, x in enumerate(langs) if x == lang]
+        ref = dr.BM25([corpus[i].split() for i in idx])
+        assert models.doc_id_maps[lang] == [docids[i] for i in idx]
+        assert models[lang].df == ref.df and models[lang].avgdl == ref.avgdl
+        qs = [corpus[i].split()[:5] for i in idx[:30] if corpus[i].split()]
+        a, sa = models[lang].retrieve_top_n_batch(qs, 10)
+        b_, sb = ref.retrieve_top_n_batch(qs, 10)
+        assert np.array_equal(a.cpu().numpy(), b_.cpu().numpy()) and np.array_equal(sa.cpu().numpy(), sb.cpu().numpy())
+    rows = [{"query": " ".join(corpus[i].split()[:6]), "lang": langs[i], "positive_docs": docids[i]} for i in range(0, 900, 9)]
+    r = dr.evaluate_recall_at_k(models, models.doc_id_maps, rows, 10)
+    assert 0.5 < r <= 1.0
