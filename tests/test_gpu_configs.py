@@ -89,6 +89,15 @@ def test_c4_slice_properties():
     ids_d, sc_d = m.retrieve_top_n_batch(q, 10)
     m.set_option("fused", 1)
     assert torch.equal(ids_f, ids_d) and torch.equal(sc_f, sc_d)
+    # the large-k tiled path (radix-select tighten) at this scale: top-100 and top-1000 of 300 queries
+    q300 = (qt[:int(qo[300])], qo[:301])
+    for kk in (100, 1000):
+        a = m.retrieve_top_n_batch(q300, kk)
+        assert m.query_stats()["queries_fused"] > 280
+        m.set_option("fused", 0)
+        b = m.retrieve_top_n_batch(q300, kk)
+        m.set_option("fused", 1)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     shards = []
     for lo, hi in shard_bounds(1_000_000, 4):
         o = do[lo:hi + 1] - do[lo]
