@@ -59,6 +59,23 @@ struct DevBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Stream-ordered scratch comes from the device's default memory pool.  With the default release threshold (0) every
+// stream synchronisation hands freed memory back to the driver and the next call pays for mapping it again (tens of
+// ms for the larger buffers): keep it in the pool.  Idempotent, per device.
+inline int retain_default_pool() {
+    static bool ready[64] = {};
+    int dev = 0;
+    BR_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !ready[dev]) {
+        cudaMemPool_t pool;
+        BR_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;
+        BR_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        ready[dev] = true;
+    }
+    return BR_OK;
+}
+
 constexpr int kNumSMs = 148;          // B200
 constexpr float kBandRel = 1e-5f;     // fp32 candidate band kept below the k-th fp32 score
 

@@ -979,18 +979,7 @@ struct AsyncBuf {   // stream-ordered scratch
     cudaStream_t st;
     explicit AsyncBuf(cudaStream_t s) : st(s) {}
     int alloc(size_t bytes) {
-        // keep freed scratch in the device's default pool: with the default release threshold (0) every stream
-        // synchronisation hands the memory back to the driver and the next call pays for mapping it again (tens of ms)
-        static bool pool_ready[64] = {};
-        int dev = 0;
-        BR_CUDA(cudaGetDevice(&dev));
-        if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
-            cudaMemPool_t pool;
-            BR_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-            uint64_t keep = UINT64_MAX;
-            BR_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-            pool_ready[dev] = true;
-        }
+        BR_TRY(retain_default_pool());
         BR_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, st));
         return BR_OK;
     }

@@ -320,13 +320,16 @@ __global__ void __launch_bounds__(256) k_lookup(const uint8_t* __restrict__ text
     token_ids[i] = term;
 }
 
-struct Tmp {
+struct Tmp {   // stream-ordered temporaries, released when the call returns
+    cudaStream_t st;
     std::vector<void*> ptrs;
-    ~Tmp() { for (void* p : ptrs) if (p) cudaFree(p); }
+    explicit Tmp(cudaStream_t s) : st(s) {}
+    ~Tmp() { for (void* p : ptrs) if (p) cudaFreeAsync(p, st); }
     template <class T>
     int alloc(T** out, size_t n) {
+        BR_TRY(retain_default_pool());
         void* p = nullptr;
-        BR_CUDA(cudaMalloc(&p, sizeof(T) * (n > 0 ? n : 1)));
+        BR_CUDA(cudaMallocAsync(&p, sizeof(T) * (n > 0 ? n : 1), st));
         ptrs.push_back(p);
         *out = reinterpret_cast<T*>(p);
         return BR_OK;
@@ -389,7 +392,7 @@ int br_tokenize_count(const uint8_t* text_dev, const int64_t* doc_byte_off_dev, 
     cudaStream_t st = (cudaStream_t)stream;
     BR_REQUIRE(doc_byte_off_dev && doc_tok_off_dev && n_tokens_host && n_docs >= 0, BR_ERR_INVALID,
                "br_tokenize_count: null pointer / negative n_docs");
-    Tmp tmp;
+    Tmp tmp(st);
     uint32_t* counts = nullptr;
     int* d_bad = nullptr;
     BR_TRY(tmp.alloc(&counts, (size_t)n_docs));
@@ -421,7 +424,7 @@ int br_vocab_build(const uint8_t* text_dev, const int64_t* doc_byte_off_dev, int
     br_vocab* v = new br_vocab();
     struct Guard { br_vocab* p; ~Guard() { if (p) vocab_free(p); } } guard{v};
     BR_CUDA(cudaGetDevice(&v->device));
-    Tmp tmp;
+    Tmp tmp(st);
     const int64_t T = n_tokens;
 
     int64_t* tok_start = nullptr;
@@ -506,7 +509,7 @@ int br_vocab_lookup(const br_vocab* v, const uint8_t* text_dev, const int64_t* d
     BR_REQUIRE(n_tokens >= 0 && n_tokens < (1LL << 31), BR_ERR_UNSUPPORTED, "br_vocab_lookup: 2^31 or more tokens");
     if (n_tokens == 0) return BR_OK;
     BR_REQUIRE(token_ids_dev, BR_ERR_INVALID, "br_vocab_lookup: null token_ids");
-    Tmp tmp;
+    Tmp tmp(st);
     int64_t* tok_start = nullptr;
     uint32_t* tok_len = nullptr;
     BR_TRY(emit_tokens(tmp, text_dev, doc_byte_off_dev, n_docs, bigrams, doc_tok_off_dev, n_tokens, st, &tok_start, &tok_len));
@@ -552,7 +555,7 @@ int br_vocab_import(const int64_t* pool_off_host, const uint8_t* pool_host, int6
     BR_CUDA(cudaMemcpyAsync(v->pool_off, pool_off_host, sizeof(int64_t) * (size_t)(V + 1), cudaMemcpyHostToDevice, st));
     if (v->pool_bytes > 0)
         BR_CUDA(cudaMemcpyAsync(v->pool, pool_host, (size_t)v->pool_bytes, cudaMemcpyHostToDevice, st));
-    Tmp tmp;
+    Tmp tmp(st);
     if (V > 0) {
         uint64_t* hash = nullptr;
         uint32_t* term = nullptr;
