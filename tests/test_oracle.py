@@ -128,3 +128,49 @@ def test_live_reference_matches_oracle():
         s2 = orc.get_scores(ix, c["q_terms"][c["q_offsets"][i]:c["q_offsets"][i + 1]])
         np.testing.assert_allclose(s2, s, rtol=1e-13, atol=0)
         assert set(m.retrieve_top_n(q, 10).tolist()) == set(orc.topk_canonical(s, 10)[0].tolist())
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present")
+def test_live_reference_property_pin_on_tiny_corpora():
+    """Property pin of the oracle against the UNMODIFIED notebook class on random tiny corpora: out-of-vocabulary and
+    duplicate query terms, one-token docs, identical docs (exact ties), k >= N.  Scores within 1e-13 (the reference sums
+    in set() order), top-n id sets equal wherever no tie straddles rank n, full ranking for n >= N."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    BM25 = ref_loader.notebook_bm25_class()
+
+    @st.composite
+    def case(draw):
+        vocab = draw(st.integers(1, 10))
+        n_docs = draw(st.integers(1, 25))
+        docs = draw(st.lists(st.lists(st.integers(0, vocab - 1), min_size=1, max_size=7), min_size=n_docs, max_size=n_docs))
+        if draw(st.booleans()) and n_docs > 2:
+            docs[-1] = list(docs[0])
+        queries = draw(st.lists(st.lists(st.integers(0, vocab + 1), min_size=0, max_size=8), min_size=1, max_size=4))
+        return vocab, docs, queries, draw(st.integers(1, n_docs + 2))
+
+    @settings(max_examples=120, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(case())
+    def run(c):
+        vocab, docs, queries, n = c
+        off = np.zeros(len(docs) + 1, np.int64)
+        np.cumsum([len(d) for d in docs], out=off[1:])
+        tok = np.asarray([t for d in docs for t in d], np.int32)
+        ix = orc.build_index(off, tok, vocab)
+        m = BM25([[f"t{t}" for t in d] for d in docs])
+        assert m.avgdl == ix.avgdl and m.corpus_size == ix.n_docs
+        for q in queries:
+            s_ref = m.get_scores([f"t{t}" for t in q])
+            s = orc.get_scores(ix, q)
+            np.testing.assert_allclose(s, s_ref, rtol=1e-13, atol=0)
+            ids, _ = orc.topk_canonical(s_ref, n)
+            got = m.retrieve_top_n([f"t{t}" for t in q], n)
+            if n >= len(docs):
+                assert sorted(got.tolist()) == list(range(len(docs)))            # full ranking, :208-209
+                assert np.all(np.diff(s_ref[got]) <= 0)
+            else:
+                kth = np.sort(s_ref)[::-1][n - 1]
+                if (s_ref == kth).sum() == 1 or (s_ref >= kth).sum() == n:       # no tie straddles rank n
+                    assert set(got.tolist()) == set(ids.tolist())
+                assert np.all(s_ref[got] >= kth)
+
+    run()
