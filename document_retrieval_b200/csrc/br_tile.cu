@@ -308,8 +308,11 @@ struct TileArgs {
     const int32_t* perm;          // group g, slot i -> query perm[g*G+i] (queries sorted by frequent-term signature)
 };
 
+#ifndef BR_TILE_MINB
+#define BR_TILE_MINB 3            // resident CTAs per SM the register allocation is sized for (64 KB of accumulators each)
+#endif
 template <int G>
-__global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
+__global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* acc = reinterpret_cast<float*>(smem_raw);                                     // [G][W][S]
     TileEntry* ent = reinterpret_cast<TileEntry*>(smem_raw + sizeof(float) * G * TILE_W * TILE_S);
