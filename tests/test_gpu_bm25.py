@@ -338,3 +338,27 @@ def test_large_k_fused_path_equals_dense_path(k):
         b = m.retrieve_top_n_batch(q, k, return_counts=True, **call)
         assert m.query_stats()["queries_fused"] == 0
         assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("k", [10, 100, 1000])
+def test_massive_ties_fall_back_exactly(k):
+    """20k identical docs: every score ties, the candidate band holds the whole corpus, the tiled path overflows its
+    candidate regions and must hand the query to the dense path - the answer is the first k doc ids."""
+    from document_retrieval_b200 import BM25
+    n = 20_000
+    off = np.arange(n + 1, dtype=np.int64) * 3
+    tok = np.tile(np.asarray([0, 1, 2], np.int32), n)
+    m = BM25.from_token_ids(off, tok, 4)
+    q = (np.asarray([0, 2, 0, 3, 1], np.int32), np.asarray([0, 2, 4, 5], np.int32))     # [0,2], [0,3(df=0)], [1]
+    ids, sc = m.retrieve_top_n_batch(q, k)
+    ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(ids[i], np.arange(k)), (i, ids[i][:12])
+        assert np.all(sc[i] == sc[i][0]) and sc[i][0] > 0
+    # a second corpus where only every 7th doc matches: ties among the matching docs, zeros after them
+    tok2 = tok.copy().reshape(n, 3)
+    tok2[np.arange(n) % 7 != 0] = [1, 1, 2]
+    m2 = BM25.from_token_ids(off, tok2.reshape(-1), 4)
+    ids2, sc2 = m2.retrieve_top_n_batch((np.asarray([0], np.int32), np.asarray([0, 1], np.int32)), k)
+    want = np.arange(0, n, 7)[:k]
+    assert np.array_equal(ids2.cpu().numpy()[0][:want.size], want)
