@@ -994,6 +994,25 @@ int row_inv_norms(const void* emb, int64_t n, int32_t d, float* out, cudaStream_
     return BR_OK;
 }
 
+int cosine_rerank(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d, const void* queries, int32_t nq,
+                  const int32_t* cand, int32_t c, int32_t k, int32_t* out_ids, float* out_sims, cudaStream_t st);
+
+__global__ void k_iota_rows(int32_t* __restrict__ out, int32_t rows, int64_t n) {
+    const int64_t total = (int64_t)rows * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int32_t)(i % n);
+}
+__global__ void k_cos_patch(const int32_t* __restrict__ rows, int32_t nr, int32_t k, const int32_t* __restrict__ ids,
+                            const float* __restrict__ sims, int64_t doc_base, int64_t* __restrict__ out_ids,
+                            float* __restrict__ out_sims) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nr * k) return;
+    const int r = i / k, j = i - r * k;
+    const int64_t o = (int64_t)rows[r] * k + j;
+    out_ids[o] = ids[i] >= 0 ? (int64_t)ids[i] + doc_base : -1;
+    out_sims[o] = sims[i];
+}
+
 int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d, const void* queries, int32_t nq,
                 int32_t k, int64_t doc_base, int64_t* out_ids, float* out_sims, cudaStream_t st) {
     BR_REQUIRE(docs && inv_nd && queries && out_ids && out_sims, BR_ERR_INVALID, "br_cosine_topk: null pointer");
@@ -1069,8 +1088,31 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     std::vector<int32_t> ovf(Q);
     BR_CUDA(cudaMemcpyAsync(ovf.data(), b_ovf.p, 4 * Q, cudaMemcpyDeviceToHost, st));
     BR_CUDA(cudaStreamSynchronize(st));
-    for (int32_t v : ovf)
-        BR_REQUIRE(!v, BR_ERR_UNSUPPORTED, "br_cosine_topk: more than 1024 near-tied candidates for one query");
+    // A query with more than COS_CAP candidates at or above its threshold in one launch (masses of duplicate / exactly tied
+    // embeddings) cannot be served by the filter: those few queries are answered exactly by scoring every doc row with the
+    // gather kernel (same normalisation, ties by doc id) - slow (one pass over the embeddings per query) but exact.
+    std::vector<int32_t> redo;
+    for (int32_t q = 0; q < nq; ++q) if (ovf[(size_t)q]) redo.push_back(q);
+    if (!redo.empty()) {
+        BR_REQUIRE(redo.size() <= 64 && d <= 1024, BR_ERR_UNSUPPORTED,
+                   "br_cosine_topk: more than 1024 near-tied candidates for more than 64 queries (or d > 1024)");
+        const int32_t nr = (int32_t)redo.size();
+        AsyncBuf b_q(st), b_c(st), b_oi(st), b_os(st), b_rows(st);
+        BR_TRY(b_q.alloc((size_t)nr * d * 2)); BR_TRY(b_c.alloc(4 * (size_t)nr * (size_t)n_docs));
+        BR_TRY(b_oi.alloc(4 * (size_t)nr * k)); BR_TRY(b_os.alloc(4 * (size_t)nr * k)); BR_TRY(b_rows.alloc(4 * (size_t)nr));
+        for (int32_t i = 0; i < nr; ++i)
+            BR_CUDA(cudaMemcpyAsync((char*)b_q.p + (size_t)i * d * 2, (const char*)queries + (size_t)redo[(size_t)i] * d * 2,
+                                    (size_t)d * 2, cudaMemcpyDeviceToDevice, st));
+        BR_CUDA(cudaMemcpyAsync(b_rows.p, redo.data(), 4 * (size_t)nr, cudaMemcpyHostToDevice, st));
+        k_iota_rows<<<kNumSMs * 8, 256, 0, st>>>((int32_t*)b_c.p, nr, n_docs);
+        BR_CUDA(cudaGetLastError());
+        BR_TRY(cosine_rerank(docs, inv_nd, n_docs, d, b_q.p, nr, (const int32_t*)b_c.p, (int32_t)n_docs, k, (int32_t*)b_oi.p,
+                             (float*)b_os.p, st));
+        k_cos_patch<<<blocks_for((int64_t)nr * k, 256), 256, 0, st>>>((const int32_t*)b_rows.p, nr, k, (const int32_t*)b_oi.p,
+                                                                      (const float*)b_os.p, doc_base, out_ids, out_sims);
+        BR_CUDA(cudaGetLastError());
+        BR_CUDA(cudaStreamSynchronize(st));
+    }
     return BR_OK;
 }
 

@@ -165,7 +165,9 @@ int br_row_inv_norms(const void* emb_bf16_dev, int64_t n, int32_t d, float* out_
 /* Exact brute-force top-k (1 <= k <= 256) of every query over all docs: bf16 tcgen05 GEMM with the
  * normalisation and the top-k filter fused into the epilogue.  doc_inv_norm_dev from
  * br_row_inv_norms (computed once per corpus).  Outputs [nq, k], best first, ties by doc id:
- * out_ids_dev int64 (doc_base + local row, -1 pads), out_sims_dev float.  Synchronises `stream`. */
+ * out_ids_dev int64 (doc_base + local row, -1 pads), out_sims_dev float.  A query with more than 1024 docs tied at
+ * its threshold (masses of duplicate embeddings) is answered exactly by a full gather pass instead of the filter
+ * (up to 64 such queries per call).  Synchronises `stream`. */
 int br_cosine_topk(const void* docs_bf16_dev, const float* doc_inv_norm_dev, int64_t n_docs, int32_t d,
                    const void* queries_bf16_dev, int32_t nq, int32_t k, int64_t doc_base,
                    int64_t* out_ids_dev, float* out_sims_dev, void* stream);

@@ -93,3 +93,20 @@ def test_cosine_rerank_of_bm25_candidates():
         assert set(ids[i].tolist()) <= set(cc.tolist())
         if not np.array_equal(ids[i], cc[ri[0]]):
             assert np.allclose(np.sort(sims[i]), np.sort(rs[0]), rtol=RTOL, atol=ATOL)
+
+
+def test_cosine_massive_ties_are_answered_exactly():
+    """2,000 identical embedding rows: a query equal to them has 2,000 candidates tied at the top - more than the filter's
+    1,024-slot lists hold - and must still get the exact answer (lowest row ids first), like every other query."""
+    from document_retrieval_b200.cosine import CosineIndex
+    g = torch.Generator().manual_seed(5)
+    docs = torch.randn(6000, 128, generator=g).to(torch.bfloat16)
+    dup = torch.arange(1000, 6000, 2)[:2000]
+    docs[dup] = docs[999].clone()
+    qs = torch.cat([docs[999:1000], torch.randn(40, 128, generator=g).to(torch.bfloat16)])
+    ids, sims = CosineIndex(docs).topk(qs, 10)
+    ids, sims = ids.cpu().numpy(), sims.cpu().numpy()
+    want = np.sort(np.concatenate([[999], dup.numpy()]))[:10]
+    assert np.array_equal(ids[0], want)
+    np.testing.assert_allclose(sims[0], 1.0, rtol=1e-5)
+    _check(ids[1:], sims[1:], docs.float().numpy(), qs[1:].float().numpy(), 10)
