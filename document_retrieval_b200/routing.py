@@ -74,8 +74,9 @@ def _batched_top(bm25_models, rows, k, preprocess, batch_size):
             if kk < 1:
                 continue
             qs = [rows[i]["query"] for i in chunk]
-            if preprocess is _default_preprocess and all(isinstance(q, str) for q in qs) and \
-                    getattr(model, "terms", None) is not None and hasattr(model, "retrieve_top_n_texts"):
+            has_vocab = getattr(model, "vocabulary", None) is not None or getattr(model, "_terms", None) is not None
+            if preprocess is _default_preprocess and all(isinstance(q, str) for q in qs) and has_vocab and \
+                    hasattr(model, "retrieve_top_n_texts"):
                 # already-preprocessed query strings: `preprocessed_query.split()` (bm25_ranking.ipynb:341-347) and the
                 # vocabulary lookup run on the GPU for the whole chunk
                 try:
