@@ -219,7 +219,9 @@ int br_set_option(br_index* ix, const char* name, int value);
  * doc_offsets, returns the token total) -> caller allocates token_ids_dev int32[n_tokens] ->
  * br_vocab_build (corpus: creates the vocabulary) or br_vocab_lookup (queries: ids under an
  * existing vocabulary, -1 = out of vocabulary, which the scoring kernels skip like
- * `if word not in self.idf: continue`, bm25_ranking.ipynb:195-196).  All three synchronise `stream`. */
+ * `if word not in self.idf: continue`, bm25_ranking.ipynb:195-196).  All three synchronise `stream`.
+ * Limits per call: fewer than 2^31 tokens, documents shorter than 2 GiB (BR_ERR_UNSUPPORTED otherwise); scratch memory
+ * is about 40 bytes per token, taken from the device's default stream-ordered pool. */
 typedef struct br_vocab br_vocab;
 int br_tokenize_count(const uint8_t* text_dev, const int64_t* doc_byte_off_dev, int64_t n_docs, int bigrams,
                       int64_t* doc_tok_off_dev, int64_t* n_tokens_host, void* stream);
