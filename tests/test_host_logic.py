@@ -52,3 +52,25 @@ def test_pack_texts_arrow_layout():
     assert off.tolist() == np.concatenate([[0], np.cumsum([len(e) for e in enc])]).tolist()
     d0, o0 = pack_texts([])
     assert d0.size == 0 and o0.tolist() == [0]
+
+
+def test_c_abi_header_is_plain_c(tmp_path):
+    """include/br_b200.h must be consumable by a C compiler (the boundary is a C ABI: no C++ or torch types): a C99
+    translation unit that includes it and takes the address of every declared entry point compiles with -Wall -Werror."""
+    import os
+    import re
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no gcc")
+    hdr = open(os.path.join(root, "include", "br_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(br_[a-z0-9_]+)\s*\(", hdr)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "br_b200.h"\n#include <stddef.h>\nconst void* const entry_points[] = {\n'
+                   + "".join(f"    (const void*)&{n},\n" for n in names) + "};\n"
+                   "int n_entry_points(void) { return (int)(sizeof(entry_points) / sizeof(entry_points[0])); }\n")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-Wno-pedantic", "-I", os.path.join(root, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "abi.o")])
