@@ -9,7 +9,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from document_retrieval_b200.cosine import CosineIndex  # noqa: E402
 
-KEYS = ["BR_COS_KERNEL", "BR_COS_QS_BN", "BR_COS_QS_WINDOW", "BR_COS_DEBUG_NOEPI", "BR_COS_CHUNK0", "BR_COS_CHUNK_MULT"]
+KEYS = ["BR_COS_KERNEL", "BR_COS_QS_BN", "BR_COS_QS_WINDOW", "BR_COS_DEBUG_NOEPI", "BR_COS_CHUNK0", "BR_COS_CHUNK_MULT", "BR_COS_TIGHTEN_T"]
 
 
 def main():

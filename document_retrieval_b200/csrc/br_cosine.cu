@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(TC_T) k_tighten_cos(float* __restrict__ thr, i
     float* hs = cand_h + (int64_t)q * COS_CAP;
     int n_sort = 32;                                   // smallest power of two covering the list
     while (n_sort < n) n_sort <<= 1;
-    for (int i = threadIdx.x; i < n_sort; i += TC_T) {
+    for (int i = threadIdx.x; i < n_sort; i += blockDim.x) {
         s_h[i] = i < n ? hs[i] : -CUDART_INF_F;
         s_id[i] = i < n ? ids[i] : 0x7fffffff;
     }
@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(TC_T) k_tighten_cos(float* __restrict__ thr, i
     for (int size = 2; size <= n_sort; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
-            for (int i = threadIdx.x; i < n_sort / 2; i += TC_T) {
+            for (int i = threadIdx.x; i < n_sort / 2; i += blockDim.x) {
                 const int x = 2 * i - (i & (stride - 1)), y = x + stride;
                 const bool up = (x & size) == 0;
                 const float hx = s_h[x], hy = s_h[y];
@@ -848,12 +848,12 @@ __global__ void __launch_bounds__(TC_T) k_tighten_cos(float* __restrict__ thr, i
     float th = thr[q];
     if (n >= K && s_h[K - 1] > th) th = s_h[K - 1];
     int keep = 0;
-    for (int i = threadIdx.x; i < n; i += TC_T) keep += (s_h[i] >= th) ? 1 : 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) keep += (s_h[i] >= th) ? 1 : 0;
     for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
     if ((threadIdx.x & 31) == 0 && keep) atomicAdd(&s_keep, keep);
     __syncthreads();
     keep = s_keep;
-    for (int i = threadIdx.x; i < n; i += TC_T) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
         ids[i] = i < keep ? s_id[i] : -1;
         hs[i] = i < keep ? s_h[i] : 0.f;
     }
@@ -1056,6 +1056,8 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     // wall time, which makes doubling (13 launches, ~120 emissions per query) faster than 3x / 4x / 8x growth
     const int chunk0 = getenv("BR_COS_CHUNK0") ? std::max(1, atoi(getenv("BR_COS_CHUNK0"))) : 1;
     const int growth = getenv("BR_COS_CHUNK_MULT") ? std::max(2, atoi(getenv("BR_COS_CHUNK_MULT"))) : 2;
+    // candidate lists are ~2k long after the first rounds: small CTAs (more of them resident, cheaper barriers)
+    const int tighten_t = getenv("BR_COS_TIGHTEN_T") ? std::min(TC_T, std::max(32, atoi(getenv("BR_COS_TIGHTEN_T")) & ~31)) : 64;
     int t0 = 0, chunk = chunk0;
     while (t0 < n_dt) {
         const int nt = std::min(chunk, n_dt - t0);
@@ -1076,7 +1078,7 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
             k_cosine_gemm<<<grid, CG_THREADS, CG_SMEM, st>>>(map_d, map_q, a);
         }
         BR_CUDA(cudaGetLastError());
-        k_tighten_cos<<<nq, TC_T, 0, st>>>(thr, (int32_t*)b_cnt.p, (int32_t*)b_prev.p, (int32_t*)b_cand.p, (float*)b_h.p, k,
+        k_tighten_cos<<<nq, tighten_t, 0, st>>>(thr, (int32_t*)b_cnt.p, (int32_t*)b_prev.p, (int32_t*)b_cand.p, (float*)b_h.p, k,
                                            (int32_t*)b_ovf.p);
         BR_CUDA(cudaGetLastError());
         t0 += nt;
