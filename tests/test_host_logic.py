@@ -74,3 +74,43 @@ def test_c_abi_header_is_plain_c(tmp_path):
                    "int n_entry_points(void) { return (int)(sizeof(entry_points) / sizeof(entry_points[0])); }\n")
     subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-Wno-pedantic", "-I", os.path.join(root, "include"),
                            "-c", str(src), "-o", str(tmp_path / "abi.o")])
+
+
+class _StandInModel:
+    """Oracle-backed stand-in with the attributes the routing layer touches (test infrastructure; the product's
+    model is CUDA-only)."""
+
+    def __init__(self, docs):
+        off = np.zeros(len(docs) + 1, np.int64)
+        np.cumsum([len(d) for d in docs], out=off[1:])
+        self.words = sorted({w for d in docs for w in d})
+        self.w2i = {w: i for i, w in enumerate(self.words)}
+        tok = np.asarray([self.w2i[w] for d in docs for w in d], np.int32)
+        self.ix = orc.build_index(off, tok, len(self.words))
+        self.corpus_size = len(docs)
+
+    def retrieve_top_n_batch(self, queries, n):
+        import torch
+        ids = np.full((len(queries), n), -1, np.int32)
+        for i, q in enumerate(queries):
+            a, _ = orc.retrieve_top_n(self.ix, [self.w2i.get(w, -1) for w in q], n)
+            ids[i, :a.size] = a
+        return torch.from_numpy(ids), None
+
+
+def test_recall_and_test_retrieval_follow_the_notebook_semantics():
+    """bm25_ranking.ipynb:329-354 / :368-389 on the CPU: unknown languages are skipped but stay in the Recall denominator
+    (:331,353) and give [] in retrieve_test_queries (:374-376); k larger than a corpus is clipped."""
+    from document_retrieval_b200 import evaluate_recall_at_k, retrieve_test_queries
+    docs = {"en": [["apple", "pie"], ["banana", "split"], ["apple", "banana", "smoothie"]], "fr": [["tarte", "pomme"], ["banane"]]}
+    models = {lang: _StandInModel(d) for lang, d in docs.items()}
+    id_maps = {lang: [f"{lang}{i}" for i in range(len(d))] for lang, d in docs.items()}
+    rows = [{"query": "apple pie", "lang": "en", "positive_docs": "en0"},
+            {"query": ["banane"], "lang": "fr", "positive_docs": "fr1"},
+            {"query": "smoothie", "lang": "en", "positive_docs": "en1"},          # a miss at k = 1
+            {"query": "whatever", "lang": "ko", "positive_docs": "ko0"}]         # unknown language
+    assert evaluate_recall_at_k(models, id_maps, rows, k=1) == 2 / 4
+    assert evaluate_recall_at_k(models, id_maps, rows, k=10) == 3 / 4
+    out = retrieve_test_queries(models, id_maps, rows, k=10)
+    assert out[3] == [] and out[0][0] == "en0" and out[1][0] == "fr1" and len(out[1]) == 2 and len(out[0]) == 3
+    assert evaluate_recall_at_k(models, id_maps, [], k=10) == 0
