@@ -46,6 +46,8 @@ def parse():
     p.add_argument("--k", type=int, default=10)
     p.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--opt", action="append", default=[], metavar="NAME=INT",
+                   help="br_set_option on the index (tuning experiments, e.g. defer_pm=800); not used by the driver")
     return p.parse_args()
 
 
@@ -261,6 +263,9 @@ def main():
     torch.cuda.synchronize()
     build_s = time.time() - t0
     model = sh.local
+    for o in args.opt:
+        name, val = o.split("=")
+        model.set_option(name, int(val))
     st = model.stats()
     keep_host = (world == 1 and rank == 0 and not args.no_cpu_baseline)
     do_h = doc_offsets.cpu().numpy() if keep_host else None

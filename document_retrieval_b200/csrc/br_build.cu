@@ -119,18 +119,36 @@ __global__ void k_df(const uint32_t* __restrict__ tstart, const uint32_t* __rest
 __global__ void k_weights(const int64_t* __restrict__ row_ptr, int32_t vocab, int64_t nnz,
                           br_posting* __restrict__ post, const uint16_t* __restrict__ tf,
                           const uint32_t* __restrict__ dl, const double* __restrict__ idf, double avgdl,
-                          double k1, double b, int variant) {
+                          double k1, double b, int variant, float* __restrict__ ub) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nnz) return;
-    // term of posting j: last t with row_ptr[t] <= j
-    int32_t lo = 0, hi = vocab;  // invariant: row_ptr[lo] <= j < row_ptr[hi]
-    while (hi - lo > 1) {
-        const int32_t mid = (lo + hi) >> 1;
-        if (row_ptr[mid] <= j) lo = mid; else hi = mid;
+    const int lane = threadIdx.x & 31;
+    int32_t lo = -1;
+    float wv = 0.f;
+    if (j < nnz) {
+        // term of posting j: last t with row_ptr[t] <= j
+        lo = 0;
+        int32_t hi = vocab;  // invariant: row_ptr[lo] <= j < row_ptr[hi]
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (row_ptr[mid] <= j) lo = mid; else hi = mid;
+        }
+        const uint32_t d = post[j].doc;
+        const double c = bm25_contrib(idf[lo], (double)tf[j], (double)dl[d], avgdl, k1, b, variant);
+        wv = isnan(c) ? 0.f : (float)c;
+        post[j].w = wv;
     }
-    const uint32_t d = post[j].doc;
-    const double c = bm25_contrib(idf[lo], (double)tf[j], (double)dl[d], avgdl, k1, b, variant);
-    post[j].w = isnan(c) ? 0.f : (float)c;
+    // ub[t] = max posting weight of term t (the score upper bound of the tiled scorer's deferral): one atomic per
+    // (warp, term) - the lanes of a warp hold consecutive postings, i.e. mostly one term.  Weights < 0 (idf without
+    // +1) count as 0; non-negative floats order like their bit patterns.
+    unsigned todo = __ballot_sync(0xffffffffu, lo >= 0);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int32_t t = __shfl_sync(0xffffffffu, lo, leader);
+        const bool mine = lo == t;
+        const unsigned mx = __reduce_max_sync(0xffffffffu, mine ? __float_as_uint(fmaxf(wv, 0.f)) : 0u);
+        if (lane == leader) atomicMax(reinterpret_cast<unsigned*>(ub) + t, mx);
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
 }
 
 __global__ void k_skip(const int64_t* __restrict__ row_ptr, const br_posting* __restrict__ post,
@@ -192,7 +210,7 @@ void index_free(br_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     cudaFree(ix->row_ptr); cudaFree(ix->post); cudaFree(ix->post_cos); cudaFree(ix->tf); cudaFree(ix->dl); cudaFree(ix->df);
-    cudaFree(ix->idf); cudaFree(ix->hot_slot); cudaFree(ix->skip); cudaFree(ix->sig_bit); cudaFree(ix->dense_rows); cudaFree(ix->row_slot);
+    cudaFree(ix->idf); cudaFree(ix->ub); cudaFree(ix->hot_slot); cudaFree(ix->skip); cudaFree(ix->sig_bit); cudaFree(ix->dense_rows); cudaFree(ix->row_slot);
     ix->ws_prep.release(); ix->ws_dense.release(); ix->ws_sel.release(); ix->ws_cand.release();
     ix->ws_misc.release(); ix->ws_tile.release(); ix->ws_sort.release();
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
@@ -205,6 +223,7 @@ static int alloc_common(br_index* ix) {
     BR_CUDA(cudaMalloc(&ix->df, sizeof(uint32_t) * (size_t)ix->vocab));
     BR_CUDA(cudaMalloc(&ix->idf, sizeof(double) * (size_t)ix->vocab));
     BR_CUDA(cudaMalloc(&ix->hot_slot, sizeof(int32_t) * (size_t)ix->vocab));
+    BR_CUDA(cudaMalloc(&ix->ub, sizeof(float) * (size_t)ix->vocab));
     return BR_OK;
 }
 
@@ -380,21 +399,18 @@ int index_finalize(br_index* ix, double k1, double b, int variant, double n_stat
         }
     }
     BR_CUDA(cudaMemcpyAsync(ix->idf, ix->h_idf.data(), sizeof(double) * V, cudaMemcpyHostToDevice, st));
+    BR_CUDA(cudaMemsetAsync(ix->ub, 0, sizeof(float) * V, st));
     if (ix->nnz > 0) {
         k_weights<<<blocks_for(ix->nnz, 256), 256, 0, st>>>(ix->row_ptr, ix->vocab, ix->nnz, ix->post, ix->tf,
-                                                            ix->dl, ix->idf, ix->avgdl, k1, b, variant);
+                                                            ix->dl, ix->idf, ix->avgdl, k1, b, variant, ix->ub);
         BR_CUDA(cudaGetLastError());
     }
     // hot-term skip tables (shard-local structure: decided from the local df)
     if (!ix->skip) {
-        ix->sub_shift = 9;
-        const char* e = getenv("BR_SUB_SHIFT");
-        if (e) { int v = atoi(e); if (v >= 5 && v <= 16) ix->sub_shift = v; }
+        ix->sub_shift = 9;                       // 512-doc sub-ranges (= TILE_SHIFT of br_tile.cu)
         ix->n_sub = (int32_t)((ix->n_docs + (1LL << ix->sub_shift) - 1) >> ix->sub_shift);
-        double frac = 0.25;
-        const char* f = getenv("BR_HOT_FRAC");
-        if (f) { double v = atof(f); if (v > 0) frac = v; }
-        const uint32_t hot_min = (uint32_t)fmax(4.0, frac * (double)ix->n_sub);
+        const uint32_t hot_min = (uint32_t)fmax(4.0, 0.25 * (double)ix->n_sub);
+        ix->hot_min = hot_min;
         std::vector<int32_t> slot(V, -1), hot_terms;
         for (size_t t = 0; t < V; ++t)
             if (ix->h_df[t] >= hot_min) { slot[t] = (int32_t)hot_terms.size(); hot_terms.push_back((int32_t)t); }
@@ -415,20 +431,29 @@ int index_finalize(br_index* ix, double k1, double b, int variant, double n_stat
         }
     }
     {   // dense rows (rebuilt at every finalize: they hold the weights)
-        double frac = 0.2;
-        if (const char* e = getenv("BR_ROW_FRAC")) { double v = atof(e); if (v > 0) frac = v; }
+        double frac = 0.2;                       // streamed rows
+        const double look_frac = 1.0 / 64.0;     // look-up rows
         std::vector<int32_t> cand_terms;
         for (size_t t = 0; t < V; ++t)
-            if (ix->n_hot > 0 && (double)ix->h_df[t] >= frac * (double)ix->n_docs && ix->h_df[t] > 0) cand_terms.push_back((int32_t)t);
-        std::sort(cand_terms.begin(), cand_terms.end(), [&](int32_t x, int32_t y) { return ix->h_df[(size_t)x] > ix->h_df[(size_t)y]; });
-        if (cand_terms.size() > 32) cand_terms.resize(32);
+            if (ix->n_hot > 0 && (double)ix->h_df[t] >= look_frac * (double)ix->n_docs && ix->h_df[t] >= ix->hot_min)
+                cand_terms.push_back((int32_t)t);
+        std::sort(cand_terms.begin(), cand_terms.end(), [&](int32_t x, int32_t y) {
+            return ix->h_df[(size_t)x] != ix->h_df[(size_t)y] ? ix->h_df[(size_t)x] > ix->h_df[(size_t)y] : x < y;
+        });
+        ix->n_pad = ((ix->n_docs + 4095) / 4096) * 4096;
+        // at most 384 rows and 16 GiB (C4: ~260 rows x 35 MB = 9 GB of the 180 GB)
+        const size_t max_rows = std::min<size_t>(384, (size_t)((16LL << 30) / (4 * ix->n_pad)));
+        if (cand_terms.size() > max_rows) cand_terms.resize(max_rows);
+        int32_t n_s = 0;
+        for (int32_t t : cand_terms)
+            if ((double)ix->h_df[(size_t)t] >= frac * (double)ix->n_docs && n_s < 32) ++n_s;
         cudaFree(ix->dense_rows); ix->dense_rows = nullptr;
         ix->n_rows = (int32_t)cand_terms.size();
-        ix->n_pad = ((ix->n_docs + 4095) / 4096) * 4096;
-        std::vector<int8_t> slot(V, (int8_t)-1);
-        for (size_t r = 0; r < cand_terms.size(); ++r) slot[(size_t)cand_terms[r]] = (int8_t)r;
-        if (!ix->row_slot) BR_CUDA(cudaMalloc(&ix->row_slot, V));
-        BR_CUDA(cudaMemcpyAsync(ix->row_slot, slot.data(), V, cudaMemcpyHostToDevice, st));
+        ix->n_srows = n_s;
+        std::vector<int16_t> slot(V, (int16_t)-1);
+        for (size_t r = 0; r < cand_terms.size(); ++r) slot[(size_t)cand_terms[r]] = (int16_t)r;
+        if (!ix->row_slot) BR_CUDA(cudaMalloc(&ix->row_slot, sizeof(int16_t) * V));
+        BR_CUDA(cudaMemcpyAsync(ix->row_slot, slot.data(), sizeof(int16_t) * V, cudaMemcpyHostToDevice, st));
         if (ix->n_rows > 0) {
             int32_t* d_terms = nullptr;
             BR_CUDA(cudaMalloc(&ix->dense_rows, sizeof(float) * (size_t)ix->n_rows * (size_t)ix->n_pad));

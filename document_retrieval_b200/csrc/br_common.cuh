@@ -104,19 +104,24 @@ struct br_index {
     uint32_t* dl = nullptr;         // [N]
     uint32_t* df = nullptr;         // [V]     shard-local document frequency
     double* idf = nullptr;          // [V]     statistics in force (NaN where df_stat == 0)
+    float* ub = nullptr;            // [V]     largest posting weight of the term on this shard (0 when none / negative):
+                                    //         the per-term score upper bound of the tiled scorer's MaxScore deferral
 
     // hot-term skip tables for the tiled scorer: term t is "hot" when hot_slot[t] >= 0; then
     // skip[hot_slot[t] * (n_sub+1) + j] = offset (relative to row_ptr[t]) of the first posting
     // with doc >= j << sub_shift.
     int sub_shift = 0;
     int32_t n_sub = 0, n_hot = 0;
+    uint32_t hot_min = 0;           // smallest df with a skip table
     int32_t* hot_slot = nullptr;    // [V]
     uint32_t* skip = nullptr;       // [n_hot, n_sub+1]
-    // dense rows: for the few terms present in >= ~20% of the docs, w[row][doc] as plain fp32 rows (0 where the doc
-    // lacks the term); the tiled scorer initialises its accumulators from them instead of walking their postings
+    // dense rows: w[row][doc] as plain fp32 rows (0 where the doc lacks the term), most frequent term first.
+    // Rows [0, n_srows) - terms present in >= ~20% of the docs - are STREAMED by the tiled scorer (accumulators are
+    // initialised from them instead of walking their postings); all n_rows rows (terms with df >= N/64) serve as
+    // LOOK-UP tables: a term the scorer has deferred (MaxScore) is added to a candidate doc with one 4-byte load.
     float* dense_rows = nullptr;    // [n_rows, n_pad]
-    int8_t* row_slot = nullptr;     // [V] row index or -1
-    int32_t n_rows = 0;
+    int16_t* row_slot = nullptr;    // [V] row index or -1
+    int32_t n_rows = 0, n_srows = 0;
     int64_t n_pad = 0;
     int8_t* sig_bit = nullptr;      // [V] rank (0 = largest df) among the 32 most frequent terms, -1 otherwise
 
@@ -129,8 +134,12 @@ struct br_index {
     br::DevBuf ws_prep, ws_dense, ws_sel, ws_cand, ws_misc, ws_tile, ws_sort;
     br_query_stats stats{};
 
-    bool allow_fused = true;
+    bool allow_fused = true, allow_fused_bigk = true;
     int tile_g = 0;
+    int defer_pm = 700;             // MaxScore deferral budget of the tiled scorer, per mille of the threshold (0 = off)
+    int tile_tpb = 8;               // consecutive tiles per CTA in the large launches
+    int tile_dense_min = 16;        // average postings of a term per 512-doc sub-range from which its slices are walked
+                                    // term by term (whole warp, pipelined) instead of concatenated with the sparse ones
 
     // optional event timing of the scoring kernel
     bool profiling = false;

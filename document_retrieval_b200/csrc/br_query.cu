@@ -707,9 +707,7 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
     PrepView pv;
     int64_t* chunk_start;
     int32_t T;
-    stage_mark("batch_enter", st);
     BR_TRY(prep_queries(ix, q_terms, q_off, nq, dedup, st, &pv, &chunk_start, &T));
-    stage_mark("prep", st);
     // algorithmic bytes of this batch: 8 B per posting of every distinct in-vocab query term
     std::vector<int64_t> hP((size_t)nq);
     BR_CUDA(cudaMemcpyAsync(hP.data(), pv.P, sizeof(int64_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
@@ -763,7 +761,6 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
     for (int64_t v : hP) sum += v;
     ix->stats.postings_bytes = 8 * sum;
     ix->prof_collect();
-    stage_mark("batch_exit", st);
     return BR_OK;
 }
 

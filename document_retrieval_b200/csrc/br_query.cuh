@@ -26,7 +26,6 @@ int launch_rescore_heads(br_index* ix, const int32_t* q_off, const PrepView& pv,
 int launch_final_select(const int32_t* cand, const double* cand_score, const int64_t* cand_off, int32_t q_begin,
                         int32_t nq, int32_t k, int positive_only, int32_t* out_ids, double* out_scores,
                         int32_t* out_counts, cudaStream_t st, const int32_t* cnt_hint = nullptr);
-void stage_mark(const char* name, cudaStream_t st);
 bool fused_supported(const br_index* ix, int32_t k, int32_t nq);
 int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t nq, int32_t k, int dedup,
                int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st,

@@ -25,8 +25,6 @@
 // so far and compacts the list.  With doubling chunks every chunk emits about k new candidates per
 // query, so the candidate list stays ~k long and the float64 re-score costs almost nothing.
 #include <math_constants.h>
-#include <stdio.h>
-#include <time.h>
 
 #include <algorithm>
 
@@ -49,14 +47,21 @@ constexpr int TILE_QT = 20;          // max distinct hot terms of one query on t
 constexpr int TILE_CAP = 1024;       // candidates kept per query between tighten rounds (k <= 32)
 constexpr int TILE_CAP_BIG = 8192;   // the same for 32 < k <= 1024: one tile of 4096 docs may pass entirely before the first
                                      // threshold exists, later chunks add about k candidates each
-constexpr uint32_t TILE_DENSE_MIN = 16;  // postings of a term in a 512-doc sub-range from which the warp works cooperatively
 static_assert((1 << 3) == TILE_W, "TILE_DOCS_SHIFT assumes W == 8");
 
 struct __align__(16) TileEntry {
     int32_t term;
     int32_t slot;
-    uint8_t mult[8];
+    uint8_t mult[4];     // multiplicity of the term in each query of the group (0: the query lacks it)
+    uint8_t pos[4];      // index of the term in that query's unique-term list (bit of the query's deferral mask)
 };
+
+// a deferred term of one query: look-up row and multiplicity
+struct __align__(8) NeEntry {
+    int32_t row;
+    float mult;
+};
+constexpr int NE_MAX = 32;           // deferred terms per query (a query on this path has <= 32 terms)
 
 // cold entry: doc offset inside the tile (12 bits) | query slot in the group (3 bits) << 12, weight
 struct __align__(8) ColdEntry {
@@ -73,9 +78,9 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
                                                    TileEntry* __restrict__ entries, int32_t* __restrict__ n_entries,
                                                    int32_t* __restrict__ elig, unsigned long long* __restrict__ cold_total,
                                                    int64_t dense_df_min, const int32_t* __restrict__ perm,
-                                                   const int8_t* __restrict__ row_slot) {
+                                                   const int16_t* __restrict__ row_slot, int n_srows) {
     __shared__ int32_t s_term[4][256];
-    __shared__ uint8_t s_q[4][256], s_m[4][256];
+    __shared__ uint8_t s_q[4][256], s_m[4][256], s_p[4][256];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int g = blockIdx.x * 4 + wl;
     const int n_groups = (nq + G - 1) / G;
@@ -112,6 +117,7 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
                 s_term[wl][p] = t;
                 s_q[wl][p] = (uint8_t)i;
                 s_m[wl][p] = (uint8_t)pv.u_mult[off + j];
+                s_p[wl][p] = (uint8_t)j;
             }
             n += __popc(m);
         }
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
             bool first = i < n;
             if (first) {
                 const int32_t t = s_term[wl][i];
-                const bool is_row = row_slot[t] >= 0;
+                const bool is_row = row_slot[t] >= 0 && row_slot[t] < n_srows;      // streamed row
                 const bool dense = row_ptr[t + 1] - row_ptr[t] >= dense_df_min;
                 const int cls = is_row ? -1 : (dense ? 0 : 1);          // rows first, then dense postings, then sparse
                 if (cls != pass) first = false;
@@ -138,9 +144,9 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
                 e.term = s_term[wl][i];
                 e.slot = pass < 0 ? (int32_t)row_slot[e.term] : hot_slot[e.term];
 #pragma unroll
-                for (int x = 0; x < 8; ++x) e.mult[x] = 0;
+                for (int x = 0; x < 4; ++x) e.mult[x] = e.pos[x] = 0;
                 for (int j = i; j < n; ++j)
-                    if (s_term[wl][j] == e.term) e.mult[s_q[wl][j]] = s_m[wl][j];
+                    if (s_term[wl][j] == e.term) { e.mult[s_q[wl][j]] = s_m[wl][j]; e.pos[s_q[wl][j]] = s_p[wl][j]; }
                 entries[(int64_t)g * umax + U + __popc(m & ((1u << lane) - 1))] = e;
             }
             U += __popc(m);
@@ -306,106 +312,219 @@ struct TileArgs {
     int tpb;                      // consecutive tiles per CTA
     int has_mult;                 // 0: every multiplicity is 1 (set(query) semantics)
     const int32_t* perm;          // group g, slot i -> query perm[g*G+i] (queries sorted by frequent-term signature)
+    const uint32_t* defer_mask;   // [nq] bit j: the j-th unique term of the query is deferred in this launch
+    const float* ne_ub;           // [nq] sum of the deferred terms' upper bounds (rounded up)
+    const int16_t* row_slot;      // [V] look-up row of a term (every deferred term has one)
 };
+
+// One fp32 select out of G registers by a run-time index (keeps per-query scalars out of local memory).
+template <int G>
+__device__ __forceinline__ float sel_q(const float (&v)[G], int q) {
+    float r = v[0];
+#pragma unroll
+    for (int i = 1; i < G; ++i) r = q == i ? v[i] : r;
+    return r;
+}
 
 #ifndef BR_TILE_MINB
 #define BR_TILE_MINB 3            // resident CTAs per SM the register allocation is sized for (64 KB of accumulators each)
 #endif
+constexpr int LIST_CAP = 64;      // crossing-list slots per warp and sub-range (overflow -> full scan of the sub-range)
+
+// MaxScore deferral (exact): between launches every query gets a plan (make_plan): the terms with the smallest upper
+// bounds ub[t] = max posting weight, as long as their sum stays below a fraction of the query's threshold, are
+// "deferred" - not streamed at all.  A doc whose partial score p over the streamed ("essential") terms satisfies
+// p + sum(deferred ub) < thr*(1-band) cannot reach the threshold and is never looked at; the few others are completed
+// by direct look-ups before the usual filter: every deferrable term (df >= N/64) has a look-up row w[row][doc], so a
+// completion is a handful of independent 4-byte loads, no search.  The densest terms have the smallest bounds, so in
+// the steady state neither the streamed rows nor the dense posting slices are read.
+// Without streamed rows every accumulator starts at zero and only grows, so the lane that has just updated one knows
+// whether it has reached t1 = thr*(1-band) - sum(deferred ub): it records (query, doc) in its warp's crossing list,
+// and after the posting phases the warp completes and filters just the listed docs (an atomic exchange on the
+// accumulator removes duplicates).  The 512 accumulators of a (query, sub-range) are scanned only for queries that
+// still stream rows / have no threshold yet, or when a crossing list overflows.
+// After the CTA prologue there is no block barrier: every warp fetches the slice bounds of its own sub-range (one tile
+// ahead, into registers) and its own copy of the thresholds.
 template <int G>
 __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* acc = reinterpret_cast<float*>(smem_raw);                                     // [G][W][S]
-    TileEntry* ent = reinterpret_cast<TileEntry*>(smem_raw + sizeof(float) * G * TILE_W * TILE_S);
+    TileEntry* ent = reinterpret_cast<TileEntry*>(smem_raw + sizeof(float) * G * TILE_W * TILE_S);   // streamed entries
     int64_t* s_base = reinterpret_cast<int64_t*>(ent + a.umax);                          // [umax]
-    uint32_t* s_bnd = reinterpret_cast<uint32_t*>(s_base + a.umax);                      // [umax][W+1]
-    float4* s_fm = reinterpret_cast<float4*>(s_bnd + a.umax * (TILE_W + 1));             // [umax] multiplicities as floats
+    float4* s_fm = reinterpret_cast<float4*>(s_base + a.umax);                           // [umax] multiplicities as floats
     uint32_t* s_skiprow = reinterpret_cast<uint32_t*>(s_fm + a.umax);                    // [umax] slot * (n_sub+1)
+    NeEntry* s_ne = reinterpret_cast<NeEntry*>(s_skiprow + a.umax);                      // [G][NE_MAX] deferred terms per query
+    uint2* s_bnd_all = reinterpret_cast<uint2*>(s_ne + G * NE_MAX);                      // [W][umax] slice (lo, hi) per warp
+    uint16_t* s_list_all = reinterpret_cast<uint16_t*>(s_bnd_all + TILE_W * a.umax);     // [W][LIST_CAP]
     __shared__ int s_qi[8];                                                              // query of each group slot (-1: none)
+    __shared__ int s_cnt[4];                                                             // Ur, Ud, U (streamed), rows mask
+    __shared__ int s_nne[4];                                                             // deferred terms of each query
+    __shared__ float s_neub[4];
+    __shared__ float s_thq[TILE_W][4], s_t1[TILE_W][4];                                  // per-warp thresholds of the tile
+    __shared__ int s_lcnt[TILE_W];
 
     const int g = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int U = a.n_entries[g] & 0x3ff, Ud = (a.n_entries[g] >> 10) & 0x3ff, Ur = a.n_entries[g] >> 20;
     const int tile_first = a.tile0 + blockIdx.y * a.tpb;
     const int tile_last = min(tile_first + a.tpb, a.tile_end);          // exclusive
 
     if (threadIdx.x < G) {
         const int pos = g * G + threadIdx.x;
         const int qi = pos < a.nq ? a.perm[pos] : -1;
-        s_qi[threadIdx.x] = (qi >= 0 && a.elig[qi]) ? qi : -1;
+        const bool ok = qi >= 0 && a.elig[qi];
+        s_qi[threadIdx.x] = ok ? qi : -1;
+        s_neub[threadIdx.x] = ok ? a.ne_ub[qi] : 0.f;
     }
-    for (int u = threadIdx.x; u < U; u += TILE_W * 32) {
-        const TileEntry e = a.entries[(int64_t)g * a.umax + u];
-        ent[u] = e;
-        s_base[u] = a.row_ptr[e.term];
-        s_fm[u] = make_float4((float)e.mult[0], (float)e.mult[1], (float)e.mult[2], (float)e.mult[3]);
-        s_skiprow[u] = (uint32_t)e.slot * (uint32_t)(a.n_sub + 1);      // row terms: slot = row index (unused here)
-    }
-    // slice bounds of the first tile; the bounds of tile t+1 are fetched into registers while tile t is processed
-    constexpr int NB = (TILE_QT * G * (TILE_W + 1) + TILE_W * 32 - 1) / (TILE_W * 32);
-    uint32_t nb[NB], bsel[NB];                       // bsel: bit 31 valid | j << 16 | u  (which bound this thread fetches)
+    __syncthreads();
+    if (w == 0) {
+        // split the group's entries into streamed and deferred ones (stable: rows, dense postings, sparse)
+        const int U0 = a.n_entries[g] & 0x3ff, Ud0 = (a.n_entries[g] >> 10) & 0x3ff, Ur0 = a.n_entries[g] >> 20;
+        uint32_t dm[G];
 #pragma unroll
-    for (int k = 0; k < NB; ++k) {
-        const int i = threadIdx.x + k * TILE_W * 32;
-        const int u = i / (TILE_W + 1), j = i - u * (TILE_W + 1);
-        bsel[k] = (i < U * (TILE_W + 1) && u >= Ur) ? (0x80000000u | ((uint32_t)j << 16) | (uint32_t)u) : 0u;
-        if (i < U * (TILE_W + 1)) s_bnd[i] = 0;      // row terms keep empty slices
-    }
-    __syncthreads();                                 // s_skiprow is complete
-    auto load_bounds = [&](int tile) {
+        for (int i = 0; i < G; ++i) dm[i] = s_qi[i] >= 0 ? a.defer_mask[s_qi[i]] : 0u;
+        int na = 0, ur = 0, ud = 0;
+        int nne[G];
 #pragma unroll
-        for (int k = 0; k < NB; ++k)
-            if (bsel[k] >> 31)
-                nb[k] = __ldg(a.skip + s_skiprow[bsel[k] & 0xffffu] + min(tile * TILE_W + (int)((bsel[k] >> 16) & 0xfu), a.n_sub));
+        for (int i = 0; i < G; ++i) nne[i] = 0;
+        unsigned rows_q = 0;
+        for (int base = 0; base < U0; base += 32) {
+            const int u = base + lane;
+            TileEntry e{};
+            float act[4] = {0.f, 0.f, 0.f, 0.f}, def[4] = {0.f, 0.f, 0.f, 0.f};
+            bool isa = false;
+            if (u < U0) {
+                e = a.entries[(int64_t)g * a.umax + u];
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    if (e.mult[i] && s_qi[i] >= 0) {
+                        if ((dm[i] >> e.pos[i]) & 1u) def[i] = (float)e.mult[i];
+                        else { act[i] = (float)e.mult[i]; isa = true; if (u < Ur0) rows_q |= 1u << i; }
+                    }
+                }
+            }
+            const unsigned ma = __ballot_sync(0xffffffffu, isa);
+            const unsigned lt = (1u << lane) - 1;
+            if (isa) {
+                const int p = na + __popc(ma & lt);
+                ent[p] = e;
+                s_base[p] = a.row_ptr[e.term];
+                s_fm[p] = make_float4(act[0], act[1], act[2], act[3]);
+                s_skiprow[p] = (uint32_t)e.slot * (uint32_t)(a.n_sub + 1);      // row terms: slot = row index (unused here)
+            }
+#pragma unroll
+            for (int i = 0; i < G; ++i) {                                        // per-query lists of deferred terms
+                const unsigned md = __ballot_sync(0xffffffffu, def[i] != 0.f);
+                if (def[i] != 0.f) {
+                    const int p = nne[i] + __popc(md & lt);
+                    if (p < NE_MAX) s_ne[i * NE_MAX + p] = NeEntry{(int32_t)a.row_slot[e.term], def[i]};
+                }
+                nne[i] += __popc(md);
+            }
+            ur += __popc(ma & __ballot_sync(0xffffffffu, u < Ur0));
+            ud += __popc(ma & __ballot_sync(0xffffffffu, u < Ud0));
+            na += __popc(ma);
+        }
+        rows_q = __reduce_or_sync(0xffffffffu, rows_q);
+        if (lane == 0) { s_cnt[0] = ur; s_cnt[1] = ud; s_cnt[2] = na; s_cnt[3] = (int)rows_q; }
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+            if (lane == 0) s_nne[i] = min(nne[i], NE_MAX);
+    }
+    __syncthreads();                                   // the only block barrier: from here on the warps run independently
+    const int Ur = s_cnt[0], Ud = s_cnt[1], U = s_cnt[2];
+    const unsigned rows_q = (unsigned)s_cnt[3];
+    uint2* s_bnd = s_bnd_all + w * a.umax;
+    uint16_t* s_list = s_list_all + w * LIST_CAP;
+
+    // slice bounds of this warp's sub-range: lane covers entries lane, lane+32, ...; fetched one tile ahead
+    constexpr int NR = (TILE_QT * G + 31) / 32;
+    uint32_t nlo[NR], nhi[NR];
+    auto load_bounds = [&](int sub) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int u = lane + 32 * r;
+            nlo[r] = nhi[r] = 0;
+            if (u >= Ur && u < U) {
+                const uint32_t* sk = a.skip + s_skiprow[u] + sub;
+                nlo[r] = __ldg(sk);
+                nhi[r] = __ldg(sk + 1);
+            }
+        }
     };
     auto store_bounds = [&]() {
 #pragma unroll
-        for (int k = 0; k < NB; ++k)
-            if (bsel[k] >> 31) s_bnd[threadIdx.x + k * TILE_W * 32] = nb[k];
+        for (int r = 0; r < NR; ++r) {
+            const int u = lane + 32 * r;
+            if (u < U) s_bnd[u] = make_uint2(nlo[r], nhi[r]);     // row terms keep empty slices
+        }
     };
-    load_bounds(tile_first);
-    store_bounds();
-    __syncthreads();
+    if (tile_first * TILE_W + w < a.n_sub) load_bounds(tile_first * TILE_W + w);
 #pragma unroll 1
     for (int tile = tile_first; tile < tile_last; ++tile) {
-    const int sub0 = tile * TILE_W;
-    if (tile + 1 < tile_last) load_bounds(tile + 1);                  // in flight during this tile
-    {   // each warp initialises its own accumulator rows: zero + the weights of the dense-row terms of each
+    const int sub = tile * TILE_W + w;
+    if (sub >= a.n_sub) break;                                        // warp-uniform; the later tiles are out of range too
+    store_bounds();
+    if (tile + 1 < tile_last && sub + TILE_W < a.n_sub) load_bounds(sub + TILE_W);     // in flight during this tile
+    // thresholds of this tile (a stale, lower value is always valid); t1: partial scores below it cannot reach thr.
+    // Queries that are scanned anyway (streamed rows / no threshold yet) never push: their t1 is +inf in shared memory.
+    if (lane < G) {
+        const int qi = s_qi[lane];
+        const float th = qi >= 0 ? __ldcg(a.thr + qi) : 0.f;
+        const float t = th * (1.f - kBandRel) * (1.f - kBandRel) - s_neub[lane];
+        const bool scan = ((rows_q >> lane) & 1u) || !(t > 0.f);
+        s_thq[w][lane] = th;
+        s_t1[w][lane] = (scan || qi < 0) ? CUDART_INF_F : t;
+    }
+    if (lane == 0) s_lcnt[w] = 0;
+    __syncwarp();
+    float t1[G];
+    unsigned scan_q = 0;
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+        t1[q] = s_t1[w][q];
+        if (t1[q] == CUDART_INF_F && s_qi[q] >= 0) scan_q |= 1u << q;
+    }
+    const uint32_t doc0 = (uint32_t)sub << TILE_SHIFT;
+    float* my = acc + w * TILE_S;                       // + q * TILE_W * TILE_S per query
+    constexpr int ROW = TILE_W * TILE_S;
+    auto push = [&](uint32_t q, uint32_t idx) {          // record a crossing (rare)
+        const int p = atomicAdd(&s_lcnt[w], 1);
+        if (p < LIST_CAP) s_list[p] = (uint16_t)((q << TILE_SHIFT) | idx);
+    };
+    {   // each warp initialises its own accumulator rows: zero + the weights of the streamed dense-row terms of each
         // query (terms present in >= ~20% of the docs are stored as plain fp32 rows, 0 where absent), 4 docs per lane
-        const uint32_t d0 = (uint32_t)(sub0 + w) << TILE_SHIFT;
 #pragma unroll 1
         for (int half = 0; half < TILE_S / 256; ++half) {       // 256 docs per pass: 2 x (4 docs per lane)
             float4 v[G][2];
 #pragma unroll
             for (int q = 0; q < G; ++q) v[q][0] = v[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int64_t off = (int64_t)d0 + half * 256 + lane * 4;
-            if (sub0 + w < a.n_sub) {
-                for (int u0 = 0; u0 < Ur; u0 += 2) {             // two rows x two segments = 4 loads in flight
-                    float4 d[2][2];
-                    float ff[2][4];
+            const int64_t off = (int64_t)doc0 + half * 256 + lane * 4;
+            for (int u0 = 0; u0 < Ur; u0 += 2) {             // two rows x two segments = 4 loads in flight
+                float4 d[2][2];
+                float ff[2][4];
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int u = min(u0 + k, Ur - 1);
-                        const float* row = a.rows + (int64_t)ent[u].slot * a.n_pad + off;
-                        d[k][0] = __ldg(reinterpret_cast<const float4*>(row));
-                        d[k][1] = __ldg(reinterpret_cast<const float4*>(row + 128));
-                        const float4 f4 = u0 + k < Ur ? s_fm[u] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        ff[k][0] = f4.x; ff[k][1] = f4.y; ff[k][2] = f4.z; ff[k][3] = f4.w;
-                    }
+                for (int k = 0; k < 2; ++k) {
+                    const int u = min(u0 + k, Ur - 1);
+                    const float* row = a.rows + (int64_t)ent[u].slot * a.n_pad + off;
+                    d[k][0] = __ldg(reinterpret_cast<const float4*>(row));
+                    d[k][1] = __ldg(reinterpret_cast<const float4*>(row + 128));
+                    const float4 f4 = u0 + k < Ur ? s_fm[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    ff[k][0] = f4.x; ff[k][1] = f4.y; ff[k][2] = f4.z; ff[k][3] = f4.w;
+                }
 #pragma unroll
-                    for (int k = 0; k < 2; ++k)
+                for (int k = 0; k < 2; ++k)
 #pragma unroll
-                        for (int q = 0; q < G; ++q) {
-                            if (ff[k][q] != 0.f) {               // warp-uniform
+                    for (int q = 0; q < G; ++q) {
+                        if (ff[k][q] != 0.f) {               // warp-uniform
 #pragma unroll
-                                for (int s = 0; s < 2; ++s) {
-                                    v[q][s].x = fmaf(d[k][s].x, ff[k][q], v[q][s].x);
-                                    v[q][s].y = fmaf(d[k][s].y, ff[k][q], v[q][s].y);
-                                    v[q][s].z = fmaf(d[k][s].z, ff[k][q], v[q][s].z);
-                                    v[q][s].w = fmaf(d[k][s].w, ff[k][q], v[q][s].w);
-                                }
+                            for (int s = 0; s < 2; ++s) {
+                                v[q][s].x = fmaf(d[k][s].x, ff[k][q], v[q][s].x);
+                                v[q][s].y = fmaf(d[k][s].y, ff[k][q], v[q][s].y);
+                                v[q][s].z = fmaf(d[k][s].z, ff[k][q], v[q][s].z);
+                                v[q][s].w = fmaf(d[k][s].w, ff[k][q], v[q][s].w);
                             }
                         }
-                }
+                    }
             }
 #pragma unroll
             for (int q = 0; q < G; ++q) {
@@ -416,26 +535,21 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
         }
     }
     __syncwarp();
-    const int sub = sub0 + w;
-    if (sub < a.n_sub) {
-    const uint32_t doc0 = (uint32_t)sub << TILE_SHIFT;
-    float* my = acc + w * TILE_S;                       // + q * TILE_W * TILE_S per query
 
-    constexpr int ROW = TILE_W * TILE_S;
-    // Phase A - sparse slices (< TILE_DENSE_MIN postings of a term in this sub-range).  Walking them
-    // term by term would waste the warp (most (term, sub-range) pairs hold 0-4 postings), so the
+    // Phase A - sparse slices (< TILE_DENSE_MIN postings of a term in this sub-range on average).  Walking them
+    // term by term would waste the warp (most (term, sub-range) pairs hold 0-8 postings), so the
     // slices of 32 union terms at a time are concatenated: a warp-scan of the slice lengths gives every
     // slice its offset, then lane j takes element j of the concatenation (owner found by a shuffle
     // binary search).  Lanes of one instruction may now carry the same doc through different terms;
-    // __match_any_sync serialises exactly those (shared float atomics are a CAS loop on sm_100).
-    // Dense slices are only marked here.
+    // __match_any_sync finds exactly those (shared float atomics are a CAS loop on sm_100).
 #pragma unroll 1
     for (int r0 = Ud; r0 < U; r0 += 32) {
         const int u = r0 + lane;
-        uint32_t lo = 0, n = 0, qmask = 0;
+        uint32_t n = 0, qmask = 0, pidx = 0;
         if (u < U) {
-            lo = s_bnd[u * (TILE_W + 1) + w];
-            n = s_bnd[u * (TILE_W + 1) + w + 1] - lo;
+            const uint2 bd = s_bnd[u];
+            n = bd.y - bd.x;
+            pidx = (uint32_t)s_base[u] + bd.x;                  // posting index of the slice (nnz < 2^32)
             const float4 f4 = s_fm[u];
             qmask = (f4.x != 0.f ? 1u : 0u) | (f4.y != 0.f ? 2u : 0u) | (f4.z != 0.f ? 4u : 0u) | (f4.w != 0.f ? 8u : 0u);
         }
@@ -448,6 +562,8 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
             if (lane >= o) incl += t2;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t start = incl - ns;
+        const uint32_t pcm = pc | (qmask << 8);
         for (uint32_t j0 = 0; j0 < total; j0 += 32) {
             const uint32_t j = j0 + lane;
             int own = 0;                                        // owner = first lane whose inclusive prefix exceeds j
@@ -458,37 +574,50 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
             }
             const bool valid = j < total;
             own = valid ? own : 0;
-            const uint32_t o_incl = __shfl_sync(0xffffffffu, incl, own);
-            const uint32_t o_ns = __shfl_sync(0xffffffffu, ns, own);
-            const uint32_t o_lo = __shfl_sync(0xffffffffu, lo, own);
-            const uint32_t o_pc = __shfl_sync(0xffffffffu, pc, own);
-            uint32_t o_mask = __shfl_sync(0xffffffffu, qmask, own);
-            const int ou = r0 + own;
-            uint32_t addr = 0;
+            const uint32_t o_start = __shfl_sync(0xffffffffu, start, own);
+            const uint32_t o_pidx = __shfl_sync(0xffffffffu, pidx, own);
+            const uint32_t o_pcm = __shfl_sync(0xffffffffu, pcm, own);
+            uint32_t addr = 0x80000000u | (uint32_t)lane;      // idle lanes: distinct dummy addresses
             float wt = 0.f;
+            uint32_t q = 0, idx = 0;
             if (valid) {
-                const uint32_t e = j - (o_incl - o_ns);        // element inside the owner's slice
-                const uint32_t idx = o_pc == 1 ? e : e / o_pc;
-                uint32_t k = o_pc == 1 ? 0u : e - idx * o_pc;   // k-th query of the term
+                const uint32_t e = j - o_start;                 // element inside the owner's slice
+                const uint32_t o_pc = o_pcm & 0xffu;
+                uint32_t o_mask = o_pcm >> 8;
+                const uint32_t pi = o_pc == 1 ? e : e / o_pc;
+                uint32_t k = o_pc == 1 ? 0u : e - pi * o_pc;    // k-th query of the term
                 while (k--) o_mask &= o_mask - 1;
-                const int q = __ffs(o_mask) - 1;
-                const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.post) + s_base[ou] + o_lo + idx);
-                addr = (uint32_t)q * ROW + (v.x - doc0);
-                wt = __uint_as_float(v.y) * reinterpret_cast<const float*>(s_fm + ou)[q];
+                q = __ffs(o_mask) - 1;
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.post) + o_pidx + pi);
+                idx = v.x - doc0;
+                addr = q * ROW + idx;
+                wt = __uint_as_float(v.y);
+                if (a.has_mult) wt *= reinterpret_cast<const float*>(s_fm + r0 + own)[q];
             }
+            const float tq = s_t1[w][q];
             // lanes that target the same accumulator (same doc and query through different terms) take turns
-            bool todo = valid;
-            while (true) {
-                const unsigned pend = __ballot_sync(0xffffffffu, todo);
-                if (!pend) break;
-                if (todo) {
-                    const unsigned peers = __match_any_sync(pend, addr);
-                    if ((peers & ((1u << lane) - 1)) == 0) {
-                        my[addr] += wt;
-                        todo = false;
-                    }
+            const unsigned peers = __match_any_sync(0xffffffffu, addr);
+            const bool first = (peers & ((1u << lane) - 1)) == 0;
+            if (__all_sync(0xffffffffu, first)) {
+                if (valid) {
+                    const float nv = my[addr] + wt;
+                    my[addr] = nv;
+                    if (nv >= tq) push(q, idx);
                 }
                 __syncwarp();
+            } else {
+                unsigned rest = peers;                          // lowest remaining lane of each peer group goes next
+                for (int round = 0; round < 32; ++round) {
+                    const bool go = valid && (rest & ((1u << lane) - 1)) == 0 && ((rest >> lane) & 1u);
+                    if (go) {
+                        const float nv = my[addr] + wt;
+                        my[addr] = nv;
+                        if (nv >= tq) push(q, idx);
+                    }
+                    __syncwarp();
+                    rest &= rest - 1;                           // every group drops its lowest remaining lane
+                    if (!__any_sync(0xffffffffu, valid && ((rest >> lane) & 1u))) break;
+                }
             }
         }
     }
@@ -497,8 +626,13 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
     // postings (4 per lane, coalesced 8-byte words) are in flight while the current ones are added.
     // Inside a chunk all docs are distinct (one term), so the read-modify-writes of a lane are
     // independent: all LDS first, then the adds, then all STS.  No atomics.
+    if (Ur < Ud) {
     auto next_dense = [&](int u) {      // first dense entry >= u with a non-empty slice here (Ud when none)
-        while (u < Ud && s_bnd[u * (TILE_W + 1) + w] >= s_bnd[u * (TILE_W + 1) + w + 1]) ++u;
+        while (u < Ud) {
+            const uint2 bd = s_bnd[u];
+            if (bd.x < bd.y) break;
+            ++u;
+        }
         return u;
     };
     const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
@@ -509,8 +643,9 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
     float fm[G];
     unsigned mask = 0;
     if (u < Ud) {
-        start = s_bnd[u * (TILE_W + 1) + w];
-        hi = s_bnd[u * (TILE_W + 1) + w + 1];
+        const uint2 bd = s_bnd[u];
+        start = bd.x;
+        hi = bd.y;
         p = reinterpret_cast<const uint2*>(a.post) + s_base[u];
 #pragma unroll
         for (int x = 0; x < 4; ++x)
@@ -532,8 +667,9 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
             nu = next_dense(u + 1);
             nstart = nhi = 0;
             if (nu < Ud) {
-                nstart = s_bnd[nu * (TILE_W + 1) + w];
-                nhi = s_bnd[nu * (TILE_W + 1) + w + 1];
+                const uint2 bd = s_bnd[nu];
+                nstart = bd.x;
+                nhi = bd.y;
                 np = reinterpret_cast<const uint2*>(a.post) + s_base[nu];
             }
         }
@@ -557,8 +693,13 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
                 for (int x = 0; x < 4; ++x)
                     if (ok[x]) r[x] = lds_f32(ad[x] + q * ROWB);
 #pragma unroll
-                for (int x = 0; x < 4; ++x)                // fmaf(w, 1.0f, acc) == acc + w exactly
-                    if (ok[x]) sts_f32(ad[x] + q * ROWB, fmaf(__uint_as_float(cur[x].y), fm[q], r[x]));
+                for (int x = 0; x < 4; ++x) {              // fmaf(w, 1.0f, acc) == acc + w exactly
+                    if (ok[x]) {
+                        const float nv = fmaf(__uint_as_float(cur[x].y), fm[q], r[x]);
+                        sts_f32(ad[x] + q * ROWB, nv);
+                        if (nv >= t1[q]) push(q, cur[x].x - doc0);
+                    }
+                }
             }
         }
         __syncwarp();
@@ -576,6 +717,7 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
         }
         u = nu; start = nstart; hi = nhi; p = np;
     }
+    }
     // cold postings of this (tile, group) bucket that fall in this warp's sub-range
     if (a.cold_off) {
         const int64_t b = (int64_t)tile * a.n_groups + g;
@@ -583,30 +725,99 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
         for (uint32_t i = c0 + lane; i < c1; i += 32) {
             const ColdEntry ce = a.cold[i];
             const uint32_t l = ce.key & ((1u << TILE_DOCS_SHIFT) - 1), q = ce.key >> TILE_DOCS_SHIFT;
-            if ((l >> TILE_SHIFT) == (uint32_t)w) atomicAdd(acc + (q * TILE_W + w) * TILE_S + (l & (TILE_S - 1)), ce.w);
+            if ((l >> TILE_SHIFT) == (uint32_t)w) {
+                const uint32_t idx = l & (TILE_S - 1);
+                const float nv = atomicAdd(acc + (q * TILE_W + w) * TILE_S + idx, ce.w) + ce.w;
+                if (nv >= s_t1[w][q]) push(q, idx);
+            }
         }
-        __syncwarp();
     }
+    __syncwarp();
 
-    // epilogue: threshold filter per query of the group
-    float thq[G];
+    // crossing list: complete (deferred terms by look-up row) and filter exactly the listed docs, one per lane
+    const int n_list = s_lcnt[w];
+    if (n_list > LIST_CAP) {
+        scan_q = (1u << G) - 1;                                        // overflow: scan every query's sub-range instead
+    } else {
+        for (int i0 = 0; i0 < n_list; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < n_list) {
+                const uint32_t en = s_list[i];
+                const uint32_t q = en >> TILE_SHIFT, idx = en & (TILE_S - 1);
+                // a doc is listed once per update at or above t1: the first taker marks the accumulator
+                float full = atomicExch(my + q * ROW + idx, -1.f);
+                if (full > 0.f) {
+                    const int nne = s_nne[q];
+                    const NeEntry* ne = s_ne + q * NE_MAX;
+                    const float* col = a.rows + (doc0 + idx);
+                    for (int x0 = 0; x0 < nne; x0 += 4) {
+                        float wv[4], mm[4];
 #pragma unroll
-    for (int q = 0; q < G; ++q) thq[q] = s_qi[q] >= 0 ? __ldcg(a.thr + s_qi[q]) : 0.f;     // all thresholds in flight at once
+                        for (int x = 0; x < 4; ++x) {
+                            const NeEntry e2 = ne[min(x0 + x, nne - 1)];
+                            mm[x] = x0 + x < nne ? e2.mult : 0.f;
+                            wv[x] = __ldg(col + (int64_t)e2.row * a.n_pad);
+                        }
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) full = fmaf(wv[x], mm[x], full);
+                    }
+                    if (full >= s_thq[w][q] * (1.f - kBandRel)) {
+                        const int qi = s_qi[q];
+                        const int pos = atomicAdd(a.cand_cnt + qi, 1);
+                        if (pos < a.cap) {
+                            a.cand[(int64_t)qi * a.cap + pos] = (int32_t)(doc0 + idx);
+                            a.cand_h[(int64_t)qi * a.cap + pos] = full;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+
+    // scan epilogue: threshold filter over all 512 accumulators of a query (streamed rows, no threshold yet, overflow)
 #pragma unroll 1
     for (int q = 0; q < G; ++q) {
         const int qi = s_qi[q];
-        if (qi < 0) continue;
+        if (qi < 0 || !((scan_q >> q) & 1u)) continue;
+        float* myq = my + q * ROW;
+        float th = s_thq[w][q];
+        const float t1q = th * (1.f - kBandRel) * (1.f - kBandRel) - s_neub[q];
         float v[TILE_S / 32];                                   // v[4*s + e] = doc s*128 + lane*4 + e
         float mx = 0.f;
 #pragma unroll
         for (int s = 0; s < TILE_S / 128; ++s) {
-            const float4 f = reinterpret_cast<const float4*>(my + q * TILE_W * TILE_S)[s * 32 + lane];
+            const float4 f = reinterpret_cast<const float4*>(myq)[s * 32 + lane];
             v[4 * s + 0] = f.x; v[4 * s + 1] = f.y; v[4 * s + 2] = f.z; v[4 * s + 3] = f.w;
             mx = fmaxf(fmaxf(mx, fmaxf(f.x, f.y)), fmaxf(f.z, f.w));
         }
-        float th = thq[q];
+        if (!__any_sync(0xffffffffu, mx >= t1q && mx > 0.f)) continue;        // nothing can reach the threshold here
         float lo_thr = th * (1.f - kBandRel);
-        if (!__any_sync(0xffffffffu, mx >= lo_thr && mx > 0.f)) continue;     // nothing above the threshold here
+        const int nne = s_nne[q];
+        if (nne > 0) {
+            // (overflow path) complete the partial scores that may still reach the threshold, in place
+            const NeEntry* ne = s_ne + q * NE_MAX;
+            unsigned pm = 0;
+#pragma unroll
+            for (int j = 0; j < TILE_S / 32; ++j) pm |= (v[j] >= t1q && v[j] > 0.f) ? (1u << j) : 0u;
+            while (pm) {
+                const int j = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint32_t idx = (uint32_t)((j >> 2) * 128 + lane * 4 + (j & 3));
+                const float* col = a.rows + (doc0 + idx);
+                float full = myq[idx];
+                for (int i = 0; i < nne; ++i) full = fmaf(__ldg(col + (int64_t)ne[i].row * a.n_pad), ne[i].mult, full);
+                myq[idx] = full;
+            }
+            __syncwarp();
+            mx = 0.f;
+#pragma unroll
+            for (int s = 0; s < TILE_S / 128; ++s) {
+                const float4 f = reinterpret_cast<const float4*>(myq)[s * 32 + lane];
+                v[4 * s + 0] = f.x; v[4 * s + 1] = f.y; v[4 * s + 2] = f.z; v[4 * s + 3] = f.w;
+                mx = fmaxf(fmaxf(mx, fmaxf(f.x, f.y)), fmaxf(f.z, f.w));
+            }
+        }
         int c = 0;
 #pragma unroll
         for (int j = 0; j < TILE_S / 32; ++j) c += (v[j] >= lo_thr && v[j] > 0.f) ? 1 : 0;
@@ -615,7 +826,8 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
         if (tot == 0) continue;
         if (tot >= a.K && a.K <= 32) {
             // K distinct docs (one per lane) score >= the K-th largest lane maximum: a valid lower
-            // bound of the K-th best score of this query over the whole shard
+            // bound of the K-th best score of this query over the whole shard (a lane maximum that is only a
+            // partial score is a lower bound of that doc's score, so the bound stays valid)
             const float srt = warp_sort_desc(mx, lane);
             const float kth = __shfl_sync(0xffffffffu, srt, a.K - 1);
             if (kth > th) {
@@ -649,13 +861,67 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
             }
         }
     }
-    }   // sub < n_sub
-    if (tile + 1 < tile_last) {
-        __syncthreads();                                              // every warp is done with this tile's bounds
-        store_bounds();
-        __syncthreads();
-    }
+    __syncwarp();
     }   // tile loop
+}
+
+// Deferral plan of one query for the next launch (one warp; see k_tile_score): greedily defer the hot terms with the
+// smallest upper bound mult * ub[t] while their sum stays below frac * thr * (1 - band).  Cold terms (no skip table)
+// are never deferred.  ne_ub is rounded up so that "partial + ne_ub < t" really excludes the doc.
+struct PlanArgs {
+    const int32_t* q_off;
+    const int32_t* u_terms;
+    const int32_t* u_mult;
+    const int32_t* u_cnt;
+    const float* ub;
+    const int16_t* row_slot;
+    int n_srows;
+    float frac;
+    uint32_t* defer_mask;
+    float* ne_ub;
+};
+// Only terms with a look-up row can be deferred.  The streamed-row terms (the densest, smallest bounds) go first and
+// all of them or nothing: a query whose accumulators start from rows needs the full epilogue scan anyway.
+__device__ __forceinline__ void make_plan(const PlanArgs& pa, int q, float thr, int lane) {
+    const int32_t off = pa.q_off[q], nu = pa.u_cnt[q];
+    uint32_t mask = 0;
+    float sum = 0.f;
+    if (thr > 0.f && pa.frac > 0.f && nu <= 32) {
+        float v = CUDART_INF_F;
+        bool srow = false;
+        if (lane < nu) {
+            const int32_t t = pa.u_terms[off + lane];
+            const int rs = pa.row_slot[t];
+            if (rs >= 0) { v = pa.ub[t] * (float)pa.u_mult[off + lane]; srow = rs < pa.n_srows; }
+        }
+        const float budget = thr * (1.f - kBandRel) * pa.frac;
+        float ssum = srow ? v : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+        if (ssum < budget) {
+            mask = __ballot_sync(0xffffffffu, srow);
+            sum = ssum;
+            if (srow) v = CUDART_INF_F;
+            for (int it = 0; it < nu; ++it) {
+                float best = v;
+                int who = lane;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+                    if (ob < best || (ob == best && ow < who)) { best = ob; who = ow; }
+                }
+                if (!(sum + best < budget)) break;         // also stops at +inf (nothing deferrable left)
+                sum += best;
+                mask |= 1u << who;
+                if (lane == who) v = CUDART_INF_F;
+            }
+        }
+    }
+    if (lane == 0) {
+        pa.defer_mask[q] = mask;
+        pa.ne_ub[q] = sum * (1.f + 1e-6f);
+    }
 }
 
 // Between chunks: thr[q] = max(thr[q], K-th best fp32 score emitted so far); keep only the candidates
@@ -663,7 +929,8 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
 constexpr int TG_T = 256;
 __global__ void __launch_bounds__(TG_T) k_tighten(float* __restrict__ thr, int32_t* __restrict__ cand_cnt,
                                                   int32_t* __restrict__ prev_cnt, int32_t* __restrict__ cand,
-                                                  float* __restrict__ cand_h, int K, int32_t* __restrict__ overflow) {
+                                                  float* __restrict__ cand_h, int K, int32_t* __restrict__ overflow,
+                                                  PlanArgs pa) {
     __shared__ float s_h[TILE_CAP];
     __shared__ int32_t s_id[TILE_CAP];
     __shared__ int s_keep;
@@ -716,6 +983,7 @@ __global__ void __launch_bounds__(TG_T) k_tighten(float* __restrict__ thr, int32
         cand_cnt[q] = keep;
         prev_cnt[q] = keep;
     }
+    if (threadIdx.x < 32) make_plan(pa, q, th, threadIdx.x);
 }
 
 // The same for long candidate lists (32 < K <= 1024, up to TILE_CAP_BIG entries): the K-th largest score by a 4 x 8-bit
@@ -725,7 +993,7 @@ __global__ void __launch_bounds__(TG_T) k_tighten(float* __restrict__ thr, int32
 __global__ void __launch_bounds__(TG_T) k_tighten_big(float* __restrict__ thr, int32_t* __restrict__ cand_cnt,
                                                       int32_t* __restrict__ prev_cnt, int32_t* __restrict__ cand,
                                                       float* __restrict__ cand_h, int K, int cap,
-                                                      int32_t* __restrict__ overflow) {
+                                                      int32_t* __restrict__ overflow, PlanArgs pa) {
     extern __shared__ __align__(16) unsigned char tb_smem[];
     uint32_t* s_h = reinterpret_cast<uint32_t*>(tb_smem);             // [cap] score bits
     int32_t* s_id = reinterpret_cast<int32_t*>(s_h + cap);            // [cap]
@@ -802,6 +1070,7 @@ __global__ void __launch_bounds__(TG_T) k_tighten_big(float* __restrict__ thr, i
         cand_cnt[q] = kept;
         prev_cnt[q] = kept;
     }
+    if (threadIdx.x < 32) make_plan(pa, q, th, threadIdx.x);
 }
 
 __global__ void k_fused_flags(const int32_t* __restrict__ elig, const int32_t* __restrict__ overflow,
@@ -830,7 +1099,7 @@ __global__ void k_fill_offsets(int64_t* __restrict__ off, int32_t nq, int64_t st
 
 template <int G>
 static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t smem, cudaStream_t st, br_index* ix,
-                        int32_t* prev_cnt, int32_t* overflow) {
+                        int32_t* prev_cnt, int32_t* overflow, const PlanArgs& pa) {
     BR_CUDA(cudaFuncSetAttribute(k_tile_score<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device
     // chunks of doubling size: thresholds learnt on the first 2^c tiles filter the next 2^c
     // first chunk: as many tiles as the candidate buffer certainly holds with thresholds still at zero
@@ -843,14 +1112,15 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
         TileArgs a = a0;
         a.tile0 = t0;
         a.tile_end = t0 + ny;
-        static const int tpb_env = getenv("BR_TILE_TPB") ? atoi(getenv("BR_TILE_TPB")) : 4;
-        a.tpb = ny >= 2 * tpb_env ? std::max(1, tpb_env) : 1;
+        // consecutive tiles per CTA: amortises the CTA prologue in the large launches, keeps the small ones wide
+        a.tpb = 1;
+        while (a.tpb * 2 <= ix->tile_tpb && ny >= 4 * a.tpb) a.tpb *= 2;
         ix->prof_begin(st);
         k_tile_score<G><<<dim3((unsigned)n_groups, (unsigned)((ny + a.tpb - 1) / a.tpb)), TILE_W * 32, smem, st>>>(a);
         BR_CUDA(cudaGetLastError());
         ix->prof_end(st);
-        if (big) k_tighten_big<<<a0.nq, TG_T, 8 * (size_t)a0.cap, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, a0.cap, overflow);
-        else k_tighten<<<a0.nq, TG_T, 0, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, overflow);
+        if (big) k_tighten_big<<<a0.nq, TG_T, 8 * (size_t)a0.cap, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, a0.cap, overflow, pa);
+        else k_tighten<<<a0.nq, TG_T, 0, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, overflow, pa);
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 2;
         t0 += ny;
@@ -860,8 +1130,7 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
 }
 
 bool fused_supported(const br_index* ix, int32_t k, int32_t nq) {
-    static const bool disabled = getenv("BR_DISABLE_FUSED") != nullptr;
-    static const bool no_big = getenv("BR_DISABLE_FUSED_BIGK") != nullptr;
+    const bool disabled = false, no_big = !ix->allow_fused_bigk;
     // 32 < k <= 1024: candidate regions of TILE_CAP_BIG slots per query (16 B each) - bounded to 6 GB of scratch
     const bool k_ok = k <= 32 || (!no_big && k <= 1024 && (int64_t)nq * TILE_CAP_BIG * 16 <= (6LL << 30));
     return !disabled && ix->allow_fused && k_ok && ix->variant != BR_OKAPI_NO_PLUS1 && ix->n_hot > 0 &&
@@ -870,24 +1139,10 @@ bool fused_supported(const br_index* ix, int32_t k, int32_t nq) {
 
 // Fused path over the whole prepared batch.  h_flags[q] != 0 afterwards -> query q must be served by
 // the dense path (not eligible, candidate overflow, or fewer than k docs with a positive score).
-void stage_mark(const char* name, cudaStream_t st) {     // BR_TIMELINE=1: wall-clock per stage (debug)
-    static const bool on = getenv("BR_TIMELINE") != nullptr;
-    static double last = 0;
-    if (!on) return;
-    cudaStreamSynchronize(st);
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
-    fprintf(stderr, "[br timeline] %-14s +%.3f ms\n", name, last == 0 ? 0.0 : now - last);
-    last = now;
-}
-
 int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t nq, int32_t k, int dedup,
                int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st,
                std::vector<int32_t>* h_flags) {
-    stage_mark("enter", st);
     int G = nq >= 4 * kNumSMs ? 4 : (nq >= 2 * kNumSMs ? 2 : 1);
-    if (const char* e = getenv("BR_TILE_G")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) G = v; }
     if (ix->tile_g) G = ix->tile_g;
     if (G > 4) G = 4;
     const int n_groups = (nq + G - 1) / G, umax = G * TILE_QT;
@@ -900,6 +1155,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     const size_t Q = (size_t)nq + 2;
     const size_t o_ent = carve(sizeof(TileEntry) * (size_t)n_groups * umax), o_ne = carve(4 * (size_t)n_groups),
                  o_el = carve(4 * Q), o_thr = carve(4 * Q), o_cnt = carve(4 * Q), o_prev = carve(4 * Q), o_ovf = carve(4 * Q),
+                 o_dm = carve(4 * Q), o_nu = carve(4 * Q),
                  o_off = carve(8 * Q), o_fl = carve(4 * Q), o_oc = carve(4 * Q), o_ct = carve(16),
                  o_bc = carve(4 * (size_t)(n_buckets + 1)), o_bo = carve(4 * (size_t)(n_buckets + 1)),
                  o_cur = carve(4 * (size_t)(n_buckets + 1)), o_part = carve(4 * (size_t)(n_scan_blocks + 1)),
@@ -915,6 +1171,8 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     int32_t* cand_cnt = (int32_t*)(p + o_cnt);
     int32_t* prev_cnt = (int32_t*)(p + o_prev);
     int32_t* overflow = (int32_t*)(p + o_ovf);
+    uint32_t* defer_mask = (uint32_t*)(p + o_dm);
+    float* ne_ub = (float*)(p + o_nu);
     int64_t* cand_off = (int64_t*)(p + o_off);
     int32_t* flags = (int32_t*)(p + o_fl);
     int32_t* cnt_tmp = out_counts ? out_counts : (int32_t*)(p + o_oc);
@@ -945,11 +1203,11 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 2;
     }
-    // one memset covers thr / cand_cnt / prev_cnt / overflow (contiguous carve)
+    // one memset covers thr / cand_cnt / prev_cnt / overflow / defer_mask / ne_ub (contiguous carve)
     BR_CUDA(cudaMemsetAsync(p + o_thr, 0, o_off - o_thr, st));
     BR_CUDA(cudaMemsetAsync(cold_total, 0, 16, st));
     k_tile_prep<<<(n_groups + 3) / 4, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, nq, G, umax, entries, n_entries,
-                                                    elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)TILE_DENSE_MIN) >> TILE_SHIFT), perm, ix->row_slot);
+                                                    elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)ix->tile_dense_min) >> TILE_SHIFT), perm, ix->row_slot, ix->n_srows);
     BR_CUDA(cudaGetLastError());
     k_fill_offsets<<<blocks_for(nq + 1, 256), 256, 0, st>>>(cand_off, nq, cap);
     BR_CUDA(cudaGetLastError());
@@ -957,7 +1215,6 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     BR_CUDA(cudaMemcpyAsync(&h_cold, cold_total, sizeof(h_cold), cudaMemcpyDeviceToHost, st));
     BR_CUDA(cudaStreamSynchronize(st));
     ix->stats.kernel_launches += 2;
-    stage_mark("tile_prep", st);
     BR_REQUIRE(h_cold < (1ull << 32), BR_ERR_UNSUPPORTED, "br_topk_batch: more than 2^32 cold postings in one batch");
 
     const ColdEntry* cold = nullptr;
@@ -983,19 +1240,18 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
         cold = d_cold;
         cold_off = b_off;
     }
-
-    stage_mark("cold_sort", st);
     TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
-               cold_off, cold, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, cap, (int)k, 0, 0, 1, dedup ? 0 : 1, perm};
+               cold_off, cold, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, cap, (int)k, 0, 0, 1, dedup ? 0 : 1, perm, defer_mask, ne_ub, ix->row_slot};
+    const PlanArgs pa{q_off, pv.u_terms, pv.u_mult, pv.u_cnt, ix->ub, ix->row_slot, ix->n_srows, (float)ix->defer_pm * 1e-3f, defer_mask, ne_ub};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
-                                                                            sizeof(uint32_t) * (TILE_W + 1) + sizeof(float4) + sizeof(uint32_t));
+                                                                            sizeof(float4) + sizeof(uint32_t) + sizeof(uint2) * TILE_W) +
+                        sizeof(NeEntry) * G * NE_MAX + sizeof(uint16_t) * TILE_W * LIST_CAP;
     switch (G) {
-        case 1: BR_TRY(launch_tiles<1>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
-        case 2: BR_TRY(launch_tiles<2>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
-        case 4: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
-        default: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow)); break;
+        case 1: BR_TRY(launch_tiles<1>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)); break;
+        case 2: BR_TRY(launch_tiles<2>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)); break;
+        case 4: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)); break;
+        default: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)); break;
     }
-    stage_mark("tiles", st);
     BR_TRY(launch_rescore_heads(ix, q_off, pv, dedup, nq, cap, cand_cnt, cand, cand_sc, st));
     BR_TRY(launch_final_select(cand, cand_sc, cand_off, 0, nq, k, positive_only, out_ids, out_scores, cnt_tmp, st, cand_cnt));
     const int32_t need = (int32_t)std::min<int64_t>(k, ix->n_docs);
@@ -1005,7 +1261,6 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     h_flags->resize((size_t)nq);
     BR_CUDA(cudaMemcpyAsync(h_flags->data(), flags, 4 * (size_t)nq, cudaMemcpyDeviceToHost, st));
     BR_CUDA(cudaStreamSynchronize(st));
-    stage_mark("tail", st);
     return BR_OK;
 }
 

@@ -73,16 +73,46 @@ def test_c3_bm25_top1000_then_cosine(c2):
         assert set(ids[i].cpu().tolist()) <= set(oi[i].tolist())
 
 
-def test_c4_slice_properties():
+@pytest.fixture(scope="module")
+def c4_slice():
+    from document_retrieval_b200 import BM25
+    do, tk = synth.make_corpus_torch(1_000_000, 1_000_000, 60, "cuda", seed=5)
+    qo, qt, _ = synth.make_queries_torch(do, tk, 2_000, 1_000_000, seed=6)
+    return do, tk, qo, qt, BM25.from_token_ids(do, tk, 1_000_000)
+
+
+def test_c4_slice_against_the_oracle(c4_slice):
+    """1M-doc slice of the C4 shape, 2,000 queries: top-10 ids and float64 scores identical to the plain-C oracle,
+    whatever the deferral budget of the tiled scorer (0 = every term streamed, 1000 = the most aggressive plan)."""
+    do, tk, qo, qt, m = c4_slice
+    co = COracle(do.cpu().numpy(), tk.cpu().numpy(), 1_000_000)
+    oi, osc, _ = co.topk_batch(qt, qo, 10)
+    for pm in (700, 0, 1000, 400):
+        m.set_option("defer_pm", pm)
+        ids, sc = m.retrieve_top_n_batch((qt, qo), 10)
+        assert m.query_stats()["queries_fused"] > 1900
+        assert np.array_equal(ids.cpu().numpy(), oi), f"defer_pm={pm}"
+        assert np.array_equal(sc.cpu().numpy(), osc), f"defer_pm={pm}"
+    m.set_option("defer_pm", 700)
+    # duplicates counted (team_run1.py:183) and the top-100 of score_documents_for_query through the large-k tiled path
+    o2 = COracle(do.cpu().numpy(), tk.cpu().numpy(), 1_000_000, variant="okapi")
+    from document_retrieval_b200 import BM25
+    m2 = BM25.from_token_ids(do, tk, 1_000_000, variant="okapi", dedup_query=False)
+    n300 = int(qo[300])
+    oi2, osc2, oc2 = o2.topk_batch(qt[:n300], qo[:301], 100, dedup=False, positive_only=True)
+    ids2, sc2, cnt2 = m2.retrieve_top_n_batch((qt[:n300], qo[:301]), 100, positive_only=True, return_counts=True)
+    assert np.array_equal(cnt2.cpu().numpy(), oc2)
+    assert np.array_equal(ids2.cpu().numpy(), oi2) and np.array_equal(sc2.cpu().numpy(), osc2)
+
+
+def test_c4_slice_properties(c4_slice):
     """1M-doc slice of the C4 shape: fused == dense, 4 fake shards == single index, save/load round trip."""
     import os
     import tempfile
     from document_retrieval_b200 import BM25
     from document_retrieval_b200.sharded import merge_topk_cuda, shard_bounds
-    do, tk = synth.make_corpus_torch(1_000_000, 1_000_000, 60, "cuda", seed=5)
-    qo, qt, _ = synth.make_queries_torch(do, tk, 2_000, 1_000_000, seed=6)
+    do, tk, qo, qt, m = c4_slice
     q = (qt, qo)
-    m = BM25.from_token_ids(do, tk, 1_000_000)
     ids_f, sc_f = m.retrieve_top_n_batch(q, 10)
     assert m.query_stats()["queries_fused"] > 1900
     m.set_option("fused", 0)
