@@ -136,6 +136,7 @@ struct br_index {
 
     bool allow_fused = true, allow_fused_bigk = true;
     int tile_g = 0;
+    bool seed_thr = true;           // threshold seeding before the first launch of the tiled scorer
     int defer_pm = 700;             // MaxScore deferral budget of the tiled scorer, per mille of the threshold (0 = off)
     int tile_tpb = 8;               // consecutive tiles per CTA in the large launches
     int tile_dense_min = 16;        // average postings of a term per 512-doc sub-range from which its slices are walked

@@ -356,12 +356,17 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
     NeEntry* s_ne = reinterpret_cast<NeEntry*>(s_skiprow + a.umax);                      // [G][NE_MAX] deferred terms per query
     uint2* s_bnd_all = reinterpret_cast<uint2*>(s_ne + G * NE_MAX);                      // [W][umax] slice (lo, hi) per warp
     uint16_t* s_list_all = reinterpret_cast<uint16_t*>(s_bnd_all + TILE_W * a.umax);     // [W][LIST_CAP]
-    __shared__ int s_qi[8];                                                              // query of each group slot (-1: none)
-    __shared__ int s_cnt[4];                                                             // Ur, Ud, U (streamed), rows mask
-    __shared__ int s_nne[4];                                                             // deferred terms of each query
-    __shared__ float s_neub[4];
-    __shared__ float s_thq[TILE_W][4], s_t1[TILE_W][4];                                  // per-warp thresholds of the tile
-    __shared__ int s_lcnt[TILE_W];
+    // small per-CTA / per-warp state, carved from the same buffer (static __shared__ arrays would have their window
+    // addresses rematerialised all over the kernel)
+    int* s_qi = reinterpret_cast<int*>(s_list_all + TILE_W * LIST_CAP);                  // [4] query of each group slot (-1: none)
+    int* s_cnt = s_qi + 4;                                                               // Ur, Ud, U (streamed), rows mask
+    int* s_nne = s_cnt + 4;                                                              // [4] deferred terms of each query (padded to x4)
+    float* s_neub = reinterpret_cast<float*>(s_nne + 4);                                 // [4]
+    float* s_thq_all = s_neub + 4;                                                       // [W][4] per-warp thresholds of the tile
+    float* s_t1_all = s_thq_all + TILE_W * 4;                                            // [W][4]
+    int* s_lcnt_all = reinterpret_cast<int*>(s_t1_all + TILE_W * 4);                     // [W]
+    int* s_nql = s_lcnt_all + TILE_W;                                                    // [4] sparse streamed terms of each query
+    uint8_t* s_ql = reinterpret_cast<uint8_t*>(s_nql + 4);                               // [G][TILE_QT] their entry indices
 
     const int g = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -383,9 +388,9 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
 #pragma unroll
         for (int i = 0; i < G; ++i) dm[i] = s_qi[i] >= 0 ? a.defer_mask[s_qi[i]] : 0u;
         int na = 0, ur = 0, ud = 0;
-        int nne[G];
+        int nne[G], nql[G];
 #pragma unroll
-        for (int i = 0; i < G; ++i) nne[i] = 0;
+        for (int i = 0; i < G; ++i) nne[i] = nql[i] = 0;
         unsigned rows_q = 0;
         for (int base = 0; base < U0; base += 32) {
             const int u = base + lane;
@@ -404,6 +409,16 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
             }
             const unsigned ma = __ballot_sync(0xffffffffu, isa);
             const unsigned lt = (1u << lane) - 1;
+#pragma unroll
+            for (int i = 0; i < G; ++i) {                                        // per-query lists of streamed sparse terms
+                const bool in = isa && u >= Ud0 && act[i] != 0.f;
+                const unsigned mq = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const int p = nql[i] + __popc(mq & lt);
+                    if (p < TILE_QT) s_ql[i * TILE_QT + p] = (uint8_t)(na + __popc(ma & lt));
+                }
+                nql[i] += __popc(mq);
+            }
             if (isa) {
                 const int p = na + __popc(ma & lt);
                 ent[p] = e;
@@ -427,14 +442,20 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
         rows_q = __reduce_or_sync(0xffffffffu, rows_q);
         if (lane == 0) { s_cnt[0] = ur; s_cnt[1] = ud; s_cnt[2] = na; s_cnt[3] = (int)rows_q; }
 #pragma unroll
-        for (int i = 0; i < G; ++i)
-            if (lane == 0) s_nne[i] = min(nne[i], NE_MAX);
+        for (int i = 0; i < G; ++i) {
+            const int n = min(nne[i], NE_MAX), n4 = (n + 3) & ~3;
+            if (lane >= n && lane < n4) s_ne[i * NE_MAX + lane] = NeEntry{0, 0.f};     // padding: row 0, multiplicity 0
+            if (lane == 0) { s_nne[i] = n4; s_nql[i] = min(nql[i], TILE_QT); }
+        }
     }
     __syncthreads();                                   // the only block barrier: from here on the warps run independently
     const int Ur = s_cnt[0], Ud = s_cnt[1], U = s_cnt[2];
     const unsigned rows_q = (unsigned)s_cnt[3];
     uint2* s_bnd = s_bnd_all + w * a.umax;
     uint16_t* s_list = s_list_all + w * LIST_CAP;
+    float* s_thq = s_thq_all + w * 4;
+    float* s_t1 = s_t1_all + w * 4;
+    int* s_lcnt = s_lcnt_all + w;
 
     // slice bounds of this warp's sub-range: lane covers entries lane, lane+32, ...; fetched one tile ahead
     constexpr int NR = (TILE_QT * G + 31) / 32;
@@ -472,26 +493,33 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
         const float th = qi >= 0 ? __ldcg(a.thr + qi) : 0.f;
         const float t = th * (1.f - kBandRel) * (1.f - kBandRel) - s_neub[lane];
         const bool scan = ((rows_q >> lane) & 1u) || !(t > 0.f);
-        s_thq[w][lane] = th;
-        s_t1[w][lane] = (scan || qi < 0) ? CUDART_INF_F : t;
+        s_thq[lane] = th;
+        s_t1[lane] = (scan || qi < 0) ? CUDART_INF_F : t;
     }
-    if (lane == 0) s_lcnt[w] = 0;
+    if (lane == 0) *s_lcnt = 0;
     __syncwarp();
     float t1[G];
     unsigned scan_q = 0;
 #pragma unroll
     for (int q = 0; q < G; ++q) {
-        t1[q] = s_t1[w][q];
+        t1[q] = s_t1[q];
         if (t1[q] == CUDART_INF_F && s_qi[q] >= 0) scan_q |= 1u << q;
     }
     const uint32_t doc0 = (uint32_t)sub << TILE_SHIFT;
     float* my = acc + w * TILE_S;                       // + q * TILE_W * TILE_S per query
     constexpr int ROW = TILE_W * TILE_S;
     auto push = [&](uint32_t q, uint32_t idx) {          // record a crossing (rare)
-        const int p = atomicAdd(&s_lcnt[w], 1);
+        const int p = atomicAdd(s_lcnt, 1);
         if (p < LIST_CAP) s_list[p] = (uint16_t)((q << TILE_SHIFT) | idx);
     };
-    {   // each warp initialises its own accumulator rows: zero + the weights of the streamed dense-row terms of each
+    if (Ur == 0) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < G; ++q)
+#pragma unroll
+            for (int s4 = 0; s4 < TILE_S / 128; ++s4) reinterpret_cast<float4*>(my + q * ROW)[s4 * 32 + lane] = z;
+    } else {
+        // each warp initialises its own accumulator rows: zero + the weights of the streamed dense-row terms of each
         // query (terms present in >= ~20% of the docs are stored as plain fp32 rows, 0 where absent), 4 docs per lane
 #pragma unroll 1
         for (int half = 0; half < TILE_S / 256; ++half) {       // 256 docs per pass: 2 x (4 docs per lane)
@@ -536,88 +564,60 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
     }
     __syncwarp();
 
-    // Phase A - sparse slices (< TILE_DENSE_MIN postings of a term in this sub-range on average).  Walking them
-    // term by term would waste the warp (most (term, sub-range) pairs hold 0-8 postings), so the
-    // slices of 32 union terms at a time are concatenated: a warp-scan of the slice lengths gives every
-    // slice its offset, then lane j takes element j of the concatenation (owner found by a shuffle
-    // binary search).  Lanes of one instruction may now carry the same doc through different terms;
-    // __match_any_sync finds exactly those (shared float atomics are a CAS loop on sm_100).
+    // Phase A - sparse slices (most (term, sub-range) pairs hold 0-8 postings).  The lanes are split into G groups of
+    // LQ = 32/G, one per query; a group walks the non-empty slices of its own query's terms, one term at a time, LQ
+    // postings per step.  The lanes of a group then touch distinct docs of one term, and different groups different
+    // accumulator rows: no two lanes of an instruction ever meet in one accumulator, so there is nothing to detect,
+    // and neither a prefix scan nor an owner search is needed.  Lane lq of a group first fetches the slice of the
+    // group's lq-th term; the walk then pulls the non-empty ones over by shuffle.
+    {
+        constexpr int LQ = 32 / G;
+        constexpr unsigned GMASK = LQ == 32 ? 0xffffffffu : ((1u << LQ) - 1u);
+        const int qg = lane / LQ, lq = lane % LQ;
+        float* myq = my + qg * ROW;
+        const float tq = s_t1[qg];
+        const int nt = s_nql[qg];
+        int nt_max = nt;
+#pragma unroll
+        for (int o = LQ; o < 32; o <<= 1) nt_max = max(nt_max, __shfl_xor_sync(0xffffffffu, nt_max, o));
 #pragma unroll 1
-    for (int r0 = Ud; r0 < U; r0 += 32) {
-        const int u = r0 + lane;
-        uint32_t n = 0, qmask = 0, pidx = 0;
-        if (u < U) {
-            const uint2 bd = s_bnd[u];
-            n = bd.y - bd.x;
-            pidx = (uint32_t)s_base[u] + bd.x;                  // posting index of the slice (nnz < 2^32)
-            const float4 f4 = s_fm[u];
-            qmask = (f4.x != 0.f ? 1u : 0u) | (f4.y != 0.f ? 2u : 0u) | (f4.z != 0.f ? 4u : 0u) | (f4.w != 0.f ? 8u : 0u);
-        }
-        const uint32_t pc = __popc(qmask);
-        const uint32_t ns = n * pc;                            // one element per (posting, query of the group that has the term)
-        uint32_t incl = ns;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t2 = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t2;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t start = incl - ns;
-        const uint32_t pcm = pc | (qmask << 8);
-        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            int own = 0;                                        // owner = first lane whose inclusive prefix exceeds j
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const uint32_t v = __shfl_sync(0xffffffffu, incl, own + step - 1);
-                if (v <= j) own += step;
+        for (int r0 = 0; r0 < nt_max; r0 += LQ) {
+            uint32_t t_lo = 0, t_hi = 0, t_pb = 0;
+            float t_mu = 1.f;
+            if (r0 + lq < nt) {
+                const int u = s_ql[qg * TILE_QT + r0 + lq];
+                const uint2 bd = s_bnd[u];
+                t_lo = bd.x; t_hi = bd.y;
+                t_pb = (uint32_t)s_base[u];                         // posting index of the term's list (nnz < 2^32)
+                if (a.has_mult) t_mu = reinterpret_cast<const float*>(s_fm + u)[qg];
             }
-            const bool valid = j < total;
-            own = valid ? own : 0;
-            const uint32_t o_start = __shfl_sync(0xffffffffu, start, own);
-            const uint32_t o_pidx = __shfl_sync(0xffffffffu, pidx, own);
-            const uint32_t o_pcm = __shfl_sync(0xffffffffu, pcm, own);
-            uint32_t addr = 0x80000000u | (uint32_t)lane;      // idle lanes: distinct dummy addresses
-            float wt = 0.f;
-            uint32_t q = 0, idx = 0;
-            if (valid) {
-                const uint32_t e = j - o_start;                 // element inside the owner's slice
-                const uint32_t o_pc = o_pcm & 0xffu;
-                uint32_t o_mask = o_pcm >> 8;
-                const uint32_t pi = o_pc == 1 ? e : e / o_pc;
-                uint32_t k = o_pc == 1 ? 0u : e - pi * o_pc;    // k-th query of the term
-                while (k--) o_mask &= o_mask - 1;
-                q = __ffs(o_mask) - 1;
-                const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.post) + o_pidx + pi);
-                idx = v.x - doc0;
-                addr = q * ROW + idx;
-                wt = __uint_as_float(v.y);
-                if (a.has_mult) wt *= reinterpret_cast<const float*>(s_fm + r0 + own)[q];
-            }
-            const float tq = s_t1[w][q];
-            // lanes that target the same accumulator (same doc and query through different terms) take turns
-            const unsigned peers = __match_any_sync(0xffffffffu, addr);
-            const bool first = (peers & ((1u << lane) - 1)) == 0;
-            if (__all_sync(0xffffffffu, first)) {
-                if (valid) {
-                    const float nv = my[addr] + wt;
-                    my[addr] = nv;
-                    if (nv >= tq) push(q, idx);
+            unsigned gm = (__ballot_sync(0xffffffffu, t_lo < t_hi) >> (qg * LQ)) & GMASK;     // non-empty slices of my group
+            uint32_t c = 0, h = 0, pb = 0;
+            float mu = 1.f;
+            bool done = false;
+            while (true) {
+                const bool need = c >= h;                           // group-uniform: current slice exhausted
+                const bool take = need && gm != 0;
+                const int src = qg * LQ + (take ? __ffs(gm) - 1 : lq);
+                const uint32_t n_lo = __shfl_sync(0xffffffffu, t_lo, src);
+                const uint32_t n_hi = __shfl_sync(0xffffffffu, t_hi, src);
+                const uint32_t n_pb = __shfl_sync(0xffffffffu, t_pb, src);
+                if (a.has_mult) { const float n_mu = __shfl_sync(0xffffffffu, t_mu, src); if (take) mu = n_mu; }
+                if (take) { c = n_lo; h = n_hi; pb = n_pb; gm &= gm - 1; }
+                else if (need) done = true;
+                if (__all_sync(0xffffffffu, done)) break;
+                if (!done) {
+                    const uint32_t pos = c + lq;
+                    if (pos < h) {
+                        const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.post) + pb + pos);
+                        const uint32_t idx = v.x - doc0;
+                        const float nv = fmaf(__uint_as_float(v.y), mu, myq[idx]);
+                        myq[idx] = nv;
+                        if (nv >= tq) push(qg, idx);
+                    }
+                    c += LQ;
                 }
                 __syncwarp();
-            } else {
-                unsigned rest = peers;                          // lowest remaining lane of each peer group goes next
-                for (int round = 0; round < 32; ++round) {
-                    const bool go = valid && (rest & ((1u << lane) - 1)) == 0 && ((rest >> lane) & 1u);
-                    if (go) {
-                        const float nv = my[addr] + wt;
-                        my[addr] = nv;
-                        if (nv >= tq) push(q, idx);
-                    }
-                    __syncwarp();
-                    rest &= rest - 1;                           // every group drops its lowest remaining lane
-                    if (!__any_sync(0xffffffffu, valid && ((rest >> lane) & 1u))) break;
-                }
             }
         }
     }
@@ -728,14 +728,14 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
             if ((l >> TILE_SHIFT) == (uint32_t)w) {
                 const uint32_t idx = l & (TILE_S - 1);
                 const float nv = atomicAdd(acc + (q * TILE_W + w) * TILE_S + idx, ce.w) + ce.w;
-                if (nv >= s_t1[w][q]) push(q, idx);
+                if (nv >= s_t1[q]) push(q, idx);
             }
         }
     }
     __syncwarp();
 
     // crossing list: complete (deferred terms by look-up row) and filter exactly the listed docs, one per lane
-    const int n_list = s_lcnt[w];
+    const int n_list = *s_lcnt;
     if (n_list > LIST_CAP) {
         scan_q = (1u << G) - 1;                                        // overflow: scan every query's sub-range instead
     } else {
@@ -750,18 +750,18 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
                     const int nne = s_nne[q];
                     const NeEntry* ne = s_ne + q * NE_MAX;
                     const float* col = a.rows + (doc0 + idx);
-                    for (int x0 = 0; x0 < nne; x0 += 4) {
+                    for (int x0 = 0; x0 < nne; x0 += 4) {          // lists are padded to a multiple of 4
                         float wv[4], mm[4];
 #pragma unroll
                         for (int x = 0; x < 4; ++x) {
-                            const NeEntry e2 = ne[min(x0 + x, nne - 1)];
-                            mm[x] = x0 + x < nne ? e2.mult : 0.f;
+                            const NeEntry e2 = ne[x0 + x];
+                            mm[x] = e2.mult;
                             wv[x] = __ldg(col + (int64_t)e2.row * a.n_pad);
                         }
 #pragma unroll
                         for (int x = 0; x < 4; ++x) full = fmaf(wv[x], mm[x], full);
                     }
-                    if (full >= s_thq[w][q] * (1.f - kBandRel)) {
+                    if (full >= s_thq[q] * (1.f - kBandRel)) {
                         const int qi = s_qi[q];
                         const int pos = atomicAdd(a.cand_cnt + qi, 1);
                         if (pos < a.cap) {
@@ -776,12 +776,13 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
     __syncwarp();
 
     // scan epilogue: threshold filter over all 512 accumulators of a query (streamed rows, no threshold yet, overflow)
+    if (scan_q)
 #pragma unroll 1
     for (int q = 0; q < G; ++q) {
         const int qi = s_qi[q];
         if (qi < 0 || !((scan_q >> q) & 1u)) continue;
         float* myq = my + q * ROW;
-        float th = s_thq[w][q];
+        float th = s_thq[q];
         const float t1q = th * (1.f - kBandRel) * (1.f - kBandRel) - s_neub[q];
         float v[TILE_S / 32];                                   // v[4*s + e] = doc s*128 + lane*4 + e
         float mx = 0.f;
@@ -922,6 +923,45 @@ __device__ __forceinline__ void make_plan(const PlanArgs& pa, int q, float thr, 
         pa.defer_mask[q] = mask;
         pa.ne_ub[q] = sum * (1.f + 1e-6f);
     }
+}
+
+// Threshold seeding (K <= 32): before any tile is scored, thr[q] := the largest, over the query's terms with df >= K,
+// of the K-th largest weight among the term's first SEED_MAX postings - K distinct docs score at least that much, so it
+// is a valid lower bound of the K-th best score, and the first launches already run with a deferral plan instead of
+// streaming every term against a zero threshold.  One warp per query; a running top-32 is kept sorted across the lanes
+// (each batch of 32 weights is sorted, reversed and merged bitonically).
+constexpr int SEED_MAX = 1024;
+__global__ void __launch_bounds__(128) k_seed_thr(const br_posting* __restrict__ post, const int64_t* __restrict__ row_ptr,
+                                                  int32_t nq, int K, const int32_t* __restrict__ elig, float* __restrict__ thr,
+                                                  PlanArgs pa) {
+    const int lane = threadIdx.x & 31;
+    const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (q >= nq || !elig[q]) return;
+    const int32_t off = pa.q_off[q], nu = pa.u_cnt[q];
+    float best = 0.f;
+    for (int j = 0; j < nu; ++j) {
+        const int32_t t = pa.u_terms[off + j];
+        const float m = (float)pa.u_mult[off + j];
+        const int64_t lo = row_ptr[t], df = row_ptr[t + 1] - lo;
+        if (df < K || !(pa.ub[t] * m > best)) continue;            // cannot raise the bound
+        const int n = (int)min(df, (int64_t)SEED_MAX);
+        float run = 0.f;                                            // lane i: i-th largest weight so far
+        for (int base = 0; base < n; base += 32) {
+            const float wv = base + lane < n ? post[lo + base + lane].w * m : 0.f;
+            const float srt = warp_sort_desc(fmaxf(wv, 0.f), lane);
+            float x = fmaxf(run, __shfl_sync(0xffffffffu, srt, 31 - lane));     // bitonic: top 32 of the union
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float y = __shfl_xor_sync(0xffffffffu, x, o);
+                x = (lane & o) ? fminf(x, y) : fmaxf(x, y);
+            }
+            run = x;
+        }
+        best = fmaxf(best, __shfl_sync(0xffffffffu, run, K - 1));
+    }
+    const float th = best * (1.f - 4e-6f);      // fp32 accumulation of the doc's other terms can only add; slack for rounding
+    if (lane == 0) thr[q] = th;
+    make_plan(pa, q, th, lane);
 }
 
 // Between chunks: thr[q] = max(thr[q], K-th best fp32 score emitted so far); keep only the candidates
@@ -1245,7 +1285,12 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     const PlanArgs pa{q_off, pv.u_terms, pv.u_mult, pv.u_cnt, ix->ub, ix->row_slot, ix->n_srows, (float)ix->defer_pm * 1e-3f, defer_mask, ne_ub};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
                                                                             sizeof(float4) + sizeof(uint32_t) + sizeof(uint2) * TILE_W) +
-                        sizeof(NeEntry) * G * NE_MAX + sizeof(uint16_t) * TILE_W * LIST_CAP;
+                        sizeof(NeEntry) * G * NE_MAX + sizeof(uint16_t) * TILE_W * LIST_CAP + 4 * (20 + 9 * TILE_W) + G * TILE_QT;
+    if (k <= 32 && ix->seed_thr) {
+        k_seed_thr<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(ix->post, ix->row_ptr, nq, (int)k, elig, thr, pa);
+        BR_CUDA(cudaGetLastError());
+        ix->stats.kernel_launches += 1;
+    }
     switch (G) {
         case 1: BR_TRY(launch_tiles<1>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)); break;
         case 2: BR_TRY(launch_tiles<2>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)); break;
