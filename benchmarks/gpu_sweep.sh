@@ -7,7 +7,7 @@ i=0
 for opts in "$@"; do
   args=""
   for o in $opts; do args="$args --opt $o"; done
-  python bench.py --steps 5 --warmup 3 --no-cpu-baseline $args > gpurun_out/bench_${tag}_$i.json 2> gpurun_out/bench_${tag}_$i.err
+  python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-secondary $args > gpurun_out/bench_${tag}_$i.json 2> gpurun_out/bench_${tag}_$i.err
   echo "== $opts rc=$?"
   python - <<PY
 import json

@@ -29,7 +29,9 @@ SIGNATURES = {
     "br_index_export_csr": (C.c_int, [_P, _P, _P, _P, _P]),
     "br_index_import_csr": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, C.POINTER(_P)]),
     "br_score_batch": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, _P, _P]),
-    "br_topk_batch": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "br_topk_batch": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "br_topk_batch_records": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int, _P, _P, _P]),
+    "br_topk_merge_records": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "br_rescore_docs": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, _P, _P, _P, _P]),
     "br_index_enable_tfidf": (C.c_int, [_P, _P]),
     "br_tfidf_cosine_topk": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),

@@ -267,10 +267,28 @@ class BM25:
             ids = torch.empty((nq, n), dtype=torch.int32, device=dev)
             sc = torch.empty((nq, n), dtype=torch.float64, device=dev)
             cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
-            check(lib.br_topk_batch(self._h, ptr(q_terms), ptr(q_off), nq, n, int(self.dedup_query),
-                                    int(positive_only), ptr(ids), ptr(sc), ptr(cnt), _lib.stream_ptr(dev)),
-                  "br_topk_batch")
+            check(lib.br_topk_batch(self._h, ptr(q_terms), ptr(q_off), nq, int(q_terms.numel()), n,
+                                    int(self.dedup_query), int(positive_only), ptr(ids), ptr(sc), ptr(cnt),
+                                    _lib.stream_ptr(dev)), "br_topk_batch")
         return (ids, sc, cnt) if return_counts else (ids, sc)
+
+    def retrieve_records_batch(self, queries, n=10, positive_only=False):
+        """retrieve_top_n_batch as packed records int64[Q, n, 2]: [..., 0] = global doc id (doc_base + local id, -1
+        pads), [..., 1] = the float64 score's bits - what a doc-sharded caller all-gathers in one collective."""
+        self._require()
+        lib = _lib.load()
+        n = int(n)
+        if not 1 <= n <= _lib.BR_MAX_K:
+            raise ValueError(f"n must be in [1, {_lib.BR_MAX_K}] for the batched call")
+        q_terms, q_off = self._to_device(*self.pack_queries(queries))
+        nq = q_off.numel() - 1
+        dev = self._device
+        with torch.cuda.device(dev):
+            rec = torch.empty((nq, n, 2), dtype=torch.int64, device=dev)
+            check(lib.br_topk_batch_records(self._h, ptr(q_terms), ptr(q_off), nq, int(q_terms.numel()), n,
+                                            int(self.dedup_query), int(positive_only), ptr(rec), None,
+                                            _lib.stream_ptr(dev)), "br_topk_batch_records")
+        return rec
 
     def exact_scores(self, query):
         """float64[N] exact re-evaluation of the reference formula for every doc (device tensor)."""

@@ -16,11 +16,25 @@ int br_score_batch(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_of
     return br::score_batch(ix, q_terms_dev, q_offsets_dev, nq, dedup, out_scores_dev, (cudaStream_t)stream);
 }
 
-int br_topk_batch(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq, int32_t k,
-                  int dedup, int positive_only, int32_t* out_ids_dev, double* out_scores_dev, int32_t* out_counts_dev,
-                  void* stream) {
-    return br::topk_batch(ix, q_terms_dev, q_offsets_dev, nq, k, dedup, positive_only, out_ids_dev, out_scores_dev,
-                          out_counts_dev, (cudaStream_t)stream);
+int br_topk_batch(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq, int32_t n_terms,
+                  int32_t k, int dedup, int positive_only, int32_t* out_ids_dev, double* out_scores_dev,
+                  int32_t* out_counts_dev, void* stream) {
+    BR_REQUIRE(out_ids_dev && out_scores_dev, BR_ERR_INVALID, "br_topk_batch: null pointer");
+    return br::topk_batch(ix, q_terms_dev, q_offsets_dev, nq, n_terms, k, dedup, positive_only, out_ids_dev, out_scores_dev,
+                          out_counts_dev, nullptr, (cudaStream_t)stream);
+}
+
+int br_topk_batch_records(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq,
+                          int32_t n_terms, int32_t k, int dedup, int positive_only, br_record* out_records_dev,
+                          int32_t* out_counts_dev, void* stream) {
+    BR_REQUIRE(out_records_dev, BR_ERR_INVALID, "br_topk_batch_records: null pointer");
+    return br::topk_batch(ix, q_terms_dev, q_offsets_dev, nq, n_terms, k, dedup, positive_only, nullptr, nullptr,
+                          out_counts_dev, out_records_dev, (cudaStream_t)stream);
+}
+
+int br_topk_merge_records(const br_record* records_dev, int32_t n_parts, int32_t nq, int32_t k, int64_t* out_ids_dev,
+                          double* out_scores_dev, void* stream) {
+    return br::topk_merge_records(records_dev, n_parts, nq, k, out_ids_dev, out_scores_dev, (cudaStream_t)stream);
 }
 
 int br_rescore_docs(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq, int dedup,

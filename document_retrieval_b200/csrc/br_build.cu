@@ -212,7 +212,7 @@ void index_free(br_index* ix) {
     cudaFree(ix->row_ptr); cudaFree(ix->post); cudaFree(ix->post_cos); cudaFree(ix->tf); cudaFree(ix->dl); cudaFree(ix->df);
     cudaFree(ix->idf); cudaFree(ix->ub); cudaFree(ix->hot_slot); cudaFree(ix->skip); cudaFree(ix->sig_bit); cudaFree(ix->dense_rows); cudaFree(ix->row_slot);
     ix->ws_prep.release(); ix->ws_dense.release(); ix->ws_sel.release(); ix->ws_cand.release();
-    ix->ws_misc.release(); ix->ws_tile.release(); ix->ws_sort.release();
+    ix->ws_misc.release(); ix->ws_tile.release(); ix->ws_sort.release(); ix->ws_cold.release(); ix->ws_rec.release();
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
     delete ix;
 }

@@ -131,15 +131,15 @@ struct br_index {
     std::vector<double> h_idf;
 
     // query-time scratch
-    br::DevBuf ws_prep, ws_dense, ws_sel, ws_cand, ws_misc, ws_tile, ws_sort;
+    br::DevBuf ws_prep, ws_dense, ws_sel, ws_cand, ws_misc, ws_tile, ws_sort, ws_cold, ws_rec;
     br_query_stats stats{};
 
     bool allow_fused = true, allow_fused_bigk = true;
     int tile_g = 0;
     bool seed_thr = true;           // threshold seeding before the first launch of the tiled scorer
     int defer_pm = 700;             // MaxScore deferral budget of the tiled scorer, per mille of the threshold (0 = off)
-    int tile_tpb = 8;               // consecutive tiles per CTA in the large launches
-    int tile_dense_min = 16;        // average postings of a term per 512-doc sub-range from which its slices are walked
+    int tile_tpb = 16;              // consecutive tiles per CTA in the large launches
+    int tile_dense_min = 32;        // average postings of a term per 512-doc sub-range from which its slices are walked
                                     // term by term (whole warp, pipelined) instead of concatenated with the sparse ones
 
     // optional event timing of the scoring kernel
@@ -182,9 +182,9 @@ void index_free(br_index* ix);
 // br_query.cu
 int score_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, int32_t nq, int dedup,
                 float* out_scores, cudaStream_t st);
-int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, int32_t nq, int32_t k,
+int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, int32_t nq, int32_t n_terms, int32_t k,
                int dedup, int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts,
-               cudaStream_t st);
+               br_record* out_recs, cudaStream_t st);
 int rescore_docs(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, int32_t nq, int dedup,
                  const int32_t* cand_ids, const int64_t* cand_off, double* out_scores, cudaStream_t st);
 int enable_tfidf(br_index* ix, cudaStream_t st);
@@ -194,4 +194,6 @@ int rerank_v3(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, in
               const int64_t* cand_off, double* out_scores, cudaStream_t st);
 int topk_merge(const int64_t* ids, const double* scores, int32_t n_parts, int32_t nq, int32_t k,
                int64_t* out_ids, double* out_scores, cudaStream_t st);
+int topk_merge_records(const br_record* recs, int32_t n_parts, int32_t nq, int32_t k, int64_t* out_ids,
+                       double* out_scores, cudaStream_t st);
 }  // namespace br

@@ -34,7 +34,12 @@ __global__ void k_prep_queries(const int32_t* __restrict__ q_terms, const int32_
     const int lane = threadIdx.x & 31;
     const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (q >= nq) return;
-    const int32_t off = q_off[q], M = q_off[q + 1] - off;
+    const int32_t off = q_off[q];
+    int32_t M = q_off[q + 1] - off;
+    if (off < 0 || M < 0 || off + M > v.t_cap) {         // offsets beyond the caller's n_terms: treated as an empty query
+        if (lane == 0) atomicOr(v.bad, 1);
+        M = 0;
+    }
     // phase 1: validity, ordered compaction into o_terms
     int32_t n_valid = 0;
     for (int32_t base = 0; base < M; base += 32) {
@@ -358,7 +363,8 @@ __global__ void __launch_bounds__(FS_T) k_final_select(const IdT* __restrict__ i
                                                        int32_t n_parts, int64_t part_stride, int32_t fixed_cnt,
                                                        int32_t k, int64_t id_base, int positive_only,
                                                        IdT* __restrict__ out_ids, double* __restrict__ out_sc,
-                                                       int32_t* __restrict__ out_cnt, const int32_t* __restrict__ cnt_hint) {
+                                                       int32_t* __restrict__ out_cnt, const int32_t* __restrict__ cnt_hint,
+                                                       const br_record* __restrict__ recs = nullptr) {
     __shared__ FsKey keys[FS_N];
     __shared__ uint32_t s_flag[FS_N];
     const int q = q_begin + blockIdx.x;
@@ -377,8 +383,11 @@ __global__ void __launch_bounds__(FS_T) k_final_select(const IdT* __restrict__ i
             if (cnt_hint) cnt = min(cnt, (int64_t)max(cnt_hint[q], 0));      // only the head of the region is in use
             const int64_t take = min((int64_t)(FS_N - filled), cnt - pos);
             for (int64_t i = threadIdx.x; i < take; i += FS_T) {
-                const IdT id = ids[base + pos + i];
-                FsKey kk = {sc[base + pos + i], (int64_t)id};
+                IdT id;
+                double scv;
+                if (recs) { const br_record r = recs[base + pos + i]; id = (IdT)r.id; scv = r.score; }   // packed {id, score}
+                else { id = ids[base + pos + i]; scv = sc[base + pos + i]; }
+                FsKey kk = {scv, (int64_t)id};
                 if (id < 0) kk = pad;
                 keys[filled + i] = kk;
             }
@@ -587,11 +596,14 @@ int launch_final_select(const int32_t* cand, const double* cand_score, const int
     BR_CUDA(cudaGetLastError());
     return BR_OK;
 }
+// n_terms >= 0: the caller knows q_offsets[nq] (or an upper bound) - no device read, no stream synchronisation.
 static int prep_queries(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, int dedup,
-                        cudaStream_t st, PrepView* pv, int64_t** chunk_start, int32_t* total_terms) {
-    int32_t T = 0;
-    BR_CUDA(cudaMemcpyAsync(&T, q_off + nq, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    BR_CUDA(cudaStreamSynchronize(st));
+                        cudaStream_t st, PrepView* pv, int64_t** chunk_start, int32_t* total_terms, int32_t n_terms = -1) {
+    int32_t T = n_terms;
+    if (T < 0) {
+        BR_CUDA(cudaMemcpyAsync(&T, q_off + nq, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        BR_CUDA(cudaStreamSynchronize(st));
+    }
     BR_REQUIRE(T >= 0, BR_ERR_INVALID, "query offsets: negative total");
     *total_terms = T;
     const size_t Tn = (size_t)T + 1, Q = (size_t)nq + 2;
@@ -600,13 +612,16 @@ static int prep_queries(br_index* ix, const int32_t* q_terms, const int32_t* q_o
     auto carve = [&](size_t n) { size_t o = bytes; bytes += (n + 255) & ~(size_t)255; return o; };
     const size_t o_ut = carve(Tn * 4), o_um = carve(Tn * 4), o_uc = carve(Tn * 8), o_un = carve(Q * 4),
                  o_ot = carve(Tn * 4), o_on = carve(Q * 4), o_P = carve(Q * 8), o_nc = carve(Q * 4),
-                 o_tmp = carve(Tn * 4), o_cs = carve(Q * 8), o_sig = carve(Q * 4);
+                 o_tmp = carve(Tn * 4), o_cs = carve(Q * 8), o_sig = carve(Q * 4), o_bad = carve(16);
     BR_TRY(ix->ws_prep.reserve(bytes));
     char* p = ix->ws_prep.as<char>();
     pv->u_terms = (int32_t*)(p + o_ut); pv->u_mult = (int32_t*)(p + o_um); pv->u_cum = (int64_t*)(p + o_uc);
     pv->u_cnt = (int32_t*)(p + o_un); pv->o_terms = (int32_t*)(p + o_ot); pv->o_cnt = (int32_t*)(p + o_on);
     pv->P = (int64_t*)(p + o_P); pv->n_chunks = (uint32_t*)(p + o_nc); pv->tmp = (int32_t*)(p + o_tmp); pv->sig = (uint32_t*)(p + o_sig);
     *chunk_start = (int64_t*)(p + o_cs);
+    pv->t_cap = T;
+    pv->bad = (int32_t*)(p + o_bad);
+    BR_CUDA(cudaMemsetAsync(pv->bad, 0, 4, st));
     k_prep_queries<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(q_terms, q_off, nq, ix->vocab, ix->row_ptr, ix->sig_bit, dedup, *pv);
     BR_CUDA(cudaGetLastError());
     k_exscan<uint32_t><<<1, 1024, 0, st>>>(pv->n_chunks, nq, *chunk_start);
@@ -695,19 +710,34 @@ static int topk_dense(br_index* ix, const int32_t* q_off, const PrepView& pv, co
     return BR_OK;
 }
 
-int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, int32_t k, int dedup,
-               int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st) {
-    BR_REQUIRE(ix && q_terms && q_off && out_ids && out_scores, BR_ERR_INVALID, "br_topk_batch: null pointer");
+// (local id, score) -> {global id, score} records, the unit of the cross-shard all-gather
+__global__ void k_pack_records(const int32_t* __restrict__ ids, const double* __restrict__ sc, int64_t n, int64_t doc_base,
+                               br_record* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t d = ids[i];
+    out[i] = br_record{d >= 0 ? (int64_t)d + doc_base : (int64_t)-1, sc[i]};
+}
+
+int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, int32_t n_terms, int32_t k, int dedup,
+               int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, br_record* out_recs,
+               cudaStream_t st) {
+    BR_REQUIRE(ix && q_terms && q_off && ((out_ids && out_scores) || out_recs), BR_ERR_INVALID, "br_topk_batch: null pointer");
     BR_REQUIRE(ix->finalized, BR_ERR_STATE, "br_topk_batch: call br_index_finalize first");
     BR_REQUIRE(k >= 1 && k <= BR_MAX_K, BR_ERR_INVALID, "br_topk_batch: k must be in [1, BR_MAX_K]");
     BR_REQUIRE(nq >= 0, BR_ERR_INVALID, "br_topk_batch: nq < 0");
     if (nq == 0) return BR_OK;
     BR_CUDA(cudaSetDevice(ix->device));
     ix->stats = br_query_stats{};
+    if (!out_ids || !out_scores) {                         // records only: ids / scores go to scratch
+        BR_TRY(ix->ws_rec.reserve((size_t)nq * k * 12 + 512));
+        out_ids = ix->ws_rec.as<int32_t>();
+        out_scores = (double*)(ix->ws_rec.as<char>() + (((size_t)nq * k * 4 + 255) & ~(size_t)255));
+    }
     PrepView pv;
     int64_t* chunk_start;
     int32_t T;
-    BR_TRY(prep_queries(ix, q_terms, q_off, nq, dedup, st, &pv, &chunk_start, &T));
+    BR_TRY(prep_queries(ix, q_terms, q_off, nq, dedup, st, &pv, &chunk_start, &T, n_terms));
     // algorithmic bytes of this batch: 8 B per posting of every distinct in-vocab query term
     std::vector<int64_t> hP((size_t)nq);
     BR_CUDA(cudaMemcpyAsync(hP.data(), pv.P, sizeof(int64_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
@@ -756,7 +786,15 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
             ix->stats.kernel_launches += 1;
         }
     }
+    if (out_recs) {
+        k_pack_records<<<blocks_for((int64_t)nq * k, 256), 256, 0, st>>>(out_ids, out_scores, (int64_t)nq * k, ix->doc_base, out_recs);
+        BR_CUDA(cudaGetLastError());
+        ix->stats.kernel_launches += 1;
+    }
+    int32_t h_bad = 0;
+    BR_CUDA(cudaMemcpyAsync(&h_bad, pv.bad, 4, cudaMemcpyDeviceToHost, st));
     BR_CUDA(cudaStreamSynchronize(st));
+    BR_REQUIRE(!h_bad, BR_ERR_INVALID, "br_topk_batch: q_offsets run past n_terms");
     int64_t sum = 0;
     for (int64_t v : hP) sum += v;
     ix->stats.postings_bytes = 8 * sum;
@@ -842,6 +880,17 @@ int topk_merge(const int64_t* ids, const double* scores, int32_t n_parts, int32_
     if (nq == 0) return BR_OK;
     k_final_select<int64_t><<<nq, FS_T, 0, st>>>(ids, scores, nullptr, 0, n_parts, (int64_t)nq * k, k, k, 0, 0, out_ids,
                                                  out_scores, nullptr, nullptr);
+    BR_CUDA(cudaGetLastError());
+    return BR_OK;
+}
+
+int topk_merge_records(const br_record* recs, int32_t n_parts, int32_t nq, int32_t k, int64_t* out_ids, double* out_scores,
+                       cudaStream_t st) {
+    BR_REQUIRE(recs && out_ids && out_scores, BR_ERR_INVALID, "br_topk_merge_records: null pointer");
+    BR_REQUIRE(n_parts >= 1 && nq >= 0 && k >= 1 && k <= BR_MAX_K, BR_ERR_INVALID, "br_topk_merge_records: bad sizes");
+    if (nq == 0) return BR_OK;
+    k_final_select<int64_t><<<nq, FS_T, 0, st>>>(nullptr, nullptr, nullptr, 0, n_parts, (int64_t)nq * k, k, k, 0, 0, out_ids,
+                                                 out_scores, nullptr, nullptr, recs);
     BR_CUDA(cudaGetLastError());
     return BR_OK;
 }

@@ -16,6 +16,8 @@ struct PrepView {
     uint32_t* n_chunks; // [nq]
     int32_t* tmp;       // [T]
     uint32_t* sig;      // [nq] bit (31 - r) set when the query contains the r-th most frequent term
+    int32_t t_cap;      // term slots the scratch arrays hold (caller's n_terms)
+    int32_t* bad;       // [1] set when q_offsets runs past t_cap
 };
 
 

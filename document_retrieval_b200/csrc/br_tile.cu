@@ -167,7 +167,7 @@ template <bool SCATTER>
 __global__ void k_cold_pass(PrepView pv, const int32_t* __restrict__ q_off, const int32_t* __restrict__ hot_slot,
                             const int64_t* __restrict__ row_ptr, const br_posting* __restrict__ post, int32_t nq, int G,
                             int n_groups, const int32_t* __restrict__ elig, const int32_t* __restrict__ inv_perm,
-                            uint32_t* __restrict__ counter, ColdEntry* __restrict__ out) {
+                            uint32_t* __restrict__ counter, ColdEntry* __restrict__ out, uint32_t out_cap) {
     const int lane = threadIdx.x & 31;
     const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (q >= nq || !elig[q]) return;
@@ -185,7 +185,7 @@ __global__ void k_cold_pass(PrepView pv, const int32_t* __restrict__ q_off, cons
             const uint32_t tile = p.doc >> TILE_DOCS_SHIFT;
             const int64_t b = (int64_t)tile * n_groups + g;
             const uint32_t pos = atomicAdd(counter + b, 1u);
-            if (SCATTER) out[pos] = ColdEntry{(p.doc & ((1u << TILE_DOCS_SHIFT) - 1)) | (slot << TILE_DOCS_SHIFT), p.w * mult};
+            if (SCATTER && pos < out_cap) out[pos] = ColdEntry{(p.doc & ((1u << TILE_DOCS_SHIFT) - 1)) | (slot << TILE_DOCS_SHIFT), p.w * mult};
         }
     }
 }
@@ -299,6 +299,7 @@ struct TileArgs {
     const int32_t* elig;
     const uint32_t* cold_off;     // [n_tiles * n_groups + 1] or null
     const ColdEntry* cold;
+    uint32_t cold_cap;            // entries the cold buffer holds (a batch that needs more is repeated with a larger one)
     const float* rows;            // dense rows [n_rows, n_pad]
     int64_t n_pad;
     float* thr;
@@ -326,9 +327,6 @@ __device__ __forceinline__ float sel_q(const float (&v)[G], int q) {
     return r;
 }
 
-#ifndef BR_TILE_MINB
-#define BR_TILE_MINB 3            // resident CTAs per SM the register allocation is sized for (64 KB of accumulators each)
-#endif
 constexpr int LIST_CAP = 64;      // crossing-list slots per warp and sub-range (overflow -> full scan of the sub-range)
 
 // MaxScore deferral (exact): between launches every query gets a plan (make_plan): the terms with the smallest upper
@@ -346,7 +344,7 @@ constexpr int LIST_CAP = 64;      // crossing-list slots per warp and sub-range 
 // After the CTA prologue there is no block barrier: every warp fetches the slice bounds of its own sub-range (one tile
 // ahead, into registers) and its own copy of the thresholds.
 template <int G>
-__global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileArgs a) {
+__global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* acc = reinterpret_cast<float*>(smem_raw);                                     // [G][W][S]
     TileEntry* ent = reinterpret_cast<TileEntry*>(smem_raw + sizeof(float) * G * TILE_W * TILE_S);   // streamed entries
@@ -522,20 +520,18 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
         // each warp initialises its own accumulator rows: zero + the weights of the streamed dense-row terms of each
         // query (terms present in >= ~20% of the docs are stored as plain fp32 rows, 0 where absent), 4 docs per lane
 #pragma unroll 1
-        for (int half = 0; half < TILE_S / 256; ++half) {       // 256 docs per pass: 2 x (4 docs per lane)
-            float4 v[G][2];
+        for (int seg = 0; seg < TILE_S / 128; ++seg) {          // 128 docs per pass
+            float4 v[G];
 #pragma unroll
-            for (int q = 0; q < G; ++q) v[q][0] = v[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int64_t off = (int64_t)doc0 + half * 256 + lane * 4;
-            for (int u0 = 0; u0 < Ur; u0 += 2) {             // two rows x two segments = 4 loads in flight
-                float4 d[2][2];
+            for (int q = 0; q < G; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int64_t off = (int64_t)doc0 + seg * 128 + lane * 4;
+            for (int u0 = 0; u0 < Ur; u0 += 2) {             // two rows in flight
+                float4 d[2];
                 float ff[2][4];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const int u = min(u0 + k, Ur - 1);
-                    const float* row = a.rows + (int64_t)ent[u].slot * a.n_pad + off;
-                    d[k][0] = __ldg(reinterpret_cast<const float4*>(row));
-                    d[k][1] = __ldg(reinterpret_cast<const float4*>(row + 128));
+                    d[k] = __ldg(reinterpret_cast<const float4*>(a.rows + (int64_t)ent[u].slot * a.n_pad + off));
                     const float4 f4 = u0 + k < Ur ? s_fm[u] : make_float4(0.f, 0.f, 0.f, 0.f);
                     ff[k][0] = f4.x; ff[k][1] = f4.y; ff[k][2] = f4.z; ff[k][3] = f4.w;
                 }
@@ -544,22 +540,15 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
 #pragma unroll
                     for (int q = 0; q < G; ++q) {
                         if (ff[k][q] != 0.f) {               // warp-uniform
-#pragma unroll
-                            for (int s = 0; s < 2; ++s) {
-                                v[q][s].x = fmaf(d[k][s].x, ff[k][q], v[q][s].x);
-                                v[q][s].y = fmaf(d[k][s].y, ff[k][q], v[q][s].y);
-                                v[q][s].z = fmaf(d[k][s].z, ff[k][q], v[q][s].z);
-                                v[q][s].w = fmaf(d[k][s].w, ff[k][q], v[q][s].w);
-                            }
+                            v[q].x = fmaf(d[k].x, ff[k][q], v[q].x);
+                            v[q].y = fmaf(d[k].y, ff[k][q], v[q].y);
+                            v[q].z = fmaf(d[k].z, ff[k][q], v[q].z);
+                            v[q].w = fmaf(d[k].w, ff[k][q], v[q].w);
                         }
                     }
             }
 #pragma unroll
-            for (int q = 0; q < G; ++q) {
-                float4* dst = reinterpret_cast<float4*>(acc + (q * TILE_W + w) * TILE_S + half * 256);
-                dst[lane] = v[q][0];
-                dst[32 + lane] = v[q][1];
-            }
+            for (int q = 0; q < G; ++q) reinterpret_cast<float4*>(my + q * ROW)[seg * 32 + lane] = v[q];
         }
     }
     __syncwarp();
@@ -622,106 +611,45 @@ __global__ void __launch_bounds__(TILE_W * 32, BR_TILE_MINB) k_tile_score(TileAr
         }
     }
     __syncwarp();
-    // Phase B - dense slices, warp-cooperative and software-pipelined (dense_term): the next 128
-    // postings (4 per lane, coalesced 8-byte words) are in flight while the current ones are added.
-    // Inside a chunk all docs are distinct (one term), so the read-modify-writes of a lane are
-    // independent: all LDS first, then the adds, then all STS.  No atomics.
-    if (Ur < Ud) {
-    auto next_dense = [&](int u) {      // first dense entry >= u with a non-empty slice here (Ud when none)
-        while (u < Ud) {
-            const uint2 bd = s_bnd[u];
-            if (bd.x < bd.y) break;
-            ++u;
-        }
-        return u;
-    };
-    const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
-    int u = next_dense(Ur);
-    uint32_t start = 0, hi = 0;                     // current chunk = postings [start, min(start+128, hi)) of term u
-    const uint2* p = reinterpret_cast<const uint2*>(a.post);
-    uint2 cur[4];
-    float fm[G];
-    unsigned mask = 0;
-    if (u < Ud) {
+    // Phase B - dense slices (terms with >= tile_dense_min postings per sub-range on average that are still streamed:
+    // rare once the deferral plans exist), whole warp per term, 64 postings per step.  Inside a term all docs are
+    // distinct, so the read-modify-writes of a step are independent.  No atomics.
+#pragma unroll 1
+    for (int u = Ur; u < Ud; ++u) {
         const uint2 bd = s_bnd[u];
-        start = bd.x;
-        hi = bd.y;
-        p = reinterpret_cast<const uint2*>(a.post) + s_base[u];
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-            if (start + lane + 32 * x < hi) cur[x] = __ldg(p + start + lane + 32 * x);
+        if (bd.x >= bd.y) continue;
         const float4 f4 = s_fm[u];
         const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
+        const uint2* p = reinterpret_cast<const uint2*>(a.post) + s_base[u];
+        for (uint32_t c = bd.x; c < bd.y; c += 64) {
+            uint2 v[2];
+            bool ok[2];
 #pragma unroll
-        for (int q = 0; q < G; ++q) {
-            fm[q] = ff[q];
-            mask |= ff[q] != 0.f ? (1u << q) : 0u;
-        }
-    }
-    while (u < Ud) {
-        // coordinates of the next chunk: same term, or the first chunk of the next dense term
-        int nu = u;
-        uint32_t nstart = start + 128, nhi = hi;
-        const uint2* np = p;
-        if (nstart >= hi) {
-            nu = next_dense(u + 1);
-            nstart = nhi = 0;
-            if (nu < Ud) {
-                const uint2 bd = s_bnd[nu];
-                nstart = bd.x;
-                nhi = bd.y;
-                np = reinterpret_cast<const uint2*>(a.post) + s_base[nu];
+            for (int x = 0; x < 2; ++x) {
+                ok[x] = c + lane + 32 * x < bd.y;
+                if (ok[x]) v[x] = __ldg(p + c + lane + 32 * x);
             }
-        }
-        uint2 nxt[4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
-            if (nstart + lane + 32 * x < nhi) nxt[x] = __ldg(np + nstart + lane + 32 * x);
-        uint32_t ad[4];
-        bool ok[4];
+            for (int x = 0; x < 2; ++x) {
+                if (ok[x]) {
+                    const uint32_t idx = v[x].x - doc0;
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            ok[x] = start + lane + 32 * x < hi;
-            ad[x] = my_s + ((cur[x].x - doc0) << 2);
-        }
-        constexpr uint32_t ROWB = TILE_W * TILE_S * 4;     // bytes between query rows
-#pragma unroll
-        for (int q = 0; q < G; ++q) {
-            if (mask & (1u << q)) {                        // warp-uniform
-                float r[4];
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-                    if (ok[x]) r[x] = lds_f32(ad[x] + q * ROWB);
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {              // fmaf(w, 1.0f, acc) == acc + w exactly
-                    if (ok[x]) {
-                        const float nv = fmaf(__uint_as_float(cur[x].y), fm[q], r[x]);
-                        sts_f32(ad[x] + q * ROWB, nv);
-                        if (nv >= t1[q]) push(q, cur[x].x - doc0);
+                    for (int q = 0; q < G; ++q) {
+                        if (ff[q] != 0.f) {                    // warp-uniform
+                            const float nv = fmaf(__uint_as_float(v[x].y), ff[q], my[q * ROW + idx]);
+                            my[q * ROW + idx] = nv;
+                            if (nv >= t1[q]) push(q, idx);
+                        }
                     }
                 }
             }
         }
-        __syncwarp();
-#pragma unroll
-        for (int x = 0; x < 4; ++x) cur[x] = nxt[x];
-        if (nu != u && nu < Ud) {
-            const float4 f4 = s_fm[nu];
-            const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
-            mask = 0;
-#pragma unroll
-            for (int q = 0; q < G; ++q) {
-                fm[q] = ff[q];
-                mask |= ff[q] != 0.f ? (1u << q) : 0u;
-            }
-        }
-        u = nu; start = nstart; hi = nhi; p = np;
     }
-    }
+    __syncwarp();
     // cold postings of this (tile, group) bucket that fall in this warp's sub-range
     if (a.cold_off) {
         const int64_t b = (int64_t)tile * a.n_groups + g;
-        const uint32_t c0 = a.cold_off[b], c1 = a.cold_off[b + 1];
+        const uint32_t c0 = a.cold_off[b], c1 = min(a.cold_off[b + 1], a.cold_cap);
         for (uint32_t i = c0 + lane; i < c1; i += 32) {
             const ColdEntry ce = a.cold[i];
             const uint32_t l = ce.key & ((1u << TILE_DOCS_SHIFT) - 1), q = ce.key >> TILE_DOCS_SHIFT;
@@ -1243,6 +1171,8 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 2;
     }
+    if (ix->ws_cold.cap == 0) BR_TRY(ix->ws_cold.reserve(sizeof(ColdEntry) * std::max<size_t>(1u << 20, (size_t)nq * 2048)));
+    for (int attempt = 0; attempt < 2; ++attempt) {
     // one memset covers thr / cand_cnt / prev_cnt / overflow / defer_mask / ne_ub (contiguous carve)
     BR_CUDA(cudaMemsetAsync(p + o_thr, 0, o_off - o_thr, st));
     BR_CUDA(cudaMemsetAsync(cold_total, 0, 16, st));
@@ -1251,21 +1181,20 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     BR_CUDA(cudaGetLastError());
     k_fill_offsets<<<blocks_for(nq + 1, 256), 256, 0, st>>>(cand_off, nq, cap);
     BR_CUDA(cudaGetLastError());
-    unsigned long long h_cold = 0;
-    BR_CUDA(cudaMemcpyAsync(&h_cold, cold_total, sizeof(h_cold), cudaMemcpyDeviceToHost, st));
-    BR_CUDA(cudaStreamSynchronize(st));
     ix->stats.kernel_launches += 2;
-    BR_REQUIRE(h_cold < (1ull << 32), BR_ERR_UNSUPPORTED, "br_topk_batch: more than 2^32 cold postings in one batch");
-
+    // Cold postings -> (tile, group) buckets.  Their number is known on the device only; reading it back here would
+    // stall the stream in the middle of the batch, so the scatter writes into the buffer kept from earlier batches
+    // (bounded by its capacity) and the total is checked after the batch: a batch that needed more is repeated once
+    // with a larger buffer.
     const ColdEntry* cold = nullptr;
     const uint32_t* cold_off = nullptr;
-    if (h_cold > 0) {
-        BR_TRY(ix->ws_misc.reserve(sizeof(ColdEntry) * (size_t)h_cold + 256));
-        ColdEntry* d_cold = ix->ws_misc.as<ColdEntry>();
+    const uint32_t cold_cap = (uint32_t)std::min<size_t>(ix->ws_cold.cap / sizeof(ColdEntry), 0xffffffffu);
+    {
+        ColdEntry* d_cold = ix->ws_cold.as<ColdEntry>();
         BR_CUDA(cudaMemsetAsync(b_cnt, 0, 4 * (size_t)(n_buckets + 1), st));
         const unsigned qb = blocks_for((int64_t)nq * 32, 128);
         k_cold_pass<false><<<qb, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, ix->post, nq, G, n_groups, elig, inv_perm,
-                                              b_cnt, nullptr);
+                                              b_cnt, nullptr, 0u);
         BR_CUDA(cudaGetLastError());
         k_scan_reduce<<<(unsigned)n_scan_blocks, SCAN_T, 0, st>>>(b_cnt, n_buckets, part);
         BR_CUDA(cudaGetLastError());
@@ -1274,14 +1203,14 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
         k_scan_apply<<<(unsigned)n_scan_blocks, SCAN_T, 0, st>>>(b_cnt, n_buckets, part_off, b_off, b_cur);
         BR_CUDA(cudaGetLastError());
         k_cold_pass<true><<<qb, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, ix->post, nq, G, n_groups, elig, inv_perm,
-                                             b_cur, d_cold);
+                                             b_cur, d_cold, cold_cap);
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 5;
         cold = d_cold;
         cold_off = b_off;
     }
     TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
-               cold_off, cold, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, cap, (int)k, 0, 0, 1, dedup ? 0 : 1, perm, defer_mask, ne_ub, ix->row_slot};
+               cold_off, cold, cold_cap, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, cap, (int)k, 0, 0, 1, dedup ? 0 : 1, perm, defer_mask, ne_ub, ix->row_slot};
     const PlanArgs pa{q_off, pv.u_terms, pv.u_mult, pv.u_cnt, ix->ub, ix->row_slot, ix->n_srows, (float)ix->defer_pm * 1e-3f, defer_mask, ne_ub};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
                                                                             sizeof(float4) + sizeof(uint32_t) + sizeof(uint2) * TILE_W) +
@@ -1304,8 +1233,18 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     BR_CUDA(cudaGetLastError());
     ix->stats.kernel_launches += 3;
     h_flags->resize((size_t)nq);
+    unsigned long long h_cold = 0;
     BR_CUDA(cudaMemcpyAsync(h_flags->data(), flags, 4 * (size_t)nq, cudaMemcpyDeviceToHost, st));
-    BR_CUDA(cudaStreamSynchronize(st));
+    BR_CUDA(cudaMemcpyAsync(&h_cold, cold_total, sizeof(h_cold), cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaStreamSynchronize(st));                    // the only host synchronisation of the fused path
+    BR_REQUIRE(h_cold < (1ull << 32), BR_ERR_UNSUPPORTED, "br_topk_batch: more than 2^32 cold postings in one batch");
+    if (h_cold > cold_cap) {                               // the cold buffer was too small: grow it and repeat the batch
+        BR_REQUIRE(attempt == 0, BR_ERR_CUDA, "br_topk_batch: cold buffer still too small after growing it");
+        BR_TRY(ix->ws_cold.reserve(sizeof(ColdEntry) * (size_t)h_cold + 256));
+        continue;
+    }
+    break;
+    }   // attempt
     return BR_OK;
 }
 

@@ -36,17 +36,43 @@ def reduce_stats(local_df: torch.Tensor, n_docs: int, sum_dl: int, group=None):
     return df.cpu().numpy(), int(st[0]), int(st[1])
 
 
+def pack_records(ids: torch.Tensor, scores: torch.Tensor):
+    """[Q, k] (int64 global id, float64 score) -> int64[Q, k, 2] records (the score's bits in [..., 1])."""
+    return torch.stack([ids.to(torch.int64), scores.to(torch.float64).view(torch.int64)], dim=-1).contiguous()
+
+
+def gather_records(rec: torch.Tensor, group=None):
+    """ONE all-gather of the per-rank packed [Q, k, 2] records -> [G, Q, k, 2]."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return rec[None]
+    out = torch.empty((world * rec.shape[0],) + tuple(rec.shape[1:]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
+    return out.view((world,) + tuple(rec.shape))
+
+
 def gather_candidates(ids: torch.Tensor, scores: torch.Tensor, group=None):
-    """all-gather of per-rank [Q, k] candidates -> ([G, Q, k] ids, [G, Q, k] scores)."""
+    """all-gather of per-rank [Q, k] candidates -> ([G, Q, k] ids, [G, Q, k] scores), one collective."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return ids[None], scores[None]
-    q, k = ids.shape
-    all_ids = torch.empty((world * q, k), dtype=ids.dtype, device=ids.device)
-    all_sc = torch.empty((world * q, k), dtype=scores.dtype, device=scores.device)
-    dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=group)
-    dist.all_gather_into_tensor(all_sc, scores.contiguous(), group=group)
-    return all_ids.view(world, q, k), all_sc.view(world, q, k)
+    allr = gather_records(pack_records(ids, scores), group)
+    return allr[..., 0].contiguous(), allr[..., 1].contiguous().view(torch.float64)
+
+
+def merge_records_cuda(all_rec: torch.Tensor, k: int):
+    """br_topk_merge_records: packed records [G, Q, k, 2] -> ([Q, k] ids, [Q, k] scores) by (score desc, id asc)."""
+    lib = _lib.load()
+    g, q, kk, _ = all_rec.shape
+    dev = all_rec.device
+    if kk != k:
+        raise ValueError("candidate width must equal k")
+    out_ids = torch.empty((q, k), dtype=torch.int64, device=dev)
+    out_sc = torch.empty((q, k), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.br_topk_merge_records(ptr(all_rec.contiguous()), g, q, k, ptr(out_ids), ptr(out_sc), _lib.stream_ptr(dev)),
+              "br_topk_merge_records")
+    return out_ids, out_sc
 
 
 def merge_topk_cuda(all_ids: torch.Tensor, all_sc: torch.Tensor, k: int):
@@ -86,6 +112,14 @@ class ShardedBM25:
 
     def retrieve_top_n_batch(self, queries, n=10):
         """-> (global ids int64[Q, n], float64 scores[Q, n]) identical on every rank."""
+        if hasattr(self.local, "retrieve_records_batch") and self.merge is merge_topk_cuda:
+            # CUDA shard: the library emits packed {global id, score} records - one all-gather, merged straight from
+            # the gathered buffer
+            rec = self.local.retrieve_records_batch(queries, n)
+            allr = gather_records(rec, self.group)
+            if allr.shape[0] == 1:
+                return rec[..., 0].contiguous(), rec[..., 1].contiguous().view(torch.float64)
+            return merge_records_cuda(allr, n)
         ids, sc = self.local.retrieve_top_n_batch(queries, n)
         gids = torch.where(ids >= 0, ids.to(torch.int64) + self.local.doc_base, torch.full_like(ids, -1, dtype=torch.int64))
         all_ids, all_sc = gather_candidates(gids, sc, self.group)

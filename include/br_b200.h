@@ -112,10 +112,23 @@ int br_score_batch(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_of
  * matching posting (team_run1.py:196); otherwise zero-score docs fill the tail in doc-id order
  * like the dense argpartition (bm25_ranking.ipynb:211).  1 <= k <= BR_MAX_K.
  * The call synchronises `stream` before returning. */
+/* n_terms = q_offsets[nq], the number of term slots of the batch, which the caller knows from packing it (an upper
+ * bound works too); pass -1 when it is unknown - the library then reads it back from the device, which costs a
+ * stream synchronisation before any kernel of the batch is launched.  q_offsets running past n_terms is
+ * BR_ERR_INVALID. */
 #define BR_MAX_K 1024
 int br_topk_batch(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev,
-                  int32_t nq, int32_t k, int dedup, int positive_only, int32_t* out_ids_dev,
+                  int32_t nq, int32_t n_terms, int32_t k, int dedup, int positive_only, int32_t* out_ids_dev,
                   double* out_scores_dev, int32_t* out_counts_dev, void* stream);
+/* The same with the result as packed records {global doc id = doc_base + local id (-1 pads), float64 score}
+ * [nq, k]: the unit a doc-sharded caller all-gathers (one collective instead of two). */
+typedef struct br_record {
+    int64_t id;
+    double score;
+} br_record;
+int br_topk_batch_records(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq,
+                          int32_t n_terms, int32_t k, int dedup, int positive_only, br_record* out_records_dev,
+                          int32_t* out_counts_dev, void* stream);
 
 /* Exact float64 BM25 of explicit (query, doc) pairs - the arithmetic of the loop body at
  * bm25_ranking.ipynb:199-203 / team_run1.py:188-194 evaluated doc-at-a-time: query q owns the
@@ -153,6 +166,9 @@ int br_rerank_v3_scores(br_index* ix, const int32_t* q_terms_dev, const int32_t*
  * double[n_parts, nq, k]; outputs [nq, k] ordered by (score desc, id asc). */
 int br_topk_merge(const int64_t* ids_dev, const double* scores_dev, int32_t n_parts, int32_t nq,
                   int32_t k, int64_t* out_ids_dev, double* out_scores_dev, void* stream);
+/* The same over the all-gathered records of br_topk_batch_records: records_dev br_record[n_parts, nq, k]. */
+int br_topk_merge_records(const br_record* records_dev, int32_t n_parts, int32_t nq, int32_t k,
+                          int64_t* out_ids_dev, double* out_scores_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense cosine similarity on bf16 embeddings.  Replaces the re-rank block of team_run1.py:269-295
