@@ -40,6 +40,7 @@ SIGNATURES = {
     "br_row_inv_norms": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
     "br_cosine_topk": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
     "br_cosine_rerank": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "br_dedupe_first_docs": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "br_last_query_stats": (C.c_int, [_P, _P]),
     "br_set_profiling": (C.c_int, [_P, C.c_int]),
     "br_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
@@ -61,6 +62,10 @@ class QueryStats(C.Structure):
 
 class BRError(RuntimeError):
     pass
+
+
+class VocabularyNotDistinct(BRError):
+    """Vocabulary.from_terms: two terms have the same string form (e.g. the int 1 and the str "1")."""
 
 
 _lib = None

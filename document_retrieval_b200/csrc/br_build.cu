@@ -209,7 +209,7 @@ __global__ void k_export(const br_posting* __restrict__ post, const uint16_t* __
 void index_free(br_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
-    cudaFree(ix->row_ptr); cudaFree(ix->post); cudaFree(ix->post_cos); cudaFree(ix->tf); cudaFree(ix->dl); cudaFree(ix->df);
+    cudaFree(ix->row_ptr); cudaFree(ix->post); cudaFree(ix->post_cos); cudaFree(ix->cos_inv_norm); cudaFree(ix->tf); cudaFree(ix->dl); cudaFree(ix->df);
     cudaFree(ix->idf); cudaFree(ix->ub); cudaFree(ix->hot_slot); cudaFree(ix->skip); cudaFree(ix->sig_bit); cudaFree(ix->dense_rows); cudaFree(ix->row_slot);
     ix->ws_prep.release(); ix->ws_dense.release(); ix->ws_sel.release(); ix->ws_cand.release();
     ix->ws_misc.release(); ix->ws_tile.release(); ix->ws_sort.release(); ix->ws_cold.release(); ix->ws_rec.release();
@@ -381,6 +381,10 @@ int index_finalize(br_index* ix, double k1, double b, int variant, double n_stat
     BR_REQUIRE(ix, BR_ERR_INVALID, "br_index_finalize: null handle");
     BR_REQUIRE(variant >= 0 && variant <= 2, BR_ERR_INVALID, "br_index_finalize: unknown variant");
     BR_CUDA(cudaSetDevice(ix->device));
+    if (ix->post_cos) {                      // the TF-IDF tables depend on idf: rebuilt on demand after a re-finalise
+        cudaFree(ix->post_cos); cudaFree(ix->cos_inv_norm);
+        ix->post_cos = nullptr; ix->cos_inv_norm = nullptr;
+    }
     ix->k1 = k1; ix->b = b; ix->variant = variant;
     ix->n_stat = n_stat > 0 ? n_stat : (double)ix->n_docs;
     const double sum_dl = sum_dl_stat > 0 ? sum_dl_stat : (double)ix->sum_dl;

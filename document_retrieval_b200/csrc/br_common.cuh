@@ -100,6 +100,7 @@ struct br_index {
     int64_t* row_ptr = nullptr;     // [V+1]
     br_posting* post = nullptr;     // [nnz]   doc ids ascending inside a term
     br_posting* post_cos = nullptr; // [nnz]   optional TF-IDF cosine weights tf*idf^2/||d|| (br_index_enable_tfidf)
+    double* cos_inv_norm = nullptr; // [N]     1/||d|| of the doc's float32 tf*idf vector, float64 (with post_cos)
     uint16_t* tf = nullptr;         // [nnz]   raw term frequency (for the float64 re-score)
     uint32_t* dl = nullptr;         // [N]
     uint32_t* df = nullptr;         // [V]     shard-local document frequency

@@ -495,7 +495,7 @@ __global__ void k_rescore_v3(RescoreIndex r, const int32_t* __restrict__ q_off, 
 // the same packed-posting layout as BM25, scored by the same kernels.
 __global__ void k_tfidf_norm2(const int64_t* __restrict__ row_ptr, int32_t vocab, int64_t nnz,
                               const br_posting* __restrict__ post, const uint16_t* __restrict__ tf,
-                              const double* __restrict__ idf, float* __restrict__ norm2) {
+                              const double* __restrict__ idf, double* __restrict__ norm2) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nnz) return;
     int32_t lo = 0, hi = vocab;
@@ -503,12 +503,17 @@ __global__ void k_tfidf_norm2(const int64_t* __restrict__ row_ptr, int32_t vocab
         const int32_t mid = (lo + hi) >> 1;
         if (row_ptr[mid] <= j) lo = mid; else hi = mid;
     }
-    const float e = (float)((double)tf[j] * idf[lo]);        // stored as float32 in the reference's lil_matrix (:88)
-    atomicAdd(norm2 + post[j].doc, e * e);
+    const double e = (double)(float)((double)tf[j] * idf[lo]);   // stored as float32 in the reference's lil_matrix (:88)
+    atomicAdd(norm2 + post[j].doc, e * e);                      // doc_norms are float64 (scipy norm(axis=1), :210)
+}
+// norm2 -> 1/sqrt(norm2) in place (0 for an empty doc: its cosine row is all zero)
+__global__ void k_tfidf_invnorm(double* __restrict__ norm2, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) norm2[i] = norm2[i] > 0.0 ? 1.0 / sqrt(norm2[i]) : 0.0;
 }
 __global__ void k_tfidf_weights(const int64_t* __restrict__ row_ptr, int32_t vocab, int64_t nnz,
                                 const br_posting* __restrict__ post, const uint16_t* __restrict__ tf,
-                                const double* __restrict__ idf, const float* __restrict__ norm2,
+                                const double* __restrict__ idf, const double* __restrict__ inv_norm,
                                 br_posting* __restrict__ out) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nnz) return;
@@ -519,23 +524,44 @@ __global__ void k_tfidf_weights(const int64_t* __restrict__ row_ptr, int32_t voc
     }
     const uint32_t d = post[j].doc;
     const float e = (float)((double)tf[j] * idf[lo]);
-    const float n = sqrtf(norm2[d]);
     out[j].doc = d;
-    out[j].w = n > 0.f ? e * (float)idf[lo] / n : 0.f;
+    out[j].w = (float)((double)e * (double)(float)idf[lo] * inv_norm[d]);
 }
-__global__ void k_gather_dense(const float* __restrict__ dense, int64_t n_docs, const int64_t* __restrict__ cand_off,
-                               int32_t q_begin, int32_t nq, const int32_t* __restrict__ cand, double* __restrict__ out) {
+
+// Exact (float64) cosine of explicit (query, doc) candidates with the reference's mixed precision
+// (cosine_similarity_bm25_reranking.py:88,121-126,210-226): doc entries float32(tf*idf) scaled by the float64
+// 1/doc_norm, query entries float32(float32(idf) * float32(1/||q||)), products and sum in float64, terms in ascending
+// id.  ||q|| is a float32 BLAS dot in the reference (platform-dependent last bit); here float32(sqrt(float64 sum)).
+__global__ void k_rescore_cos(RescoreIndex r, const double* __restrict__ inv_norm, const int32_t* __restrict__ q_off, PrepView v,
+                              const int64_t* __restrict__ cand_off, int32_t q_begin, int32_t nq,
+                              const int32_t* __restrict__ cand, double* __restrict__ out) {
     const int64_t c0 = cand_off[q_begin], c1 = cand_off[q_begin + nq];
     for (int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t doc = cand[c];
+        if (doc < 0) continue;
         int32_t lo = q_begin, hi = q_begin + nq;
         while (hi - lo > 1) {
             const int32_t mid = (lo + hi) >> 1;
             if (cand_off[mid] <= c) lo = mid; else hi = mid;
         }
-        out[c] = (double)dense[(int64_t)(lo - q_begin) * n_docs + cand[c]];
+        const int32_t q = lo, off = q_off[q], nt = v.u_cnt[q];
+        const int32_t* terms = v.u_terms + off;              // distinct in-corpus terms, ascending
+        double n2 = 0.0;
+        for (int32_t i = 0; i < nt; ++i) { const double x = (double)(float)r.idf[terms[i]]; n2 += x * x; }
+        const float inv_q = 1.0f / (float)sqrt(n2);
+        const double inv_d = inv_norm[doc];
+        double s = 0.0;
+        for (int32_t i = 0; i < nt; ++i) {
+            const int32_t t = terms[i];
+            const int32_t tf = lookup_tf(r, t, (uint32_t)doc);
+            if (tf == 0) continue;
+            const double e = (double)(float)((double)tf * r.idf[t]);
+            const double qn = (double)((float)r.idf[t] * inv_q);
+            s = __dadd_rn(s, __dmul_rn(__dmul_rn(e, inv_d), qn));
+        }
+        out[c] = s;
     }
 }
-
 // fused path: query q owns the fixed-stride region [q*stride, (q+1)*stride), only its first cnt[q] slots are live
 __global__ void __launch_bounds__(64) k_rescore_heads(RescoreIndex r, const int32_t* __restrict__ q_off, PrepView v, int dedup,
                                                       int32_t stride, const int32_t* __restrict__ cnt,
@@ -694,8 +720,9 @@ static int topk_dense(br_index* ix, const int32_t* q_off, const PrepView& pv, co
         k_emit_cands<<<bn, SEL_T, 0, st>>>(dense, N, positive_only, sv, b0, cand_off, cand);
         BR_CUDA(cudaGetLastError());
         if (total > 0 && fp32_rank) {
-            k_gather_dense<<<(unsigned)std::min<int64_t>((total + 255) / 256, kNumSMs * 16), 256, 0, st>>>(dense, N, cand_off, b0, bn,
-                                                                                                     cand, cand_sc);
+            // TF-IDF stage: the fp32 row only selects the band; the candidates are re-scored in float64
+            k_rescore_cos<<<(unsigned)std::min<int64_t>((total + 127) / 128, kNumSMs * 16), 128, 0, st>>>(
+                rescore_view(ix), ix->cos_inv_norm, q_off, pv, cand_off, b0, bn, cand, cand_sc);
             BR_CUDA(cudaGetLastError());
         } else if (total > 0) {
             BR_TRY(launch_rescore(ix, q_off, pv, dedup, cand_off, b0, bn, cand, cand_sc, total, st));
@@ -821,22 +848,23 @@ int enable_tfidf(br_index* ix, cudaStream_t st) {
     BR_REQUIRE(ix && ix->finalized, BR_ERR_STATE, "br_index_enable_tfidf: call br_index_finalize first");
     if (ix->post_cos) return BR_OK;
     BR_CUDA(cudaSetDevice(ix->device));
-    float* norm2 = nullptr;
-    BR_CUDA(cudaMalloc(&norm2, sizeof(float) * (size_t)ix->n_docs));
+    BR_CUDA(cudaMalloc(&ix->cos_inv_norm, sizeof(double) * (size_t)ix->n_docs));
     if (cudaMalloc(&ix->post_cos, sizeof(br_posting) * (size_t)std::max<int64_t>(ix->nnz, 1)) != cudaSuccess) {
-        cudaFree(norm2);
+        cudaFree(ix->cos_inv_norm);
+        ix->cos_inv_norm = nullptr;
+        ix->post_cos = nullptr;
         set_error("br_index_enable_tfidf: out of device memory");
         return BR_ERR_CUDA;
     }
-    cudaMemsetAsync(norm2, 0, sizeof(float) * (size_t)ix->n_docs, st);
+    BR_CUDA(cudaMemsetAsync(ix->cos_inv_norm, 0, sizeof(double) * (size_t)ix->n_docs, st));
     if (ix->nnz > 0) {
-        k_tfidf_norm2<<<blocks_for(ix->nnz, 256), 256, 0, st>>>(ix->row_ptr, ix->vocab, ix->nnz, ix->post, ix->tf, ix->idf, norm2);
-        k_tfidf_weights<<<blocks_for(ix->nnz, 256), 256, 0, st>>>(ix->row_ptr, ix->vocab, ix->nnz, ix->post, ix->tf, ix->idf, norm2,
-                                                                  ix->post_cos);
+        k_tfidf_norm2<<<blocks_for(ix->nnz, 256), 256, 0, st>>>(ix->row_ptr, ix->vocab, ix->nnz, ix->post, ix->tf, ix->idf,
+                                                                ix->cos_inv_norm);
+        k_tfidf_invnorm<<<blocks_for(ix->n_docs, 256), 256, 0, st>>>(ix->cos_inv_norm, ix->n_docs);
+        k_tfidf_weights<<<blocks_for(ix->nnz, 256), 256, 0, st>>>(ix->row_ptr, ix->vocab, ix->nnz, ix->post, ix->tf, ix->idf,
+                                                                  ix->cos_inv_norm, ix->post_cos);
     }
-    const cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(norm2);
-    BR_CUDA(e);
+    BR_CUDA(cudaStreamSynchronize(st));
     BR_CUDA(cudaGetLastError());
     return BR_OK;
 }
@@ -845,6 +873,8 @@ int tfidf_topk(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
                double* out_scores, int32_t* out_counts, cudaStream_t st) {
     BR_REQUIRE(ix && q_terms && q_off && out_ids && out_scores, BR_ERR_INVALID, "br_tfidf_cosine_topk: null pointer");
     BR_REQUIRE(k >= 1 && k <= BR_MAX_K && nq >= 0, BR_ERR_INVALID, "br_tfidf_cosine_topk: bad sizes");
+    BR_REQUIRE(ix, BR_ERR_INVALID, "br_tfidf_cosine_topk: null handle");
+    BR_CUDA(cudaSetDevice(ix->device));
     BR_TRY(enable_tfidf(ix, st));
     if (nq == 0) return BR_OK;
     ix->stats = br_query_stats{};

@@ -858,7 +858,7 @@ __device__ __forceinline__ void make_plan(const PlanArgs& pa, int q, float thr, 
 // is a valid lower bound of the K-th best score, and the first launches already run with a deferral plan instead of
 // streaming every term against a zero threshold.  One warp per query; a running top-32 is kept sorted across the lanes
 // (each batch of 32 weights is sorted, reversed and merged bitonically).
-constexpr int SEED_MAX = 1024;
+constexpr int SEED_MAX = 256;
 __global__ void __launch_bounds__(128) k_seed_thr(const br_posting* __restrict__ post, const int64_t* __restrict__ row_ptr,
                                                   int32_t nq, int K, const int32_t* __restrict__ elig, float* __restrict__ thr,
                                                   PlanArgs pa) {
@@ -867,8 +867,8 @@ __global__ void __launch_bounds__(128) k_seed_thr(const br_posting* __restrict__
     if (q >= nq || !elig[q]) return;
     const int32_t off = pa.q_off[q], nu = pa.u_cnt[q];
     float best = 0.f;
-    for (int j = 0; j < nu; ++j) {
-        const int32_t t = pa.u_terms[off + j];
+    for (int j = nu - 1; j >= 0; --j) {         // descending term id: in a frequency-ranked vocabulary the rare (high-bound)
+        const int32_t t = pa.u_terms[off + j];  // terms come first and the frequent ones are then skipped by the ub test
         const float m = (float)pa.u_mult[off + j];
         const int64_t lo = row_ptr[t], df = row_ptr[t + 1] - lo;
         if (df < K || !(pa.ub[t] * m > best)) continue;            // cannot raise the bound
@@ -894,8 +894,8 @@ __global__ void __launch_bounds__(128) k_seed_thr(const br_posting* __restrict__
 
 // Between chunks: thr[q] = max(thr[q], K-th best fp32 score emitted so far); keep only the candidates
 // inside the band of the new threshold (sorted by score); sticky overflow flag.
-constexpr int TG_T = 256;
-__global__ void __launch_bounds__(TG_T) k_tighten(float* __restrict__ thr, int32_t* __restrict__ cand_cnt,
+constexpr int TG_T = 256, TGS_T = 64;
+__global__ void __launch_bounds__(TGS_T) k_tighten(float* __restrict__ thr, int32_t* __restrict__ cand_cnt,
                                                   int32_t* __restrict__ prev_cnt, int32_t* __restrict__ cand,
                                                   float* __restrict__ cand_h, int K, int32_t* __restrict__ overflow,
                                                   PlanArgs pa) {
@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(TG_T) k_tighten(float* __restrict__ thr, int32
     float* hs = cand_h + (int64_t)q * TILE_CAP;
     int n_sort = 32;                                   // smallest power of two covering the list
     while (n_sort < n) n_sort <<= 1;
-    for (int i = threadIdx.x; i < n_sort; i += TG_T) {
+    for (int i = threadIdx.x; i < n_sort; i += TGS_T) {
         s_h[i] = i < n ? hs[i] : -1.f;
         s_id[i] = i < n ? ids[i] : -1;
     }
@@ -921,7 +921,7 @@ __global__ void __launch_bounds__(TG_T) k_tighten(float* __restrict__ thr, int32
     for (int size = 2; size <= n_sort; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
-            for (int i = threadIdx.x; i < n_sort / 2; i += TG_T) {
+            for (int i = threadIdx.x; i < n_sort / 2; i += TGS_T) {
                 const int x = 2 * i - (i & (stride - 1)), y = x + stride;
                 const bool up = (x & size) == 0;
                 const float hx = s_h[x], hy = s_h[y];
@@ -937,12 +937,12 @@ __global__ void __launch_bounds__(TG_T) k_tighten(float* __restrict__ thr, int32
     if (n >= K && s_h[K - 1] > th) th = s_h[K - 1];
     const float lo = th * (1.f - kBandRel);
     int keep = 0;
-    for (int i = threadIdx.x; i < n; i += TG_T) keep += (s_h[i] >= lo) ? 1 : 0;
+    for (int i = threadIdx.x; i < n; i += TGS_T) keep += (s_h[i] >= lo) ? 1 : 0;
     for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
     if ((threadIdx.x & 31) == 0 && keep) atomicAdd(&s_keep, keep);
     __syncthreads();
     keep = s_keep;
-    for (int i = threadIdx.x; i < n; i += TG_T) {
+    for (int i = threadIdx.x; i < n; i += TGS_T) {
         ids[i] = i < keep ? s_id[i] : -1;
         hs[i] = i < keep ? s_h[i] : 0.f;
     }
@@ -1088,7 +1088,7 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
         BR_CUDA(cudaGetLastError());
         ix->prof_end(st);
         if (big) k_tighten_big<<<a0.nq, TG_T, 8 * (size_t)a0.cap, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, a0.cap, overflow, pa);
-        else k_tighten<<<a0.nq, TG_T, 0, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, overflow, pa);
+        else k_tighten<<<a0.nq, TGS_T, 0, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, overflow, pa);
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 2;
         t0 += ny;

@@ -99,6 +99,93 @@ def rank_documents_with_cosine_similarity_and_bm25(corpus, train_query, tf_dict,
     return out
 
 
+def _lang_models_for(tf_dict, corpus, corpus_lang):
+    """Per-language sub-indexes of the corpus ``tf_dict`` came from, finalised with the GLOBAL statistics (N, sum of doc
+    lengths, df): the TF-IDF cosine and the re-rank score of a doc depend only on its own tf and on global idf / avgdl,
+    so ranking inside one of these equals ranking the whole corpus and dropping the other languages."""
+    import torch
+    model, doc_ids = _model_for(tf_dict, corpus)
+    cache = getattr(model, "_lang_models", None)
+    if cache is not None and cache[0] is corpus_lang:
+        return model, doc_ids, cache[1]
+    c = model._export_csr()
+    df_global = np.diff(c["row_ptr"]).astype(np.int64)
+    n_global, sum_dl = model.corpus_size, int(c["dl"].sum())
+    vocab = model.vocab
+    by_lang = {}
+    for i, d in enumerate(doc_ids):
+        by_lang.setdefault(corpus_lang[d], []).append(i)
+    texts = list(corpus["preprocessed_text"])
+    out = {}
+    for lang, idxs in by_lang.items():
+        toks = [[vocab[w] for w in str(texts[i]).split()] for i in idxs]
+        off = np.zeros(len(idxs) + 1, np.int64)
+        np.cumsum([len(t) for t in toks], out=off[1:])
+        flat = np.fromiter((t for ts in toks for t in ts), dtype=np.int32, count=int(off[-1]))
+        m = BM25.from_token_ids(off, flat, model.vocab_size, model.k1, model.b, variant="okapi_no_plus1",
+                                dedup_query=False, device=model._device, finalize=False)
+        m.finalize(n_global, sum_dl, df_global)
+        m.terms = model.terms
+        out[lang] = (m, [doc_ids[i] for i in idxs])
+    model._lang_models = (corpus_lang, out)
+    return model, doc_ids, out
+
+
+def rank_documents_with_cosine_similarity_and_bm25_lang(corpus, train_query, tf_dict, idf_dict, avgdl, corpus_lang,
+                                                        batch_size=400, n_candidates=1000, k=100):
+    """The language-filtered variant, text_preprocessing_and_embedding_setup.py:264-389: candidates are the first
+    ``n_candidates`` (1000, :342) docs OF THE QUERY'S LANGUAGE in descending TF-IDF cosine order (:333-343), re-scored
+    with bm25_score (:345-346) and sorted descending, first ``k`` (100, :349-352).  ``corpus_lang`` maps docid ->
+    language; ``train_query`` has columns id / preprocessed_query / lang.
+    -> ``(ranked_documents_dict, query_lang_dict)`` like the reference.  Each language is a GPU sub-index finalised with
+    the global statistics, so no other-language doc is ever scored."""
+    import torch
+    _, _, lang_models = _lang_models_for(tf_dict, corpus, corpus_lang)
+    q_ids = list(train_query["id"])
+    q_lang = list(train_query["lang"])
+    queries = [str(t).split() for t in train_query["preprocessed_query"]]
+    ranked, query_lang_dict = {}, {}
+    by_lang = {}
+    for i, lang in enumerate(q_lang):
+        by_lang.setdefault(lang, []).append(i)
+        query_lang_dict[q_ids[i]] = lang
+    for lang, idxs in by_lang.items():
+        if lang not in lang_models:
+            for i in idxs:
+                ranked[q_ids[i]] = []
+            continue
+        m, ids_l = lang_models[lang]
+        n_cand = min(n_candidates, m.corpus_size)
+        for s in range(0, len(idxs), batch_size):
+            chunk = idxs[s:s + batch_size]
+            qs = [queries[i] for i in chunk]
+            cand, _ = m.tfidf_cosine_top_n_batch(qs, n_cand)
+            v3 = m.rerank_scores_v3(qs, cand)
+            v3 = torch.where(cand >= 0, v3, torch.full_like(v3, float("-inf")))
+            order = torch.sort(v3, dim=1, descending=True, stable=True).indices[:, :k]
+            top = torch.gather(cand, 1, order).cpu().numpy()
+            for i, row in zip(chunk, top):
+                ranked[q_ids[i]] = [ids_l[int(d)] for d in row if d >= 0]
+    return {qid: ranked[qid] for qid in q_ids}, query_lang_dict
+
+
+def per_language_recall(ranked_docs, positive_docs, query_lang_dict, query_ids=None):
+    """text_preprocessing_and_embedding_setup.py:534-562: overall fraction of queries whose positive doc is in the
+    ranked list and the same per language.  ``ranked_docs`` {query_id: [docid]}; ``positive_docs`` aligned with
+    ``query_ids`` (default: the dict's order).  -> ``(overall, {lang: fraction})``"""
+    query_ids = list(ranked_docs.keys()) if query_ids is None else list(query_ids)
+    per_q, per_hit, hits = {}, {}, 0
+    for qid, pos in zip(query_ids, positive_docs):
+        lang = query_lang_dict[qid]
+        per_q[lang] = per_q.get(lang, 0) + 1
+        per_hit.setdefault(lang, 0)
+        if pos in ranked_docs[qid]:
+            hits += 1
+            per_hit[lang] += 1
+    n = len(query_ids)
+    return (hits / n if n else 0), {lang: per_hit[lang] / per_q[lang] for lang in per_q}
+
+
 def compute_idf(df_dict, num_docs):
     """cosine_similarity_bm25_reranking.py:176-182: ``{term: np.log((N - df + .5) / (df + .5))}`` - no
     +1, negative when df > N/2.  A dict-to-dict host function (V logs); the device-side idf of an

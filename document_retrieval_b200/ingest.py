@@ -136,7 +136,10 @@ class Vocabulary:
     @classmethod
     def from_terms(cls, terms, bigrams=False, device=None):
         """Vocabulary with term id = position in ``terms`` (distinct strings)."""
-        data, off = pack_texts(list(terms))
+        terms = [str(t) for t in terms]
+        if len(set(terms)) != len(terms):
+            raise _lib.VocabularyNotDistinct("vocabulary terms are not distinct as strings")
+        data, off = pack_texts(terms)
         self = cls.__new__(cls)
         self.__setstate__(dict(pool_off=off, pool=data, bigrams=bigrams))
         return self

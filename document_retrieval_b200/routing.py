@@ -15,6 +15,8 @@ from collections import defaultdict
 
 import numpy as np
 
+from ._lib import VocabularyNotDistinct
+
 
 def _default_preprocess(query, lang):
     if isinstance(query, str):
@@ -81,7 +83,7 @@ def _batched_top(bm25_models, rows, k, preprocess, batch_size):
                 # vocabulary lookup run on the GPU for the whole chunk
                 try:
                     ids, _ = model.retrieve_top_n_texts(qs, kk)
-                except RuntimeError:                 # e.g. a vocabulary whose str() forms are not distinct
+                except VocabularyNotDistinct:        # term strings collide: look the tokens up on the host instead
                     ids, _ = model.retrieve_top_n_batch([preprocess(q, lang) for q in qs], kk)
             else:
                 ids, _ = model.retrieve_top_n_batch([preprocess(q, lang) for q in qs], kk)
@@ -132,27 +134,6 @@ def retrieve_top_n_batch(args):
         return [bm25_model.retrieve_top_n(q, n=k) for q in tokenized_query_batch]
     ids, _ = bm25_model.retrieve_top_n_batch(tokenized_query_batch, k)
     return [r.astype(np.int64) for r in ids.cpu().numpy()]
-
-
-def dedupe_sentences_to_docs(sentence_ids, sentence_to_doc, k=10):
-    """team_run1.py:286-294: walk the ranked sentences, keep the first occurrence of every parent doc, stop
-    at ``k`` docs.  ``sentence_ids`` [Q, n] (best first, -1 pads; numpy or torch), ``sentence_to_doc`` maps a
-    sentence index to its doc index -> int64[Q, k] (-1 pads).  Vectorised on the device the ids live on."""
-    import torch
-    s = torch.as_tensor(sentence_ids)
-    m = torch.as_tensor(sentence_to_doc).to(s.device)
-    valid = s >= 0
-    docs = torch.where(valid, m[s.clamp(min=0).long()], torch.full_like(s, -1, dtype=m.dtype)).long()
-    # first occurrence: no equal doc earlier in the row
-    eq = docs[:, :, None] == docs[:, None, :]
-    earlier = torch.tril(torch.ones(s.shape[1], s.shape[1], dtype=torch.bool, device=s.device), diagonal=-1)
-    first = valid & ~(eq & earlier[None]).any(dim=2)
-    rank = torch.cumsum(first.long(), dim=1) - 1
-    out = torch.full((s.shape[0], k), -1, dtype=torch.long, device=s.device)
-    keep = first & (rank < k)
-    rows = torch.arange(s.shape[0], device=s.device)[:, None].expand_as(s)
-    out[rows[keep], rank[keep]] = docs[keep]
-    return out
 
 
 def mrr_recall_at_k(ranked_docs, relevant_docs, k_values=(1, 5, 10)):

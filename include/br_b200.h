@@ -148,9 +148,11 @@ int br_rescore_docs(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_o
  * (create_tfidf_embedding :72-110, doc_norms :210-211).  Idempotent. */
 int br_index_enable_tfidf(br_index* ix, void* stream);
 /* First stage: top-k docs by TF-IDF cosine against the query vector "idf per distinct in-corpus term"
- * (generate_query_embedding :121-126).  out_scores_dev double[nq,k] = fp32 sum_t w'[d,t]
- * (= cosine * ||q||); order (score desc, doc id asc); zero-score docs fill a short tail in doc order
- * like the full argsort (:229).  Synchronises `stream`. */
+ * (generate_query_embedding :121-126).  The fp32 accumulation of w' only selects a candidate band; every band
+ * member is re-scored in float64 with the reference's mixed precision (float32 tf*idf entries, float64 doc norms,
+ * float32 normalised query, float64 products, :88,210-226), so the top-k SET is the reference's wherever its own
+ * order is defined.  out_scores_dev double[nq,k] = that cosine; order (cosine desc, doc id asc); zero-cosine docs
+ * fill a short tail in doc order like the full argsort (:229).  Synchronises `stream`. */
 int br_tfidf_cosine_topk(br_index* ix, const int32_t* q_terms_dev, const int32_t* q_offsets_dev, int32_t nq,
                          int32_t k, int32_t* out_ids_dev, double* out_scores_dev, int32_t* out_counts_dev,
                          void* stream);
@@ -194,6 +196,13 @@ int br_cosine_topk(const void* docs_bf16_dev, const float* doc_inv_norm_dev, int
 int br_cosine_rerank(const void* docs_bf16_dev, const float* doc_inv_norm_dev, int64_t n_docs, int32_t d,
                      const void* queries_bf16_dev, int32_t nq, const int32_t* cand_ids_dev, int32_t c,
                      int32_t k, int32_t* out_ids_dev, float* out_sims_dev, void* stream);
+
+/* Sentence -> document step of the sentence-level retrieval (team_run1.py:286-294): for every query walk its ranked
+ * sentences sentence_ids_dev int64[nq, n] (best first, -1 = padding), map each to its parent doc through
+ * sentence_to_doc_dev int32[n_sentences], keep the first occurrence of every doc and stop at k docs (k <= 32; the
+ * reference uses 10).  out_docs_dev int64[nq, k], -1 pads.  Synchronises `stream`. */
+int br_dedupe_first_docs(const int64_t* sentence_ids_dev, const int32_t* sentence_to_doc_dev, int64_t n_sentences,
+                         int32_t nq, int32_t n, int32_t k, int64_t* out_docs_dev, void* stream);
 
 /* Counters of the last br_topk_batch call on this handle (bench / tests): kernels launched,
  * queries served by the fused tiled path, by the dense path, and candidate rows re-scored. */

@@ -216,3 +216,80 @@ def cosine_topk(doc_emb, query_emb, k: int):
         o = np.lexsort((np.arange(sims.shape[1]), -sims[i]))[:k]
         ids[i], val[i] = o, sims[i, o]
     return ids, val
+
+
+def tfidf_cosine_scores(ix: OracleIndex, q_terms, idf: np.ndarray) -> np.ndarray:
+    """Sparse TF-IDF cosine of one query against every doc, cosine_similarity_bm25_reranking.py:72-110,121-126,
+    210-226, with the reference's mixed precision (probed with scipy 1.18): doc vector ``float32(tf * idf)``
+    (lil_matrix float32, :88); ``doc_norms`` float64 (sqrt of the float64 sum of squares, :210); query vector
+    ``float32(idf)`` per DISTINCT in-corpus term (set, not add, :121-126) times the float32 scalar ``1/norm(q)``
+    (:222-223); the product ``normalized.dot(q.T)`` is float64 (:226).  A zero-norm doc gives 0.  -> float64[N]"""
+    ts = np.unique(np.asarray([int(t) for t in q_terms if 0 <= int(t) < ix.vocab and ix.row_ptr[int(t) + 1] > ix.row_ptr[int(t)]],
+                              dtype=np.int64))
+    out = np.zeros(ix.n_docs, np.float64)
+    if ts.size == 0:
+        return out
+    q = idf[ts].astype(np.float32)
+    qnorm = np.linalg.norm(q)           # float32, what scipy.sparse.linalg.norm returns for the float32 query row (BLAS sdot)
+    qn = (q * np.float32(np.float32(1.0) / qnorm)).astype(np.float32)
+    norm2 = doc_sq_norms(ix, idf)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / np.sqrt(norm2)
+    for j, t in enumerate(ts):                                   # ascending term id
+        lo, hi = int(ix.row_ptr[t]), int(ix.row_ptr[t + 1])
+        d = ix.post_doc[lo:hi]
+        e = (ix.post_tf[lo:hi].astype(np.float64) * float(idf[t])).astype(np.float32).astype(np.float64)
+        out[d] += (e * inv[d]) * float(qn[j])
+    return np.nan_to_num(out, nan=0.0, posinf=0.0, neginf=0.0)
+
+
+def doc_sq_norms(ix: OracleIndex, idf: np.ndarray) -> np.ndarray:
+    """float64 sum over the doc's terms of float32(tf*idf)^2 (the square of ``doc_norms``, :210)."""
+    cache = getattr(ix, "_sq_norms", None)
+    if cache is not None and cache[0] is idf:
+        return cache[1]
+    term_of = np.repeat(np.arange(ix.vocab), np.diff(ix.row_ptr))
+    e = (ix.post_tf.astype(np.float64) * np.nan_to_num(idf[term_of])).astype(np.float32).astype(np.float64)
+    n2 = np.zeros(ix.n_docs, np.float64)
+    np.add.at(n2, ix.post_doc, e * e)
+    try:
+        ix._sq_norms = (idf, n2)
+    except Exception:
+        pass
+    return n2
+
+
+def rank_cosine_then_bm25(ix: OracleIndex, queries, idf: np.ndarray, avgdl: float, n_candidates=200, k=10,
+                          doc_lang=None, query_lang=None):
+    """rank_documents_with_cosine_similarity_and_bm25, cosine_similarity_bm25_reranking.py:198-238: cosine over the
+    whole corpus -> first ``n_candidates`` of the descending order (:229; canonical order (cosine desc, doc id asc)) ->
+    bm25_score of the candidates (:232-233) -> stable descending sort, first ``k`` (:234).  With ``doc_lang`` /
+    ``query_lang`` the candidates are the first ``n_candidates`` docs OF THE QUERY'S LANGUAGE in that order
+    (text_preprocessing_and_embedding_setup.py:333-343; there n_candidates = 1000 and k = 100, :349).
+    ``queries`` is a list of term-id lists.  -> list of (ids int64[<=k], cand ids, cand cosines)"""
+    out = []
+    ids = np.arange(ix.n_docs)
+    for i, q in enumerate(queries):
+        cos = tfidf_cosine_scores(ix, q, idf)
+        order = np.lexsort((ids, -cos))
+        if doc_lang is not None:
+            order = order[np.asarray(doc_lang)[order] == query_lang[i]]
+        cand = order[:n_candidates]
+        sc = np.array([bm25_score_rerank(ix, q, int(d), idf, avgdl) for d in cand], dtype=np.float64)
+        o = np.argsort(-sc, kind="stable")[:k]
+        out.append((cand[o].astype(np.int64), cand.astype(np.int64), cos[cand]))
+    return out
+
+
+def per_language_recall(ranked_docs, positives, query_langs):
+    """text_preprocessing_and_embedding_setup.py:534-562: overall hit rate and hits / queries per language."""
+    per_q, per_hit = {}, {}
+    hits = 0
+    for r, p, lang in zip(ranked_docs, positives, query_langs):
+        per_q[lang] = per_q.get(lang, 0) + 1
+        per_hit.setdefault(lang, 0)
+        if p in list(r):
+            hits += 1
+            per_hit[lang] += 1
+    n = len(positives)
+    return (hits / n if n else 0), {lang: per_hit[lang] / per_q[lang] for lang in per_q}

@@ -153,12 +153,32 @@ def rerank_fixture(do, tk, vocab, qo, qt):
                 pair_scores[i, j] = ns["bm25_score"](qs[i], f"d{int(pair_docs[i, j])}", tf_dict, idf_dict, avgdl)
         ranked = ns["rank_documents_with_cosine_similarity_and_bm25"](corpus, queries, tf_dict, idf_dict, avgdl,
                                                                       batch_size=16)
+        # the candidate stage the ranker does not return: its own embedding functions (unmodified) + the four lines
+        # of cosine_similarity_bm25_reranking.py:210-211,222-226 -> float64 cosines, then `argsort()[::-1][:200]` (:229)
+        from scipy.sparse import csr_matrix, vstack
+        from scipy.sparse.linalg import norm
+        term_index = {term: idx for idx, term in enumerate(tf_dict.keys())}
+        emb, emb_ids = ns["create_tfidf_embedding"](corpus, tf_dict, idf_dict, term_index)
+        emb = emb.tocsr()
+        assert emb_ids == list(corpus["docid"])
+        doc_norms = norm(emb, axis=1).reshape(-1, 1)
+        normalized = emb.multiply(1 / doc_norms)
+        qe = []
+        for text in queries["preprocessed_query"]:
+            q = ns["generate_query_embedding"](text, tf_dict, idf_dict, term_index)
+            qe.append(q.multiply(1 / norm(q)))
+        cos = normalized.dot(csr_matrix(vstack(qe)).T).toarray()          # [N, nq] float64
+        cos = np.nan_to_num(cos, nan=0.0)
+        n_c = min(200, n_docs)
+        cos_top = np.stack([np.argsort(cos[:, i])[::-1][:n_c] for i in range(nq)]).astype(np.int64)
+        cos_all = cos.T.copy()                                            # [nq, N]
         top10 = np.full((nq, 10), -1, np.int64)
         for i in range(nq):
             ids = [int(d[1:]) for d in ranked[i]]
             top10[i, :len(ids)] = ids
     np.savez_compressed(os.path.join(HERE, "rerank_v3.npz"), df=df, idf=idf, avgdl=avgdl, num_docs=num_docs,
-                        term_order=term_order, pair_docs=pair_docs, pair_scores=pair_scores, top10=top10)
+                        term_order=term_order, pair_docs=pair_docs, pair_scores=pair_scores, top10=top10,
+                        cos_top200=cos_top, cos_all=cos_all)
     print("rerank_v3", nq, "queries")
 
 
@@ -202,6 +222,10 @@ def cosine_fixture():
 
 def main():
     assert ref_loader.available(), "reference checkout not found"
+    if "--rerank-only" in sys.argv:           # refresh rerank_v3.npz alone (inputs come from the stored nb_small fixture)
+        g = np.load(os.path.join(HERE, "nb_small.npz"))
+        rerank_fixture(g["doc_offsets"], g["token_ids"], 400, g["q_offsets"], g["q_terms"])
+        return
     do, tk, qo, qt, _ = notebook_fixture("nb_small", 300, 400, 30, 40, (101,), keep_scores=True)
     team_run1_fixture(do, tk, 400, qo, qt)
     rerank_fixture(do, tk, 400, qo, qt)

@@ -362,3 +362,72 @@ def test_massive_ties_fall_back_exactly(k):
     ids2, sc2 = m2.retrieve_top_n_batch((np.asarray([0], np.int32), np.asarray([0, 1], np.int32)), k)
     want = np.arange(0, n, 7)[:k]
     assert np.array_equal(ids2.cpu().numpy()[0][:want.size], want)
+
+
+def test_tfidf_candidate_stage_is_exact(golden):
+    """a11: the TF-IDF cosine stage returns the reference's top-200 candidate SET (float64 cosine, band + re-score)
+    and its cosines, cosine_similarity_bm25_reranking.py:210-229.  The query norm is a float32 BLAS dot in the
+    reference (platform-dependent last bit), hence 3e-7 on the values and on what counts as a tie at the cut."""
+    from document_retrieval_b200 import BM25
+    g, r = golden("nb_small"), golden("rerank_v3")
+    m = BM25.from_token_ids(g["doc_offsets"], g["token_ids"], int(g["vocab"]), variant="okapi_no_plus1", dedup_query=False)
+    ids, sc = m.tfidf_cosine_top_n_batch((g["q_terms"], g["q_offsets"]), 200)
+    ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+    nq = g["q_offsets"].size - 1
+    checked = 0
+    for i in range(nq):
+        cos = r["cos_all"][i]
+        srt = np.sort(cos)[::-1]
+        np.testing.assert_allclose(sc[i], cos[ids[i]], rtol=3e-7, atol=1e-12)
+        assert np.all(np.diff(sc[i]) <= 0)
+        if srt[199] - srt[200] > 3e-7 * max(srt[199], 1e-30):
+            assert set(ids[i].tolist()) == set(r["cos_top200"][i].tolist()), i
+            checked += 1
+        else:                                          # tie at the cut (zero cosines): everything strictly above it must be in
+            must = set(np.flatnonzero(cos > srt[199] * (1 + 3e-7)).tolist())
+            assert must <= set(ids[i].tolist())
+    assert checked >= 35
+
+
+def test_language_filtered_pipeline_and_per_language_recall(golden):
+    """text_preprocessing_and_embedding_setup.py:333-352,534-562: candidates restricted to the query's language
+    (per-language GPU sub-indexes finalised with the global statistics) against the numpy restatement."""
+    import pandas as pd
+    from document_retrieval_b200 import (compute_idf, compute_tf_df_and_avgdl, per_language_recall,
+                                         rank_documents_with_cosine_similarity_and_bm25_lang)
+    g, r = golden("nb_small"), golden("rerank_v3")
+    vocab = int(g["vocab"])
+    docs = synth.to_strings(g["doc_offsets"], g["token_ids"])
+    qs = synth.queries_to_strings(g["q_offsets"], g["q_terms"], vocab)
+    langs = ["en", "fr", "de"]
+    doc_lang = {f"d{i}": langs[i % 3] for i in range(len(docs))}
+    corpus = pd.DataFrame({"docid": [f"d{i}" for i in range(len(docs))], "preprocessed_text": [" ".join(d) for d in docs]})
+    ql = [langs[i % 3] if i % 7 else "xx" for i in range(len(qs))]          # "xx": a language without docs
+    queries = pd.DataFrame({"id": list(range(len(qs))), "preprocessed_query": [" ".join(q) for q in qs], "lang": ql})
+    tf_dict, df_dict, avgdl, num_docs = compute_tf_df_and_avgdl(corpus)
+    idf_dict = compute_idf(df_dict, num_docs)
+    ranked, qlang = rank_documents_with_cosine_similarity_and_bm25_lang(corpus, queries, tf_dict, idf_dict, avgdl, doc_lang,
+                                                                        batch_size=16, n_candidates=40, k=10)
+    assert qlang == dict(enumerate(ql))
+    ix = orc.build_index(g["doc_offsets"], g["token_ids"], vocab)
+    lang_arr = np.array([doc_lang[f"d{i}"] for i in range(len(docs))])
+    q_ids = [g["q_terms"][g["q_offsets"][i]:g["q_offsets"][i + 1]] for i in range(len(qs))]
+    want = orc.rank_cosine_then_bm25(ix, q_ids, r["idf"], float(r["avgdl"]), n_candidates=40, k=10, doc_lang=lang_arr, query_lang=ql)
+    checked = 0
+    for i in range(len(qs)):
+        mine = [int(d[1:]) for d in ranked[i]]
+        if ql[i] == "xx":
+            assert mine == []
+            continue
+        assert all(lang_arr[d] == ql[i] for d in mine)
+        ref_ids, cand, cos = want[i]
+        if cos.size == 40 and cos[-1] > 0:             # cut not inside the zero-cosine tail
+            sc = [orc.bm25_score_rerank(ix, q_ids[i], int(d), r["idf"], float(r["avgdl"])) for d in ref_ids]
+            if all(abs(a - b) > 1e-9 * max(abs(a), 1e-30) for a, b in zip(sc[:-1], sc[1:])):
+                assert mine == ref_ids.tolist(), i
+                checked += 1
+    assert checked >= 15
+    pos = [f"d{int(x)}" for x in g["qrels"]] + ["d0"] * (len(qs) - g["qrels"].size)
+    got = per_language_recall(ranked, pos, qlang)
+    exp = orc.per_language_recall([ranked[i] for i in range(len(qs))], pos, ql)
+    assert got == exp

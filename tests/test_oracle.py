@@ -99,6 +99,39 @@ def test_rerank_v3(golden):
             np.testing.assert_allclose(got, r["pair_scores"][i, j], rtol=1e-13, atol=0)
 
 
+def test_tfidf_cosine_pipeline(golden):
+    """cosine_similarity_bm25_reranking.py:198-238 restated (tfidf_cosine_scores / rank_cosine_then_bm25) against the
+    reference's own float64 cosine matrix, its top-200 candidates and its final top-10."""
+    g, r = golden("nb_small"), golden("rerank_v3")
+    ix = orc.build_index(g["doc_offsets"], g["token_ids"], int(g["vocab"]))
+    nq = g["q_offsets"].size - 1
+    qs = [_q(g, i) for i in range(nq)]
+    for i in range(nq):
+        np.testing.assert_allclose(orc.tfidf_cosine_scores(ix, qs[i], r["idf"]), r["cos_all"][i], rtol=0, atol=2e-15)
+    res = orc.rank_cosine_then_bm25(ix, qs, r["idf"], float(r["avgdl"]), n_candidates=200, k=10)
+    defined = 0
+    for i in range(nq):
+        srt = np.sort(r["cos_all"][i])[::-1]
+        if srt[199] > srt[200]:                       # the reference's own cut is not inside a tie
+            assert set(res[i][1].tolist()) == set(r["cos_top200"][i].tolist())
+            defined += 1
+        if srt[9] > 0:
+            assert res[i][0].tolist() == [int(d) for d in r["top10"][i] if d >= 0]
+    assert defined >= 35
+    # language filter: restricting the order to one language == ranking that language's docs alone
+    lang = np.arange(ix.n_docs) % 3
+    ql = [i % 3 for i in range(nq)]
+    fl = orc.rank_cosine_then_bm25(ix, qs, r["idf"], float(r["avgdl"]), n_candidates=50, k=10, doc_lang=lang, query_lang=ql)
+    for i in range(nq):
+        assert all(lang[d] == ql[i] for d in fl[i][1])
+        cos = r["cos_all"][i]
+        mine = np.flatnonzero(lang == ql[i])
+        want = mine[np.lexsort((mine, -cos[mine]))][:50]
+        assert fl[i][1].tolist() == want.tolist()
+    overall, per = orc.per_language_recall([[1, 2], [3], [4]], [2, 9, 4], ["en", "en", "fr"])
+    assert overall == 2 / 3 and per == {"en": 0.5, "fr": 1.0}
+
+
 def test_cosine_oracle(golden):
     import torch
     g = golden("cosine_small")
