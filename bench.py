@@ -208,7 +208,7 @@ def cpu_oracle_run(args, doc_offsets_h, token_ids_h, q_terms, q_off, n_sample, t
 
 
 
-def secondary_benchmarks(args, dev, rank, world, dist_on):
+def secondary_benchmarks(args, dev, rank, world, dist_on, model=None, q_dev=None, ids_ref=None):
     """Figures of the other rows of the hot path, measured in the same run so that they are on the driver's record
     (each with its own clock samples): the brute-force cosine GEMM (BASELINE config 5: 1.25 M x 768 bf16 rows per GPU,
     10k queries - the whole 10 M-row config when run on 8 GPUs), the candidate re-rank (config 3) and the index file."""
@@ -337,6 +337,33 @@ def secondary_benchmarks(args, dev, rank, world, dist_on):
             "rerank_GB/s": bytes3 / (ms_r * 1e-3) / 1e9, "rerank_frac_of_hbm": bytes3 / (ms_r * 1e-3) / 1e9 / hbm,
             "note": "re-rank algorithmic bytes = c*D*2 + D*2 + 8k per query (SURVEY 8d); gather-bound", "clocks": clocks3}
         del m3, ci, emb
+        torch.cuda.empty_cache()
+    # ---- index file: BM25.save / BM25.load of this run's index (flat binary, no pickle) - the step whose joblib
+    # counterpart took the reference longer than its retrieval (bm25_ranking.ipynb:222-251)
+    if rank == 0 and world == 1 and model is not None:
+        import tempfile
+        from document_retrieval_b200 import BM25
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "index.brix")
+            torch.cuda.synchronize()
+            t0 = time.time()
+            model.save(path)
+            save_s = time.time() - t0
+            nbytes = os.path.getsize(path)
+            t0 = time.time()
+            m2 = BM25.load(path, device=dev)
+            torch.cuda.synchronize()
+            load_s = time.time() - t0
+            ns = min(256, args.queries)
+            d_terms, d_off, q_off_h = q_dev
+            i2, _ = m2.retrieve_top_n_batch((d_terms[:int(q_off_h[ns])], d_off[:ns + 1]), args.k)
+            same = bool(torch.equal(i2.to(torch.int64).cpu(), ids_ref[:ns]))
+            del m2
+        out["index_file"] = {"bytes": nbytes, "save_s": save_s, "load_s": load_s, "load_GB/s": nbytes / load_s / 1e9,
+                             "loaded_index_top10_identical": same,
+                             "note": "load = read (page cache: the file was just written) -> pinned staging -> H2D -> device-side "
+                                     "validation -> weights, skip tables, rows rebuilt on the GPU; the reference's joblib.load of "
+                                     "its dict-of-dicts model is measured at small scale in BASELINE.md"}
         torch.cuda.empty_cache()
     if dist_on:
         dist.barrier()
@@ -587,7 +614,7 @@ def main():
         line["verify"] = {"sample": f"first {ns} queries recomputed on rank 0 against a single (unsharded) index of all "
                                     f"{args.docs} docs", "ids_identical_to_single_index": ok}
     if not args.no_secondary:
-        line["secondary"] = secondary_benchmarks(args, dev, rank, world, dist_on)
+        line["secondary"] = secondary_benchmarks(args, dev, rank, world, dist_on, model, (d_terms, d_off, q_off), ids_e2e)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_sample = args.cpu_sample or cpu_sample_size(args, threads)
         cpu_qps, cpu_build_s, cpu_s, out = cpu_oracle_run(args, do_h, tk_h, q_terms, q_off, n_sample, threads)

@@ -24,10 +24,13 @@ SIGNATURES = {
     "br_index_destroy": (None, [_P]),
     "br_index_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                  C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "br_index_stats_in_force": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "br_index_df_dev": (_P, [_P]),
     "br_index_export_df_idf": (C.c_int, [_P, _P, _P]),
     "br_index_export_csr": (C.c_int, [_P, _P, _P, _P, _P]),
     "br_index_import_csr": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, C.POINTER(_P)]),
+    "br_index_export_csr_dev": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "br_index_import_csr_dev": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P, C.POINTER(_P)]),
     "br_score_batch": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, _P, _P]),
     "br_topk_batch": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int, _P, _P, _P, _P]),
     "br_topk_batch_records": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int, _P, _P, _P]),
@@ -39,6 +42,7 @@ SIGNATURES = {
     "br_topk_merge": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "br_row_inv_norms": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
     "br_cosine_topk": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
+    "br_set_cosine_option": (C.c_int, [C.c_char_p, C.c_int]),
     "br_cosine_rerank": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "br_dedupe_first_docs": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "br_last_query_stats": (C.c_int, [_P, _P]),

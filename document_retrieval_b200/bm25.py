@@ -41,6 +41,7 @@ class BM25:
         self._h = None                 # br_index*
         self._vocab = None             # str -> term id (string API only; lazy when built from texts)
         self._terms = None             # term id -> str
+        self._term_pool = None         # (offsets, utf-8 pool) of a loaded index file, decoded lazily
         self.vocabulary = None         # ingest.Vocabulary (GPU hash table) when built with from_texts
         self.bigrams = False           # from_texts(bigrams=True): query texts get the same 2-gram expansion
         self.vocab_size = 0
@@ -76,11 +77,15 @@ class BM25:
     def terms(self):
         if self._terms is None and self.vocabulary is not None:
             self._terms = self.vocabulary.terms
+        if self._terms is None and getattr(self, "_term_pool", None) is not None:
+            off, pool = self._term_pool                     # loaded index file: decode on first use
+            raw, o = pool.tobytes(), off.tolist()
+            self._terms = [raw[o[i]:o[i + 1]].decode("utf-8") for i in range(len(o) - 1)]
         return self._terms
 
     @terms.setter
     def terms(self, v):
-        self._terms, self._vocab = v, None
+        self._terms, self._vocab, self._term_pool = v, None, None
 
     @property
     def vocab(self):
@@ -433,31 +438,19 @@ class BM25:
 
     # ------------------------------------------------------------------ native (de)serialisation
     def save(self, path):
-        """Flat CSR file (numpy .npz, uncompressed): row_ptr / doc / tf / dl + vocabulary + statistics.
-        Replaces the joblib/pickle model files whose loading dominated the reference's run time
-        (bm25_ranking.ipynb:222-251, final_implementation.py:187-287): the arrays are memcpy'd to the GPU
-        and the weights / skip tables are rebuilt there."""
-        st = self.__getstate__()
-        c = st.pop("csr")
-        stat = st.pop("stat")
-        terms = st.pop("terms")
-        np.savez(path, row_ptr=c["row_ptr"], doc=c["doc"], tf=c["tf"], dl=c["dl"], df_stat=stat["df"],
-                 avgdl=np.float64(stat["avgdl"]), terms=np.asarray(terms if terms is not None else [], dtype=object),
-                 has_terms=np.bool_(terms is not None),
-                 meta=np.asarray([repr({k: st[k] for k in ("k1", "b", "variant", "dedup_query", "vocab_size",
-                                                           "corpus_size", "doc_base", "bigrams")})], dtype=object))
+        """Flat binary index file: a JSON header followed by the raw arrays (row_ptr int64, doc int32, tf uint16,
+        dl int32, optionally the statistics in force for a doc shard and the vocabulary as a UTF-8 byte pool + offsets),
+        each at a 4096-byte aligned offset.  No pickle anywhere.  Replaces the joblib / pickle model files whose loading
+        dominated the reference's run time (bm25_ranking.ipynb:222-251, final_implementation.py:187-287): ``load``
+        streams the arrays through pinned memory to the GPU, validates them there and rebuilds the weights, skip tables
+        and rows on the device."""
+        from . import indexfile
+        indexfile.save(self, path)
 
     @classmethod
     def load(cls, path, device=None):
-        import ast
-        with np.load(path if str(path).endswith(".npz") else str(path) + ".npz", allow_pickle=True) as z:
-            meta = ast.literal_eval(str(z["meta"][0]))
-            st = dict(meta, terms=[str(t) for t in z["terms"]] if bool(z["has_terms"]) else None,
-                      csr=dict(row_ptr=z["row_ptr"], doc=z["doc"], tf=z["tf"], dl=z["dl"]),
-                      stat=dict(avgdl=float(z["avgdl"]), df=z["df_stat"]))
-        self = cls.__new__(cls)
-        self.__setstate__(st)
-        return self
+        from . import indexfile
+        return indexfile.load(cls, path, device)
 
     # ------------------------------------------------------------------ pickling (joblib.dump, :312)
     def __getstate__(self):
@@ -471,8 +464,8 @@ class BM25:
             st["stat"] = dict(avgdl=s["avgdl"], df=df)
         return st
 
-    def __setstate__(self, st):
-        self.__init__(None, st["k1"], st["b"], variant=st["variant"], dedup_query=st["dedup_query"])
+    def __setstate__(self, st, device=None):
+        self.__init__(None, st["k1"], st["b"], variant=st["variant"], dedup_query=st["dedup_query"], device=device)
         self.terms = st["terms"]
         self.bigrams = bool(st.get("bigrams", False))
         self.vocab_size, self.corpus_size, self.doc_base = st["vocab_size"], st["corpus_size"], st["doc_base"]
@@ -480,7 +473,7 @@ class BM25:
         if c is None:
             return
         lib = _lib.load()
-        dev = _lib.require_cuda(None)
+        dev = _lib.require_cuda(self._device)
         self._device = dev
         h = C.c_void_p()
         with torch.cuda.device(dev):

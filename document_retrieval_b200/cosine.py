@@ -18,6 +18,11 @@ def _bf16(x, dev):
     return t.to(dev).contiguous()
 
 
+def set_cosine_option(name, value):
+    """br_set_cosine_option: process-wide kernel-variant / schedule switches of the brute-force path (tests, sweeps)."""
+    check(_lib.load().br_set_cosine_option(name.encode(), int(value)), "br_set_cosine_option")
+
+
 class CosineIndex:
     """Doc embeddings resident in HBM with their inverse norms (``1/(||e||+1e-10)``, computed once)."""
 

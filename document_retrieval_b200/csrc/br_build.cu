@@ -183,14 +183,59 @@ __global__ void k_rows_fill(const int64_t* __restrict__ row_ptr, const br_postin
     }
 }
 
-__global__ void k_import(const int32_t* __restrict__ doc, const int32_t* __restrict__ tf_in, int64_t nnz,
-                         br_posting* __restrict__ post, uint16_t* __restrict__ tf, int* __restrict__ bad) {
+// CSR validation for imported indexes (a truncated / corrupt file must not cause out-of-bounds accesses later):
+// bit 1: row_ptr not monotone or outside [0, nnz]; bit 2: doc id outside [0, n_docs); bit 8: doc ids not strictly
+// ascending inside a row; bit 4: tf == 0
+__global__ void k_validate_rows(const int64_t* __restrict__ row_ptr, int32_t vocab, int64_t nnz, uint32_t* __restrict__ df,
+                                int* __restrict__ bad) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= vocab) return;
+    const int64_t a = row_ptr[t], b = row_ptr[t + 1];
+    if (a < 0 || b < a || b > nnz || (t == 0 && a != 0) || (t == vocab - 1 && b != nnz)) { atomicOr(bad, 1); df[t] = 0; return; }
+    df[t] = (uint32_t)(b - a);
+}
+__global__ void k_validate_postings(const int64_t* __restrict__ row_ptr, int32_t vocab, const int32_t* __restrict__ doc,
+                                    const uint16_t* __restrict__ tf_in, int64_t nnz, int64_t n_docs,
+                                    br_posting* __restrict__ post, uint16_t* __restrict__ tf, int* __restrict__ bad) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nnz) return;
-    post[j].doc = (uint32_t)doc[j];
+    const int32_t d = doc[j];
+    if (d < 0 || d >= n_docs) atomicOr(bad, 2);
+    if (tf_in[j] == 0) atomicOr(bad, 4);
+    if (j > 0 && d <= doc[j - 1]) {
+        // allowed only at the first posting of a row: is j some row_ptr[t]?
+        int32_t lo = 0, hi = vocab;                       // last t with row_ptr[t] <= j
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (row_ptr[mid] <= j) lo = mid; else hi = mid;
+        }
+        if (row_ptr[lo] != j) atomicOr(bad, 8);
+    }
+    post[j].doc = (uint32_t)d;
     post[j].w = 0.f;
-    if (tf_in[j] < 0 || tf_in[j] > 65535) atomicOr(bad, 4);
-    tf[j] = (uint16_t)tf_in[j];
+    tf[j] = tf_in[j];
+}
+__global__ void k_sum_dl(const int32_t* __restrict__ dl_in, int64_t n, uint32_t* __restrict__ dl, unsigned long long* __restrict__ sum,
+                         int* __restrict__ bad) {
+    unsigned long long s = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = dl_in[i];
+        if (v < 0) atomicOr(bad, 16);
+        dl[i] = (uint32_t)v;
+        s += (unsigned long long)max(v, 0);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(sum, s);
+}
+__global__ void k_tf_to_u16(const int32_t* __restrict__ tf_in, int64_t nnz, uint16_t* __restrict__ out, int* __restrict__ bad) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nnz) return;
+    if (tf_in[j] < 0 || tf_in[j] > 65535) atomicOr(bad, 32);
+    out[j] = (uint16_t)tf_in[j];
+}
+__global__ void k_export_u16(const br_posting* __restrict__ post, int64_t nnz, int32_t* __restrict__ doc_out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nnz) doc_out[j] = (int32_t)post[j].doc;
 }
 
 __global__ void k_export(const br_posting* __restrict__ post, const uint16_t* __restrict__ tf, int64_t nnz,
@@ -326,54 +371,94 @@ int index_build(const int32_t* tok, const int64_t* doc_off, int64_t n_docs, int3
     return BR_OK;
 }
 
+// Import from DEVICE arrays (the flat index file is staged through pinned memory by the caller): validates the CSR on the
+// device, copies it into library-owned arrays.  Call index_finalize afterwards.
+int index_import_dev(const int64_t* row_ptr, const int32_t* doc, const uint16_t* tf, const int32_t* dl, int64_t n_docs,
+                     int32_t vocab, int64_t nnz, int64_t doc_base, cudaStream_t st, br_index** out) {
+    BR_REQUIRE(out && row_ptr && dl && (nnz == 0 || (doc && tf)), BR_ERR_INVALID, "br_index_import_csr_dev: null pointer");
+    BR_REQUIRE(n_docs > 0 && n_docs < (1LL << 31) && vocab > 0 && nnz >= 0 && nnz < (1LL << 32), BR_ERR_INVALID,
+               "br_index_import_csr_dev: bad sizes");
+    *out = nullptr;
+    br_index* ix = new br_index();
+    BR_CUDA(cudaGetDevice(&ix->device));
+    ix->n_docs = n_docs; ix->vocab = vocab; ix->doc_base = doc_base; ix->nnz = nnz;
+    struct Guard { br_index* p; ~Guard() { if (p) index_free(p); } } guard{ix};
+    BR_TRY(alloc_common(ix));
+    const size_t np = (size_t)(nnz > 0 ? nnz : 1);
+    BR_CUDA(cudaMalloc(&ix->post, sizeof(br_posting) * np));
+    BR_CUDA(cudaMalloc(&ix->tf, sizeof(uint16_t) * np));
+    int* d_bad = nullptr;
+    unsigned long long* d_sum = nullptr;
+    struct Tmp { void** p; ~Tmp() { if (*p) cudaFree(*p); } };
+    Tmp t0{(void**)&d_bad}, t1{(void**)&d_sum};
+    BR_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    BR_CUDA(cudaMalloc(&d_sum, sizeof(unsigned long long)));
+    BR_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    BR_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(unsigned long long), st));
+    BR_CUDA(cudaMemcpyAsync(ix->row_ptr, row_ptr, sizeof(int64_t) * ((size_t)vocab + 1), cudaMemcpyDeviceToDevice, st));
+    k_validate_rows<<<blocks_for(vocab, 256), 256, 0, st>>>(ix->row_ptr, vocab, nnz, ix->df, d_bad);
+    BR_CUDA(cudaGetLastError());
+    int bad = 0;
+    BR_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaStreamSynchronize(st));                  // row_ptr must be sound before the posting pass searches it
+    BR_REQUIRE(!bad, BR_ERR_INVALID, "br_index_import_csr: row_ptr is not a monotone [0 .. nnz] offset array");
+    if (nnz > 0) {
+        k_validate_postings<<<blocks_for(nnz, 256), 256, 0, st>>>(ix->row_ptr, vocab, doc, tf, nnz, n_docs, ix->post, ix->tf, d_bad);
+        BR_CUDA(cudaGetLastError());
+    }
+    k_sum_dl<<<kNumSMs * 4, 256, 0, st>>>(dl, n_docs, ix->dl, d_sum, d_bad);
+    BR_CUDA(cudaGetLastError());
+    ix->h_df.resize((size_t)vocab);
+    unsigned long long sum = 0;
+    BR_CUDA(cudaMemcpyAsync(ix->h_df.data(), ix->df, sizeof(uint32_t) * (size_t)vocab, cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaMemcpyAsync(&sum, d_sum, sizeof(sum), cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BR_CUDA(cudaStreamSynchronize(st));
+    BR_REQUIRE(!(bad & 2), BR_ERR_INVALID, "br_index_import_csr: doc id outside [0, n_docs)");
+    BR_REQUIRE(!(bad & 8), BR_ERR_INVALID, "br_index_import_csr: doc ids not strictly ascending inside a posting list");
+    BR_REQUIRE(!(bad & 4), BR_ERR_INVALID, "br_index_import_csr: tf outside [1, 65535]");
+    BR_REQUIRE(!(bad & 16), BR_ERR_INVALID, "br_index_import_csr: negative doc length");
+    ix->sum_dl = (int64_t)sum;
+    guard.p = nullptr;
+    *out = ix;
+    return BR_OK;
+}
+
+// Import from HOST arrays (unpickling): upload, then the same validation.
 int index_import(const int64_t* row_ptr, const int32_t* doc, const int32_t* tf, const int32_t* dl, int64_t n_docs,
                  int32_t vocab, int64_t doc_base, cudaStream_t st, br_index** out) {
     BR_REQUIRE(out && row_ptr && doc && tf && dl, BR_ERR_INVALID, "br_index_import_csr: null pointer");
     BR_REQUIRE(n_docs > 0 && n_docs < (1LL << 31) && vocab > 0, BR_ERR_INVALID, "br_index_import_csr: bad sizes");
     *out = nullptr;
-    br_index* ix = new br_index();
-    BR_CUDA(cudaGetDevice(&ix->device));
-    ix->n_docs = n_docs; ix->vocab = vocab; ix->doc_base = doc_base;
-    struct Guard { br_index* p; ~Guard() { if (p) index_free(p); } } guard{ix};
     const int64_t nnz = row_ptr[vocab];
-    BR_REQUIRE(nnz >= 0 && row_ptr[0] == 0, BR_ERR_INVALID, "br_index_import_csr: bad row_ptr");
-    ix->nnz = nnz;
-    BR_TRY(alloc_common(ix));
-    const size_t np = (size_t)(nnz > 0 ? nnz : 1);
-    BR_CUDA(cudaMalloc(&ix->post, sizeof(br_posting) * np));
-    BR_CUDA(cudaMalloc(&ix->tf, sizeof(uint16_t) * np));
-    int32_t *d_doc = nullptr, *d_tf = nullptr;
+    BR_REQUIRE(nnz >= 0 && nnz < (1LL << 32) && row_ptr[0] == 0, BR_ERR_INVALID, "br_index_import_csr: bad row_ptr");
+    int64_t* d_rp = nullptr;
+    int32_t *d_doc = nullptr, *d_tf = nullptr, *d_dl = nullptr;
+    uint16_t* d_tf16 = nullptr;
     int* d_bad = nullptr;
     struct Tmp { void** p; ~Tmp() { if (*p) cudaFree(*p); } };
-    Tmp t0{(void**)&d_doc}, t1{(void**)&d_tf}, t2{(void**)&d_bad};
+    Tmp t0{(void**)&d_rp}, t1{(void**)&d_doc}, t2{(void**)&d_tf}, t3{(void**)&d_dl}, t4{(void**)&d_tf16}, t5{(void**)&d_bad};
+    const size_t np = (size_t)(nnz > 0 ? nnz : 1);
+    BR_CUDA(cudaMalloc(&d_rp, sizeof(int64_t) * ((size_t)vocab + 1)));
     BR_CUDA(cudaMalloc(&d_doc, sizeof(int32_t) * np));
     BR_CUDA(cudaMalloc(&d_tf, sizeof(int32_t) * np));
+    BR_CUDA(cudaMalloc(&d_tf16, sizeof(uint16_t) * np));
+    BR_CUDA(cudaMalloc(&d_dl, sizeof(int32_t) * (size_t)n_docs));
     BR_CUDA(cudaMalloc(&d_bad, sizeof(int)));
     BR_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    BR_CUDA(cudaMemcpyAsync(d_rp, row_ptr, sizeof(int64_t) * ((size_t)vocab + 1), cudaMemcpyHostToDevice, st));
     BR_CUDA(cudaMemcpyAsync(d_doc, doc, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
     BR_CUDA(cudaMemcpyAsync(d_tf, tf, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
-    BR_CUDA(cudaMemcpyAsync(ix->row_ptr, row_ptr, sizeof(int64_t) * ((size_t)vocab + 1), cudaMemcpyHostToDevice, st));
-    BR_CUDA(cudaMemcpyAsync(ix->dl, dl, sizeof(int32_t) * (size_t)n_docs, cudaMemcpyHostToDevice, st));
+    BR_CUDA(cudaMemcpyAsync(d_dl, dl, sizeof(int32_t) * (size_t)n_docs, cudaMemcpyHostToDevice, st));
     if (nnz > 0) {
-        k_import<<<blocks_for(nnz, 256), 256, 0, st>>>(d_doc, d_tf, nnz, ix->post, ix->tf, d_bad);
+        k_tf_to_u16<<<blocks_for(nnz, 256), 256, 0, st>>>(d_tf, nnz, d_tf16, d_bad);
         BR_CUDA(cudaGetLastError());
     }
-    ix->h_df.resize((size_t)vocab);
-    int64_t sum = 0;
-    for (int32_t t = 0; t < vocab; ++t) {
-        BR_REQUIRE(row_ptr[t + 1] >= row_ptr[t], BR_ERR_INVALID, "br_index_import_csr: row_ptr not monotone");
-        ix->h_df[(size_t)t] = (uint32_t)(row_ptr[t + 1] - row_ptr[t]);
-    }
-    for (int64_t d = 0; d < n_docs; ++d) sum += dl[d];
-    ix->sum_dl = sum;
-    BR_CUDA(cudaMemcpyAsync(ix->df, ix->h_df.data(), sizeof(uint32_t) * (size_t)vocab, cudaMemcpyHostToDevice, st));
     int bad = 0;
     BR_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     BR_CUDA(cudaStreamSynchronize(st));
     BR_REQUIRE(!bad, BR_ERR_INVALID, "br_index_import_csr: tf outside [0, 65535]");
-    guard.p = nullptr;
-    *out = ix;
-    return BR_OK;
+    return index_import_dev(d_rp, d_doc, d_tf16, d_dl, n_docs, vocab, nnz, doc_base, st, out);
 }
 
 int index_finalize(br_index* ix, double k1, double b, int variant, double n_stat, double sum_dl_stat,
@@ -388,6 +473,7 @@ int index_finalize(br_index* ix, double k1, double b, int variant, double n_stat
     ix->k1 = k1; ix->b = b; ix->variant = variant;
     ix->n_stat = n_stat > 0 ? n_stat : (double)ix->n_docs;
     const double sum_dl = sum_dl_stat > 0 ? sum_dl_stat : (double)ix->sum_dl;
+    ix->sum_dl_stat = sum_dl;
     ix->avgdl = sum_dl / ix->n_stat;                       // sum(len(doc)) / corpus_size, :171
     const size_t V = (size_t)ix->vocab;
     ix->h_df_stat.resize(V);
@@ -516,6 +602,27 @@ int br_index_import_csr(const int64_t* row_ptr_host, const int32_t* doc_host, co
                             (cudaStream_t)stream, out);
 }
 
+int br_index_import_csr_dev(const int64_t* row_ptr_dev, const int32_t* doc_dev, const uint16_t* tf_dev, const int32_t* dl_dev,
+                            int64_t n_docs, int32_t vocab, int64_t nnz, int64_t doc_base, void* stream, br_index** out) {
+    return br::index_import_dev(row_ptr_dev, doc_dev, tf_dev, dl_dev, n_docs, vocab, nnz, doc_base, (cudaStream_t)stream, out);
+}
+
+int br_index_export_csr_dev(const br_index* ix, int64_t* row_ptr_dev, int32_t* doc_dev, uint16_t* tf_dev, int32_t* dl_dev,
+                            void* stream) {
+    BR_REQUIRE(ix && row_ptr_dev && dl_dev && (ix->nnz == 0 || (doc_dev && tf_dev)), BR_ERR_INVALID,
+               "br_index_export_csr_dev: null pointer");
+    BR_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    BR_CUDA(cudaMemcpyAsync(row_ptr_dev, ix->row_ptr, sizeof(int64_t) * ((size_t)ix->vocab + 1), cudaMemcpyDeviceToDevice, st));
+    BR_CUDA(cudaMemcpyAsync(dl_dev, ix->dl, sizeof(uint32_t) * (size_t)ix->n_docs, cudaMemcpyDeviceToDevice, st));
+    if (ix->nnz > 0) {
+        BR_CUDA(cudaMemcpyAsync(tf_dev, ix->tf, sizeof(uint16_t) * (size_t)ix->nnz, cudaMemcpyDeviceToDevice, st));
+        br::k_export_u16<<<br::blocks_for(ix->nnz, 256), 256, 0, st>>>(ix->post, ix->nnz, doc_dev);
+        BR_CUDA(cudaGetLastError());
+    }
+    return BR_OK;
+}
+
 void br_index_destroy(br_index* ix) { br::index_free(ix); }
 
 int br_index_stats(const br_index* ix, int64_t* n_docs, int32_t* vocab, int64_t* nnz, double* avgdl,
@@ -531,6 +638,13 @@ int br_index_stats(const br_index* ix, int64_t* n_docs, int32_t* vocab, int64_t*
 }
 
 const uint32_t* br_index_df_dev(const br_index* ix) { return ix ? ix->df : nullptr; }
+
+int br_index_stats_in_force(const br_index* ix, double* n_stat, double* sum_dl_stat) {
+    BR_REQUIRE(ix && ix->finalized, BR_ERR_STATE, "br_index_stats_in_force: call br_index_finalize first");
+    if (n_stat) *n_stat = ix->n_stat;
+    if (sum_dl_stat) *sum_dl_stat = ix->sum_dl_stat;
+    return BR_OK;
+}
 
 int br_index_export_df_idf(const br_index* ix, int64_t* df_host, double* idf_host) {
     BR_REQUIRE(ix, BR_ERR_INVALID, "br_index_export_df_idf: null handle");

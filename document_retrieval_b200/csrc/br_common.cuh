@@ -94,7 +94,7 @@ struct br_index {
     int32_t vocab = 0;
     bool finalized = false;
     int variant = 0;
-    double k1 = 1.5, b = 0.75, n_stat = 0, avgdl = 0;
+    double k1 = 1.5, b = 0.75, n_stat = 0, sum_dl_stat = 0, avgdl = 0;
 
     // CSR by term (device)
     int64_t* row_ptr = nullptr;     // [V+1]
@@ -179,6 +179,8 @@ int index_finalize(br_index* ix, double k1, double b, int variant, double n_stat
                    const int64_t* df_stat_host, cudaStream_t st);
 int index_import(const int64_t* row_ptr, const int32_t* doc, const int32_t* tf, const int32_t* dl,
                  int64_t n_docs, int32_t vocab, int64_t doc_base, cudaStream_t st, br_index** out);
+int index_import_dev(const int64_t* row_ptr, const int32_t* doc, const uint16_t* tf, const int32_t* dl, int64_t n_docs,
+                     int32_t vocab, int64_t nnz, int64_t doc_base, cudaStream_t st, br_index** out);
 void index_free(br_index* ix);
 // br_query.cu
 int score_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_offsets, int32_t nq, int dedup,

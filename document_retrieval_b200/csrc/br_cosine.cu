@@ -172,9 +172,7 @@ struct CosArgs {
     int32_t nq;
     int32_t d;
     int32_t tile_begin, tile_end;   // doc tiles [tile_begin, tile_end) of CG_BM rows
-    int32_t debug_skip_epilogue;    // measurement aid (BR_COS_DEBUG_NOEPI): epilogue warps only hand the accumulators back
     int32_t window;                 // query-stationary kernel: doc tiles per L2 window
-    int32_t* dbg_dummy;             // [nq] measurement aid (BR_COS_DEBUG_NOEPI=6: one extra atomic round trip per emission)
 };
 
 __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_constant__ CUtensorMap map_docs,
@@ -290,10 +288,9 @@ __global__ void __launch_bounds__(CG_THREADS, 1) k_cosine_gemm(const __grid_cons
             // thresholds read as float4; the next 32 columns are already on their way from TMEM.  Only when m >= 0
             // are the 32 columns rescanned and emitted.
             uint32_t v[2][32];
-            if (!a.debug_skip_epilogue) tc_ld_32x32(taddr, v[0]);
+            tc_ld_32x32(taddr, v[0]);
 #pragma unroll
             for (int b = 0; b < (CG_BN / 32); ++b) {
-                if (a.debug_skip_epilogue) break;
                 tc_wait_ld();
                 if (b + 1 < CG_BN / 32) tc_ld_32x32(taddr + (b + 1) * 32, v[(b + 1) & 1]);
                 const uint32_t (&cur)[32] = v[b & 1];
@@ -455,10 +452,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS, 1) k_cos
             // thresholds read as float4; the next 32 columns are already on their way from TMEM.  Only when m >= 0
             // are the 32 columns rescanned and emitted.
             uint32_t v[2][32];
-            if (!a.debug_skip_epilogue) tc_ld_32x32(taddr, v[0]);
+            tc_ld_32x32(taddr, v[0]);
 #pragma unroll
             for (int b = 0; b < (CG_BN / 32); ++b) {
-                if (a.debug_skip_epilogue) break;
                 tc_wait_ld();
                 if (b + 1 < CG_BN / 32) tc_ld_32x32(taddr + (b + 1) * 32, v[(b + 1) & 1]);
                 const uint32_t (&cur)[32] = v[b & 1];
@@ -740,7 +736,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QS_THREADS, 1) k_cos
             acc_phase[acc] ^= 1;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)col0;
-            if (a.debug_skip_epilogue != 1) {
+            {
                 // common case (nothing passes) is branch-free: per 16-column chunk mc = max_j (acc_j * inv_d - thr_j)
                 float mc[NCH];
                 {
@@ -752,7 +748,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QS_THREADS, 1) k_cos
                     for (int c = 0; c < NCH; ++c) {
                         const float4* t4 = reinterpret_cast<const float4*>(s_thr + col0 + c * 16);
                         float m = -CUDART_INF_F;
-                        if (a.debug_skip_epilogue != 2) {     // 2: measurement aid, TMEM reads without the filter arithmetic
+                        {
 #pragma unroll
                             for (int j4 = 0; j4 < 4; ++j4) {
                                 const float4 th = t4[j4];
@@ -770,7 +766,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QS_THREADS, 1) k_cos
                 // and its passing (doc, query) pairs are appended to the queries' candidate lists
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
-                    if (a.debug_skip_epilogue == 3 || !__any_sync(0xffffffffu, mc[c] >= 0.f)) continue;   // 3: measurement aid
+                    if (!__any_sync(0xffffffffu, mc[c] >= 0.f)) continue;
                     uint32_t e[16];
                     tc_ld_32x16(taddr + c * 16, e);
                     tc_wait_ld();
@@ -781,8 +777,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QS_THREADS, 1) k_cos
                             const int col = col0 + c * 16 + j;
                             if (sc >= s_thr[col]) {
                                 const int q = un.qb * QS_BN + col;
-                                int pos = atomicAdd(a.cand_cnt + q, 1);
-                                if (a.debug_skip_epilogue == 6) pos += atomicAdd(a.dbg_dummy + q, 1) & 0;
+                                const int pos = atomicAdd(a.cand_cnt + q, 1);
                                 if (pos < COS_CAP) {
                                     a.cand[(int64_t)q * COS_CAP + pos] = (int32_t)doc;
                                     a.cand_h[(int64_t)q * COS_CAP + pos] = sc * s_inq[col];
@@ -1013,6 +1008,30 @@ __global__ void k_cos_patch(const int32_t* __restrict__ rows, int32_t nr, int32_
     out_sims[o] = sims[i];
 }
 
+// Process-wide tuning / test switches of br_cosine_topk (br_set_cosine_option): every setting returns bit-identical results.
+struct CosOptions {
+    int kernel = 0;          // 0 auto (query-stationary CTA pairs when d <= 768, else 2-CTA multicast), 1 multicast, 2 one CTA per tile
+    int qs_bn = 224;         // query block width of the query-stationary kernel: 128, 160, 192 or 224
+    int qs_window = 64;      // doc tiles per L2 window
+    int chunk0 = 1;          // doc tiles of the first launch
+    int chunk_mult = 2;      // growth of the launches
+    int tighten_threads = 64;
+};
+static CosOptions g_cos;
+
+int set_cosine_option(const char* name, int value) {
+    BR_REQUIRE(name, BR_ERR_INVALID, "br_set_cosine_option: null name");
+    const std::string n(name);
+    if (n == "kernel") { BR_REQUIRE(value >= 0 && value <= 2, BR_ERR_INVALID, "br_set_cosine_option: kernel must be 0, 1 or 2"); g_cos.kernel = value; }
+    else if (n == "qs_bn") { BR_REQUIRE(value == 128 || value == 160 || value == 192 || value == 224, BR_ERR_INVALID, "br_set_cosine_option: qs_bn must be 128, 160, 192 or 224"); g_cos.qs_bn = value; }
+    else if (n == "qs_window") { BR_REQUIRE(value >= 1 && value <= 4096, BR_ERR_INVALID, "br_set_cosine_option: qs_window must be in [1, 4096]"); g_cos.qs_window = value; }
+    else if (n == "chunk0") { BR_REQUIRE(value >= 1, BR_ERR_INVALID, "br_set_cosine_option: chunk0 must be >= 1"); g_cos.chunk0 = value; }
+    else if (n == "chunk_mult") { BR_REQUIRE(value >= 2 && value <= 64, BR_ERR_INVALID, "br_set_cosine_option: chunk_mult must be in [2, 64]"); g_cos.chunk_mult = value; }
+    else if (n == "tighten_threads") { BR_REQUIRE(value >= 32 && value <= TC_T && value % 32 == 0, BR_ERR_INVALID, "br_set_cosine_option: tighten_threads must be a multiple of 32 up to 256"); g_cos.tighten_threads = value; }
+    else { set_error("br_set_cosine_option: unknown option " + n); return BR_ERR_INVALID; }
+    return BR_OK;
+}
+
 int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d, const void* queries, int32_t nq,
                 int32_t k, int64_t doc_base, int64_t* out_ids, float* out_sims, cudaStream_t st) {
     BR_REQUIRE(docs && inv_nd && queries && out_ids && out_sims, BR_ERR_INVALID, "br_cosine_topk: null pointer");
@@ -1022,13 +1041,10 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     BR_REQUIRE(((uintptr_t)docs & 15) == 0 && ((uintptr_t)queries & 15) == 0, BR_ERR_INVALID, "br_cosine_topk: 16-byte alignment required");
     if (nq == 0) return BR_OK;
     // kernel choice: "qs" query-stationary CTA pairs (default when the query block fits: d <= 768), "mc" 2-CTA multicast,
-    // "plain" one CTA per tile (BR_COS_KERNEL overrides)
-    const char* env_kernel = getenv("BR_COS_KERNEL");
-    const bool use_mc = getenv("BR_COS_NO_MULTICAST") == nullptr && !(env_kernel && !strcmp(env_kernel, "plain"));
-    const bool use_qs = d <= QS_NKB * CG_BK && (!env_kernel || !strcmp(env_kernel, "qs"));
-    const int qs_bn = getenv("BR_COS_QS_BN") ? atoi(getenv("BR_COS_QS_BN")) : 224;
-    const int qs_window = getenv("BR_COS_QS_WINDOW") ? atoi(getenv("BR_COS_QS_WINDOW")) : 64;
-    BR_REQUIRE(qs_bn == 128 || qs_bn == 160 || qs_bn == 192 || qs_bn == 224, BR_ERR_INVALID, "BR_COS_QS_BN must be 128, 160, 192 or 224");
+    // "plain" one CTA per tile (br_set_cosine_option("kernel", ...) overrides)
+    const bool use_mc = g_cos.kernel != 2;
+    const bool use_qs = d <= QS_NKB * CG_BK && g_cos.kernel == 0;
+    const int qs_bn = g_cos.qs_bn, qs_window = g_cos.qs_window;
     CUtensorMap map_d, map_q;
     BR_TRY(make_map(&map_d, docs, n_docs, d, (use_mc || use_qs) ? 128 : CG_BM));
     BR_TRY(make_map(&map_q, queries, nq, d, use_qs ? qs_bn / 2 : CG_BN));
@@ -1039,9 +1055,9 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));      // per device
     BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));
     const size_t Q = (size_t)nq;
-    AsyncBuf b_inq(st), b_thr(st), b_cnt(st), b_prev(st), b_ovf(st), b_cand(st), b_h(st), b_dbg(st);
+    AsyncBuf b_inq(st), b_thr(st), b_cnt(st), b_prev(st), b_ovf(st), b_cand(st), b_h(st);
     BR_TRY(b_inq.alloc(4 * Q)); BR_TRY(b_thr.alloc(4 * Q)); BR_TRY(b_cnt.alloc(4 * Q)); BR_TRY(b_prev.alloc(4 * Q));
-    BR_TRY(b_ovf.alloc(4 * Q)); BR_TRY(b_cand.alloc(4 * Q * COS_CAP)); BR_TRY(b_h.alloc(4 * Q * COS_CAP)); BR_TRY(b_dbg.alloc(4 * Q));
+    BR_TRY(b_ovf.alloc(4 * Q)); BR_TRY(b_cand.alloc(4 * Q * COS_CAP)); BR_TRY(b_h.alloc(4 * Q * COS_CAP));
     float* inv_nq = (float*)b_inq.p;
     float* thr = (float*)b_thr.p;
     BR_TRY(row_inv_norms(queries, nq, d, inv_nq, st));
@@ -1054,15 +1070,14 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     // doc chunks of growing size: thresholds learnt on the docs so far filter the next chunk.  A launch emits about
     // k (growth - 1) candidates per query whatever its size; measured on the config-5 shard an emission costs ~1.7 ns of
     // wall time, which makes doubling (13 launches, ~120 emissions per query) faster than 3x / 4x / 8x growth
-    const int chunk0 = getenv("BR_COS_CHUNK0") ? std::max(1, atoi(getenv("BR_COS_CHUNK0"))) : 1;
-    const int growth = getenv("BR_COS_CHUNK_MULT") ? std::max(2, atoi(getenv("BR_COS_CHUNK_MULT"))) : 2;
+    const int chunk0 = g_cos.chunk0, growth = g_cos.chunk_mult;
     // candidate lists are ~2k long after the first rounds: small CTAs (more of them resident, cheaper barriers)
-    const int tighten_t = getenv("BR_COS_TIGHTEN_T") ? std::min(TC_T, std::max(32, atoi(getenv("BR_COS_TIGHTEN_T")) & ~31)) : 64;
+    const int tighten_t = g_cos.tighten_threads;
     int t0 = 0, chunk = chunk0;
     while (t0 < n_dt) {
         const int nt = std::min(chunk, n_dt - t0);
         CosArgs a{inv_nd, inv_nq, thr, (int32_t*)b_cnt.p, (int32_t*)b_cand.p, (float*)b_h.p, n_docs, nq, d, t0, t0 + nt,
-                  getenv("BR_COS_DEBUG_NOEPI") ? atoi(getenv("BR_COS_DEBUG_NOEPI")) : 0, qs_window, (int32_t*)b_dbg.p};
+                  qs_window};
         if (use_qs) {
             const int64_t units = (int64_t)nt * ((nq + qs_bn - 1) / qs_bn);
             const int grid = 2 * (int)std::min<int64_t>(units, kNumSMs / 2);
@@ -1096,24 +1111,32 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     std::vector<int32_t> redo;
     for (int32_t q = 0; q < nq; ++q) if (ovf[(size_t)q]) redo.push_back(q);
     if (!redo.empty()) {
-        BR_REQUIRE(redo.size() <= 64 && d <= 1024, BR_ERR_UNSUPPORTED,
-                   "br_cosine_topk: more than 1024 near-tied candidates for more than 64 queries (or d > 1024)");
-        const int32_t nr = (int32_t)redo.size();
+        // Any number of such queries: sub-batches of at most 64 bound the scratch (4 B x 64 x n_docs candidate ids).
+        // This also covers a corpus whose row order correlates with the queries (every launch then passes far more
+        // than COS_CAP rows above the threshold learnt on the rows before it).
+        BR_REQUIRE(d <= 1024, BR_ERR_UNSUPPORTED,
+                   "br_cosine_topk: candidate overflow (more than 1024 rows at or above a query's running threshold in one "
+                   "launch) needs the exact gather pass, which supports d <= 1024");
+        const int32_t sub = 64;
         AsyncBuf b_q(st), b_c(st), b_oi(st), b_os(st), b_rows(st);
-        BR_TRY(b_q.alloc((size_t)nr * d * 2)); BR_TRY(b_c.alloc(4 * (size_t)nr * (size_t)n_docs));
-        BR_TRY(b_oi.alloc(4 * (size_t)nr * k)); BR_TRY(b_os.alloc(4 * (size_t)nr * k)); BR_TRY(b_rows.alloc(4 * (size_t)nr));
-        for (int32_t i = 0; i < nr; ++i)
-            BR_CUDA(cudaMemcpyAsync((char*)b_q.p + (size_t)i * d * 2, (const char*)queries + (size_t)redo[(size_t)i] * d * 2,
-                                    (size_t)d * 2, cudaMemcpyDeviceToDevice, st));
-        BR_CUDA(cudaMemcpyAsync(b_rows.p, redo.data(), 4 * (size_t)nr, cudaMemcpyHostToDevice, st));
-        k_iota_rows<<<kNumSMs * 8, 256, 0, st>>>((int32_t*)b_c.p, nr, n_docs);
+        const int32_t nr_max = (int32_t)std::min<size_t>(redo.size(), (size_t)sub);
+        BR_TRY(b_q.alloc((size_t)nr_max * d * 2)); BR_TRY(b_c.alloc(4 * (size_t)nr_max * (size_t)n_docs));
+        BR_TRY(b_oi.alloc(4 * (size_t)nr_max * k)); BR_TRY(b_os.alloc(4 * (size_t)nr_max * k)); BR_TRY(b_rows.alloc(4 * (size_t)nr_max));
+        k_iota_rows<<<kNumSMs * 8, 256, 0, st>>>((int32_t*)b_c.p, nr_max, n_docs);
         BR_CUDA(cudaGetLastError());
-        BR_TRY(cosine_rerank(docs, inv_nd, n_docs, d, b_q.p, nr, (const int32_t*)b_c.p, (int32_t)n_docs, k, (int32_t*)b_oi.p,
-                             (float*)b_os.p, st));
-        k_cos_patch<<<blocks_for((int64_t)nr * k, 256), 256, 0, st>>>((const int32_t*)b_rows.p, nr, k, (const int32_t*)b_oi.p,
-                                                                      (const float*)b_os.p, doc_base, out_ids, out_sims);
-        BR_CUDA(cudaGetLastError());
-        BR_CUDA(cudaStreamSynchronize(st));
+        for (size_t r0 = 0; r0 < redo.size(); r0 += (size_t)sub) {
+            const int32_t nr = (int32_t)std::min<size_t>((size_t)sub, redo.size() - r0);
+            for (int32_t i = 0; i < nr; ++i)
+                BR_CUDA(cudaMemcpyAsync((char*)b_q.p + (size_t)i * d * 2, (const char*)queries + (size_t)redo[r0 + (size_t)i] * d * 2,
+                                        (size_t)d * 2, cudaMemcpyDeviceToDevice, st));
+            BR_CUDA(cudaMemcpyAsync(b_rows.p, redo.data() + r0, 4 * (size_t)nr, cudaMemcpyHostToDevice, st));
+            BR_TRY(cosine_rerank(docs, inv_nd, n_docs, d, b_q.p, nr, (const int32_t*)b_c.p, (int32_t)n_docs, k, (int32_t*)b_oi.p,
+                                 (float*)b_os.p, st));             // synchronises: b_rows / b_q may be reused afterwards
+            k_cos_patch<<<blocks_for((int64_t)nr * k, 256), 256, 0, st>>>((const int32_t*)b_rows.p, nr, k, (const int32_t*)b_oi.p,
+                                                                          (const float*)b_os.p, doc_base, out_ids, out_sims);
+            BR_CUDA(cudaGetLastError());
+            BR_CUDA(cudaStreamSynchronize(st));
+        }
     }
     return BR_OK;
 }
@@ -1167,6 +1190,8 @@ int br_cosine_topk(const void* docs_bf16_dev, const float* doc_inv_norm_dev, int
     return br::cosine_topk(docs_bf16_dev, doc_inv_norm_dev, n_docs, d, queries_bf16_dev, nq, k, doc_base, out_ids_dev,
                            out_sims_dev, (cudaStream_t)stream);
 }
+
+int br_set_cosine_option(const char* name, int value) { return br::set_cosine_option(name, value); }
 
 int br_cosine_rerank(const void* docs_bf16_dev, const float* doc_inv_norm_dev, int64_t n_docs, int32_t d,
                      const void* queries_bf16_dev, int32_t nq, const int32_t* cand_ids_dev, int32_t c, int32_t k,

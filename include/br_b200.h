@@ -71,6 +71,9 @@ void br_index_destroy(br_index* ix);
 /* corpus_size / nnz / avgdl / sum(dl) attributes (bm25_ranking.ipynb:170-171). Any out may be NULL. */
 int br_index_stats(const br_index* ix, int64_t* n_docs, int32_t* vocab, int64_t* nnz,
                    double* avgdl, int64_t* sum_dl, int64_t* doc_base);
+/* The corpus statistics the weights were computed with (br_index_finalize's n_stat / sum_dl_stat after defaulting):
+ * differ from br_index_stats for a doc shard.  Stored in the flat index file so that a shard can be re-finalised. */
+int br_index_stats_in_force(const br_index* ix, double* n_stat, double* sum_dl_stat);
 /* Device pointer to the shard-local df histogram, uint32[vocab] (for the cross-shard all-reduce). */
 const uint32_t* br_index_df_dev(const br_index* ix);
 /* `df` / `idf` attributes (bm25_ranking.ipynb:173-174,188-189; compute_idf
@@ -86,6 +89,18 @@ int br_index_export_csr(const br_index* ix, int64_t* row_ptr_host, int32_t* doc_
 int br_index_import_csr(const int64_t* row_ptr_host, const int32_t* doc_host, const int32_t* tf_host,
                         const int32_t* dl_host, int64_t n_docs, int32_t vocab, int64_t doc_base,
                         void* stream, br_index** out);
+
+/* The same two with DEVICE arrays and 16-bit tf - the path of the flat index file (BM25.save / BM25.load): the file's
+ * arrays are staged through pinned host memory straight into device buffers, no host-side copy or conversion.  This
+ * is what replaces the joblib model files whose loading dominated the reference's run time (bm25_ranking.ipynb:222-251,
+ * final_implementation.py:187-287).  Import validates the CSR on the device (row_ptr a monotone [0 .. nnz] offset array,
+ * doc ids in range and strictly ascending inside a posting list, 1 <= tf <= 65535, doc lengths >= 0) and fails with
+ * BR_ERR_INVALID otherwise; br_index_import_csr goes through the same checks.  Call br_index_finalize afterwards. */
+int br_index_export_csr_dev(const br_index* ix, int64_t* row_ptr_dev, int32_t* doc_dev, uint16_t* tf_dev,
+                            int32_t* dl_dev, void* stream);
+int br_index_import_csr_dev(const int64_t* row_ptr_dev, const int32_t* doc_dev, const uint16_t* tf_dev,
+                            const int32_t* dl_dev, int64_t n_docs, int32_t vocab, int64_t nnz, int64_t doc_base,
+                            void* stream, br_index** out);
 
 /* ---------------------------------------------------------------------------------------------
  * Queries.  A batch is CSR-packed term ids: q_terms_dev int32[q_offsets[nq]], q_offsets_dev
@@ -183,12 +198,18 @@ int br_row_inv_norms(const void* emb_bf16_dev, int64_t n, int32_t d, float* out_
 /* Exact brute-force top-k (1 <= k <= 256) of every query over all docs: bf16 tcgen05 GEMM with the
  * normalisation and the top-k filter fused into the epilogue.  doc_inv_norm_dev from
  * br_row_inv_norms (computed once per corpus).  Outputs [nq, k], best first, ties by doc id:
- * out_ids_dev int64 (doc_base + local row, -1 pads), out_sims_dev float.  A query with more than 1024 docs tied at
- * its threshold (masses of duplicate embeddings) is answered exactly by a full gather pass instead of the filter
- * (up to 64 such queries per call).  Synchronises `stream`. */
+ * out_ids_dev int64 (doc_base + local row, -1 pads), out_sims_dev float.  A query for which one launch finds more
+ * than 1024 rows at or above its running threshold (masses of duplicate embeddings, or rows ordered by similarity to
+ * the queries) is answered exactly by a full gather pass instead of the filter - any number of such queries, 64 per
+ * pass; slower, never wrong.  Synchronises `stream`. */
 int br_cosine_topk(const void* docs_bf16_dev, const float* doc_inv_norm_dev, int64_t n_docs, int32_t d,
                    const void* queries_bf16_dev, int32_t nq, int32_t k, int64_t doc_base,
                    int64_t* out_ids_dev, float* out_sims_dev, void* stream);
+/* Process-wide tuning / test switches of br_cosine_topk; every setting returns bit-identical results.  name = "kernel"
+ * (0 auto: query-stationary CTA pairs for d <= 768, else 2-CTA multicast; 1 multicast; 2 one CTA per tile), "qs_bn" (query
+ * block width 128/160/192/224), "qs_window" (doc tiles per L2 window), "chunk0", "chunk_mult" (launch schedule),
+ * "tighten_threads". */
+int br_set_cosine_option(const char* name, int value);
 /* Re-rank: query q against its own candidates cand_ids_dev[q, 0..c) (local rows, -1 = empty slot),
  * e.g. the BM25 top-1000 (text_preprocessing_and_embedding_setup.py:342).  doc_inv_norm_dev may be
  * NULL (norms are then computed on the fly).  Outputs [nq, k] (k <= BR_MAX_K): out_ids_dev int32,

@@ -151,8 +151,69 @@ def test_c4_slice_properties(c4_slice):
     assert torch.equal(ids_m, ids_f.long()) and torch.equal(sc_m, sc_f)
     del shards
     with tempfile.TemporaryDirectory() as tmp:
-        path = os.path.join(tmp, "index.npz")
+        path = os.path.join(tmp, "index.brix")
         m.save(path)
         m2 = BM25.load(path)
         i2, s2 = m2.retrieve_top_n_batch(q, 10)
         assert torch.equal(i2, ids_f) and torch.equal(s2, sc_f)
+
+
+def test_index_file_roundtrip_against_the_oracle(tmp_path):
+    """BM25.save / BM25.load (flat binary file, no pickle): the loaded index answers like the plain-C oracle built
+    from the original tokens; string vocabulary, a doc shard's statistics in force, and corrupt files."""
+    import json
+    from document_retrieval_b200 import BM25, indexfile
+    from document_retrieval_b200._lib import BRError
+    c = synth.make_config("C1", scale=0.3)
+    co = COracle(c["doc_offsets"], c["token_ids"], c["vocab"])
+    oi, osc, _ = co.topk_batch(c["q_terms"], c["q_offsets"], 10)
+    m = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"])
+    path = str(tmp_path / "c1.brix")
+    m.save(path)
+    assert open(path, "rb").read(8) == b"BRIX0001" and b"pickle" not in open(path, "rb").read(4096)
+    m2 = BM25.load(path)
+    ids, sc = m2.retrieve_top_n_batch((c["q_terms"], c["q_offsets"]), 10)
+    assert np.array_equal(ids.cpu().numpy(), oi) and np.array_equal(sc.cpu().numpy(), osc)
+    assert m2.avgdl == co.avgdl and m2.corpus_size == co.n_docs
+    # string surface: terms survive as a byte pool, decoded lazily
+    docs = synth.to_strings(c["doc_offsets"][:201], c["token_ids"][:int(c["doc_offsets"][200])])
+    ms = BM25(docs)
+    p2 = str(tmp_path / "s.brix")
+    ms.save(p2)
+    ml = BM25.load(p2)
+    assert ml._terms is None and ml.terms == ms.terms
+    q = docs[7][:5]
+    assert np.array_equal(ml.retrieve_top_n(q, 10), ms.retrieve_top_n(q, 10))
+    assert ml.df == ms.df and ml.idf == ms.idf
+    # a doc shard keeps the global statistics it was finalised with
+    half = 1500
+    do, tk = c["doc_offsets"], c["token_ids"]
+    sh = BM25.from_token_ids(do[:half + 1], tk[:int(do[half])], c["vocab"], finalize=False)
+    full_df = np.diff(m._export_csr()["row_ptr"]).astype(np.int64)
+    sh.finalize(m.corpus_size, int(m.stats()["sum_dl"]), full_df)
+    p3 = str(tmp_path / "shard.brix")
+    sh.save(p3)
+    assert indexfile.read_header(p3)["shard"] is True
+    sl = BM25.load(p3)
+    a = sh.retrieve_top_n_batch((c["q_terms"], c["q_offsets"]), 10)
+    b = sl.retrieve_top_n_batch((c["q_terms"], c["q_offsets"]), 10)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and sl.avgdl == m.avgdl
+    # corrupt files fail loudly instead of reading out of bounds
+    raw = bytearray(open(path, "rb").read())
+    open(str(tmp_path / "trunc.brix"), "wb").write(raw[:len(raw) // 2])
+    with pytest.raises(BRError):
+        BM25.load(str(tmp_path / "trunc.brix"))
+    h = indexfile.read_header(path)
+    off = next(x["offset"] for x in h["arrays"] if x["name"] == "doc")
+    bad = bytearray(raw)
+    bad[off:off + 4] = (10 ** 9).to_bytes(4, "little")                    # doc id far outside [0, n_docs)
+    open(str(tmp_path / "bad.brix"), "wb").write(bad)
+    with pytest.raises(BRError):
+        BM25.load(str(tmp_path / "bad.brix"))
+    bad = bytearray(raw)
+    bad[off + 4:off + 8] = bad[off:off + 4]                               # doc ids not ascending inside a list
+    open(str(tmp_path / "dup.brix"), "wb").write(bad)
+    with pytest.raises(BRError):
+        BM25.load(str(tmp_path / "dup.brix"))
+    with pytest.raises(BRError):
+        BM25.load(__file__)

@@ -55,20 +55,25 @@ def test_cosine_topk_random(n, d, nq, k):
     _check(ids.cpu().numpy() - 1000, sims.cpu().numpy(), docs.float().numpy(), qs.float().numpy(), k)
 
 
-@pytest.mark.parametrize("env", [{"BR_COS_KERNEL": "mc"}, {"BR_COS_KERNEL": "plain"}, {"BR_COS_QS_BN": "128"},
-                                 {"BR_COS_QS_BN": "160"}, {"BR_COS_QS_BN": "192"}, {"BR_COS_QS_WINDOW": "3"}])
-def test_cosine_kernel_variants_agree(env, monkeypatch):
+@pytest.mark.parametrize("opt", [{"kernel": 1}, {"kernel": 2}, {"qs_bn": 128}, {"qs_bn": 160}, {"qs_bn": 192},
+                                 {"qs_window": 3}, {"chunk0": 4, "chunk_mult": 3}])
+def test_cosine_kernel_variants_agree(opt):
     """Every GEMM variant (query-stationary CTA pairs at each block width, 2-CTA multicast, one CTA per tile) returns
     the same ids and bit-identical similarities as the default: same K order of accumulation per element."""
-    from document_retrieval_b200.cosine import CosineIndex
+    from document_retrieval_b200.cosine import CosineIndex, set_cosine_option
+    defaults = {"kernel": 0, "qs_bn": 224, "qs_window": 64, "chunk0": 1, "chunk_mult": 2}
     g = torch.Generator().manual_seed(99)
     docs = torch.randn(9000, 320, generator=g).to(torch.bfloat16)
     qs = torch.randn(700, 320, generator=g).to(torch.bfloat16)
     ix = CosineIndex(docs)
     ids0, s0 = ix.topk(qs, 10)
-    for k_, v in env.items():
-        monkeypatch.setenv(k_, v)
-    ids1, s1 = ix.topk(qs, 10)
+    try:
+        for k_, v in opt.items():
+            set_cosine_option(k_, v)
+        ids1, s1 = ix.topk(qs, 10)
+    finally:
+        for k_ in opt:
+            set_cosine_option(k_, defaults[k_])
     assert torch.equal(ids0, ids1) and torch.equal(s0, s1)
 
 
@@ -110,3 +115,29 @@ def test_cosine_massive_ties_are_answered_exactly():
     assert np.array_equal(ids[0], want)
     np.testing.assert_allclose(sims[0], 1.0, rtol=1e-5)
     _check(ids[1:], sims[1:], docs.float().numpy(), qs[1:].float().numpy(), 10)
+
+
+def test_cosine_topk_overflow_fallback_for_many_queries():
+    """more than 64 queries whose candidates overflow the filter lists in one launch.  (a) 100 queries equal to a
+    row that is duplicated 2,000 times; (b) a corpus SORTED by similarity to the query direction, so that every launch sees
+    only rows better than everything before it.  Both must be answered exactly (gather-pass fallback in sub-batches)."""
+    from document_retrieval_b200.cosine import CosineIndex
+    g = torch.Generator().manual_seed(synth.ROOT_SEED + 77)
+    n, d, k = 30000, 64, 10
+    docs = torch.randn(n, d, generator=g).to(torch.bfloat16)
+    docs[5000:7000] = docs[123]                                   # 2,001 identical rows
+    qs = docs[123:124].repeat(100, 1).clone()
+    qs[50:] += (0.01 * torch.randn(50, d, generator=g)).to(torch.bfloat16)
+    ix = CosineIndex(docs)
+    ids, sims = ix.topk(qs, k)
+    _check(ids.cpu().numpy(), sims.cpu().numpy(), docs.float().numpy(), qs.float().numpy(), k)
+    assert ids[0].cpu().tolist() == [123] + list(range(5000, 5009))          # exact ties by row id
+    # (b) rows sorted by ascending cosine to a direction; 80 queries close to that direction
+    v = torch.randn(d, generator=g)
+    base = torch.randn(n, d, generator=g)
+    order = torch.argsort((base / base.norm(dim=1, keepdim=True)) @ (v / v.norm()))
+    docs2 = base[order].to(torch.bfloat16)
+    qs2 = (v[None, :] + 0.05 * torch.randn(80, d, generator=g)).to(torch.bfloat16)
+    ix2 = CosineIndex(docs2)
+    ids2, sims2 = ix2.topk(qs2, k)
+    _check(ids2.cpu().numpy(), sims2.cpu().numpy(), docs2.float().numpy(), qs2.float().numpy(), k)
