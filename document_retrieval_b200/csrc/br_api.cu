@@ -78,6 +78,7 @@ int br_set_option(br_index* ix, const char* name, int value) {
     const std::string n(name);
     if (n == "fused") ix->allow_fused = value != 0;
     else if (n == "fused_bigk") ix->allow_fused_bigk = value != 0;
+    else if (n == "fused_long") ix->allow_fused_long = value != 0;
     else if (n == "seed_thr") ix->seed_thr = value != 0;
     else if (n == "tile_g") {
         BR_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 8, BR_ERR_INVALID,

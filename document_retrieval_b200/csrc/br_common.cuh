@@ -135,7 +135,7 @@ struct br_index {
     br::DevBuf ws_prep, ws_dense, ws_sel, ws_cand, ws_misc, ws_tile, ws_sort, ws_cold, ws_rec;
     br_query_stats stats{};
 
-    bool allow_fused = true, allow_fused_bigk = true;
+    bool allow_fused = true, allow_fused_bigk = true, allow_fused_long = true;
     int tile_g = 0;
     bool seed_thr = true;           // threshold seeding before the first launch of the tiled scorer
     int defer_pm = 700;             // MaxScore deferral budget of the tiled scorer, per mille of the threshold (0 = off)

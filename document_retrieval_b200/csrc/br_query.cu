@@ -773,44 +773,66 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
     } else {
         std::vector<int32_t> flags;
         BR_TRY(topk_fused(ix, q_off, pv, nq, k, dedup, positive_only, out_ids, out_scores, out_counts, st, &flags));
+        {   // offsets past n_terms make queries empty: report before the scratch of this batch is reused below
+            int32_t h_bad = 0;
+            BR_CUDA(cudaMemcpyAsync(&h_bad, pv.bad, 4, cudaMemcpyDeviceToHost, st));
+            BR_CUDA(cudaStreamSynchronize(st));
+            BR_REQUIRE(!h_bad, BR_ERR_INVALID, "br_topk_batch: q_offsets run past n_terms");
+        }
         std::vector<int32_t> redo;
         for (int32_t q = 0; q < nq; ++q) if (flags[(size_t)q]) redo.push_back(q);
         ix->stats.queries_fused += nq - (int64_t)redo.size();
         if (!redo.empty()) {
-            // the few queries the fused path cannot serve exactly (too many distinct terms, candidate
-            // overflow, fewer than k docs with a hit) go through the dense path as a compacted sub-batch
+            // The queries the regular pass cannot serve exactly (more than 32 terms / 20 hot terms, candidate overflow,
+            // fewer than k docs with a hit) are compacted into a sub-batch: first the long-query pass of the tiled
+            // scorer (up to 64 terms / 40 hot terms: bigram-expanded queries), then, for what is still left, the dense path.
             std::vector<int32_t> h_off((size_t)nq + 1), h_terms((size_t)std::max(T, 1));
             BR_CUDA(cudaMemcpyAsync(h_off.data(), q_off, 4 * ((size_t)nq + 1), cudaMemcpyDeviceToHost, st));
             BR_CUDA(cudaMemcpyAsync(h_terms.data(), q_terms, 4 * (size_t)T, cudaMemcpyDeviceToHost, st));
             BR_CUDA(cudaStreamSynchronize(st));
-            const int32_t ns = (int32_t)redo.size();
-            std::vector<int32_t> s_off((size_t)ns + 1, 0), s_terms;
-            for (int32_t i = 0; i < ns; ++i) {
-                const int32_t q = redo[(size_t)i];
-                s_terms.insert(s_terms.end(), h_terms.begin() + h_off[(size_t)q], h_terms.begin() + h_off[(size_t)q + 1]);
-                s_off[(size_t)i + 1] = (int32_t)s_terms.size();
+            for (int pass = 0; pass < 2 && !redo.empty(); ++pass) {
+                const bool long_pass = pass == 0;
+                if (long_pass && !ix->allow_fused_long) continue;
+                const int32_t ns = (int32_t)redo.size();
+                std::vector<int32_t> s_off((size_t)ns + 1, 0), s_terms;
+                for (int32_t i = 0; i < ns; ++i) {
+                    const int32_t q = redo[(size_t)i];
+                    s_terms.insert(s_terms.end(), h_terms.begin() + h_off[(size_t)q], h_terms.begin() + h_off[(size_t)q + 1]);
+                    s_off[(size_t)i + 1] = (int32_t)s_terms.size();
+                }
+                size_t bytes = 0;
+                auto carve = [&](size_t n) { size_t o = bytes; bytes += (n + 255) & ~(size_t)255; return o; };
+                const size_t o_t = carve(4 * (s_terms.size() + 1)), o_o = carve(4 * ((size_t)ns + 1)), o_q = carve(4 * (size_t)ns),
+                             o_i = carve(4 * (size_t)ns * k), o_s = carve(8 * (size_t)ns * k), o_c = carve(4 * (size_t)ns);
+                BR_TRY(ix->ws_misc.reserve(bytes));
+                char* p = ix->ws_misc.as<char>();
+                int32_t *d_t = (int32_t*)(p + o_t), *d_o = (int32_t*)(p + o_o), *d_q = (int32_t*)(p + o_q),
+                        *d_i = (int32_t*)(p + o_i), *d_c = (int32_t*)(p + o_c);
+                double* d_s = (double*)(p + o_s);
+                BR_CUDA(cudaMemcpyAsync(d_t, s_terms.data(), 4 * s_terms.size(), cudaMemcpyHostToDevice, st));
+                BR_CUDA(cudaMemcpyAsync(d_o, s_off.data(), 4 * ((size_t)ns + 1), cudaMemcpyHostToDevice, st));
+                BR_CUDA(cudaMemcpyAsync(d_q, redo.data(), 4 * (size_t)ns, cudaMemcpyHostToDevice, st));
+                PrepView spv;
+                int64_t* s_chunk;
+                int32_t sT;
+                BR_TRY(prep_queries(ix, d_t, d_o, ns, dedup, st, &spv, &s_chunk, &sT, (int32_t)s_terms.size()));
+                std::vector<int32_t> next;
+                if (long_pass) {
+                    std::vector<int32_t> f2;
+                    BR_TRY(topk_fused(ix, d_o, spv, ns, k, dedup, positive_only, d_i, d_s, d_c, st, &f2, true));
+                    for (int32_t i = 0; i < ns; ++i) if (f2[(size_t)i]) next.push_back(redo[(size_t)i]);
+                    ix->stats.queries_fused += ns - (int64_t)next.size();
+                } else {
+                    BR_TRY(topk_dense(ix, d_o, spv, s_chunk, 0, ns, k, dedup, positive_only, d_i, d_s, d_c, st));
+                }
+                // rows of queries that go on to the next pass are overwritten there (same stream)
+                k_scatter_rows<<<blocks_for((int64_t)ns * k, 256), 256, 0, st>>>(d_q, ns, k, d_i, d_s, d_c, out_ids, out_scores,
+                                                                                out_counts);
+                BR_CUDA(cudaGetLastError());
+                BR_CUDA(cudaStreamSynchronize(st));              // the host vectors and ws_misc are reused by the next pass
+                ix->stats.kernel_launches += 1;
+                redo.swap(next);
             }
-            size_t bytes = 0;
-            auto carve = [&](size_t n) { size_t o = bytes; bytes += (n + 255) & ~(size_t)255; return o; };
-            const size_t o_t = carve(4 * (s_terms.size() + 1)), o_o = carve(4 * ((size_t)ns + 1)), o_q = carve(4 * (size_t)ns),
-                         o_i = carve(4 * (size_t)ns * k), o_s = carve(8 * (size_t)ns * k), o_c = carve(4 * (size_t)ns);
-            BR_TRY(ix->ws_misc.reserve(bytes));
-            char* p = ix->ws_misc.as<char>();
-            int32_t *d_t = (int32_t*)(p + o_t), *d_o = (int32_t*)(p + o_o), *d_q = (int32_t*)(p + o_q),
-                    *d_i = (int32_t*)(p + o_i), *d_c = (int32_t*)(p + o_c);
-            double* d_s = (double*)(p + o_s);
-            BR_CUDA(cudaMemcpyAsync(d_t, s_terms.data(), 4 * s_terms.size(), cudaMemcpyHostToDevice, st));
-            BR_CUDA(cudaMemcpyAsync(d_o, s_off.data(), 4 * ((size_t)ns + 1), cudaMemcpyHostToDevice, st));
-            BR_CUDA(cudaMemcpyAsync(d_q, redo.data(), 4 * (size_t)ns, cudaMemcpyHostToDevice, st));
-            PrepView spv;
-            int64_t* s_chunk;
-            int32_t sT;
-            BR_TRY(prep_queries(ix, d_t, d_o, ns, dedup, st, &spv, &s_chunk, &sT));
-            BR_TRY(topk_dense(ix, d_o, spv, s_chunk, 0, ns, k, dedup, positive_only, d_i, d_s, d_c, st));
-            k_scatter_rows<<<blocks_for((int64_t)ns * k, 256), 256, 0, st>>>(d_q, ns, k, d_i, d_s, d_c, out_ids, out_scores,
-                                                                            out_counts);
-            BR_CUDA(cudaGetLastError());
-            ix->stats.kernel_launches += 1;
         }
     }
     if (out_recs) {
@@ -818,10 +840,7 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 1;
     }
-    int32_t h_bad = 0;
-    BR_CUDA(cudaMemcpyAsync(&h_bad, pv.bad, 4, cudaMemcpyDeviceToHost, st));
     BR_CUDA(cudaStreamSynchronize(st));
-    BR_REQUIRE(!h_bad, BR_ERR_INVALID, "br_topk_batch: q_offsets run past n_terms");
     int64_t sum = 0;
     for (int64_t v : hP) sum += v;
     ix->stats.postings_bytes = 8 * sum;

@@ -43,7 +43,9 @@ constexpr int TILE_W = 8;            // warps per CTA = sub-ranges per tile
 constexpr int TILE_SHIFT = BR_TILE_SHIFT;   // 512 docs per sub-range (must equal br_index::sub_shift)
 constexpr int TILE_S = 1 << TILE_SHIFT;
 constexpr int TILE_DOCS_SHIFT = TILE_SHIFT + 3;   // log2(W * S)
-constexpr int TILE_QT = 20;          // max distinct hot terms of one query on this path (more -> dense path)
+constexpr int TILE_QT = 20;          // max distinct hot terms of one query in the regular pass (groups of up to 4 queries)
+constexpr int TILE_QT_LONG = 40;     // the same in the long-query pass (groups of up to 2 queries with up to 64 terms, e.g.
+                                     // bigram-expanded queries, bm25_ranking.ipynb:105-107); more -> dense path
 constexpr int TILE_CAP = 1024;       // candidates kept per query between tighten rounds (k <= 32)
 constexpr int TILE_CAP_BIG = 8192;   // the same for 32 < k <= 1024: one tile of 4096 docs may pass entirely before the first
                                      // threshold exists, later chunks add about k candidates each
@@ -78,7 +80,8 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
                                                    TileEntry* __restrict__ entries, int32_t* __restrict__ n_entries,
                                                    int32_t* __restrict__ elig, unsigned long long* __restrict__ cold_total,
                                                    int64_t dense_df_min, const int32_t* __restrict__ perm,
-                                                   const int16_t* __restrict__ row_slot, int n_srows) {
+                                                   const int16_t* __restrict__ row_slot, int n_srows, int qt_max,
+                                                   int max_terms) {
     __shared__ int32_t s_term[4][256];
     __shared__ uint8_t s_q[4][256], s_m[4][256], s_p[4][256];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(128) k_tile_prep(PrepView pv, const int32_t* _
         }
         for (int o = 16; o > 0; o >>= 1) cold += __shfl_xor_sync(0xffffffffu, cold, o);
         bad = __any_sync(0xffffffffu, bad);
-        const bool ok = hot <= TILE_QT && !bad && pv.o_cnt[q] <= 32;   // longer queries: dense path (wider fp32 band)
+        const bool ok = hot <= qt_max && !bad && pv.o_cnt[q] <= max_terms;   // longer queries: long pass / dense path
         if (lane == 0) elig[q] = ok ? 1 : 0;
         if (!ok) continue;
         cold_sum += cold;
@@ -343,7 +346,7 @@ constexpr int LIST_CAP = 64;      // crossing-list slots per warp and sub-range 
 // still stream rows / have no threshold yet, or when a crossing list overflows.
 // After the CTA prologue there is no block barrier: every warp fetches the slice bounds of its own sub-range (one tile
 // ahead, into registers) and its own copy of the thresholds.
-template <int G>
+template <int G, int QT>
 __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* acc = reinterpret_cast<float*>(smem_raw);                                     // [G][W][S]
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
     float* s_t1_all = s_thq_all + TILE_W * 4;                                            // [W][4]
     int* s_lcnt_all = reinterpret_cast<int*>(s_t1_all + TILE_W * 4);                     // [W]
     int* s_nql = s_lcnt_all + TILE_W;                                                    // [4] sparse streamed terms of each query
-    uint8_t* s_ql = reinterpret_cast<uint8_t*>(s_nql + 4);                               // [G][TILE_QT] their entry indices
+    uint8_t* s_ql = reinterpret_cast<uint8_t*>(s_nql + 4);                               // [G][QT] their entry indices
 
     const int g = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
 #pragma unroll
                 for (int i = 0; i < G; ++i) {
                     if (e.mult[i] && s_qi[i] >= 0) {
-                        if ((dm[i] >> e.pos[i]) & 1u) def[i] = (float)e.mult[i];
+                        if (e.pos[i] < 32 && ((dm[i] >> e.pos[i]) & 1u)) def[i] = (float)e.mult[i];
                         else { act[i] = (float)e.mult[i]; isa = true; if (u < Ur0) rows_q |= 1u << i; }
                     }
                 }
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
                 const unsigned mq = __ballot_sync(0xffffffffu, in);
                 if (in) {
                     const int p = nql[i] + __popc(mq & lt);
-                    if (p < TILE_QT) s_ql[i * TILE_QT + p] = (uint8_t)(na + __popc(ma & lt));
+                    if (p < QT) s_ql[i * QT + p] = (uint8_t)(na + __popc(ma & lt));
                 }
                 nql[i] += __popc(mq);
             }
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
         for (int i = 0; i < G; ++i) {
             const int n = min(nne[i], NE_MAX), n4 = (n + 3) & ~3;
             if (lane >= n && lane < n4) s_ne[i * NE_MAX + lane] = NeEntry{0, 0.f};     // padding: row 0, multiplicity 0
-            if (lane == 0) { s_nne[i] = n4; s_nql[i] = min(nql[i], TILE_QT); }
+            if (lane == 0) { s_nne[i] = n4; s_nql[i] = min(nql[i], QT); }
         }
     }
     __syncthreads();                                   // the only block barrier: from here on the warps run independently
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
     int* s_lcnt = s_lcnt_all + w;
 
     // slice bounds of this warp's sub-range: lane covers entries lane, lane+32, ...; fetched one tile ahead
-    constexpr int NR = (TILE_QT * G + 31) / 32;
+    constexpr int NR = (QT * G + 31) / 32;
     uint32_t nlo[NR], nhi[NR];
     auto load_bounds = [&](int sub) {
 #pragma unroll
@@ -574,7 +577,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
             uint32_t t_lo = 0, t_hi = 0, t_pb = 0;
             float t_mu = 1.f;
             if (r0 + lq < nt) {
-                const int u = s_ql[qg * TILE_QT + r0 + lq];
+                const int u = s_ql[qg * QT + r0 + lq];
                 const uint2 bd = s_bnd[u];
                 t_lo = bd.x; t_hi = bd.y;
                 t_pb = (uint32_t)s_base[u];                         // posting index of the term's list (nnz < 2^32)
@@ -1065,10 +1068,10 @@ __global__ void k_fill_offsets(int64_t* __restrict__ off, int32_t nq, int64_t st
     if (q <= nq) off[q] = (int64_t)q * stride;
 }
 
-template <int G>
+template <int G, int QT>
 static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t smem, cudaStream_t st, br_index* ix,
                         int32_t* prev_cnt, int32_t* overflow, const PlanArgs& pa) {
-    BR_CUDA(cudaFuncSetAttribute(k_tile_score<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device
+    BR_CUDA(cudaFuncSetAttribute(k_tile_score<G, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device
     // chunks of doubling size: thresholds learnt on the first 2^c tiles filter the next 2^c
     // first chunk: as many tiles as the candidate buffer certainly holds with thresholds still at zero
     // (every sub-range can emit up to ~3k docs before its first tightening)
@@ -1084,7 +1087,7 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
         a.tpb = 1;
         while (a.tpb * 2 <= ix->tile_tpb && ny >= 4 * a.tpb) a.tpb *= 2;
         ix->prof_begin(st);
-        k_tile_score<G><<<dim3((unsigned)n_groups, (unsigned)((ny + a.tpb - 1) / a.tpb)), TILE_W * 32, smem, st>>>(a);
+        k_tile_score<G, QT><<<dim3((unsigned)n_groups, (unsigned)((ny + a.tpb - 1) / a.tpb)), TILE_W * 32, smem, st>>>(a);
         BR_CUDA(cudaGetLastError());
         ix->prof_end(st);
         if (big) k_tighten_big<<<a0.nq, TG_T, 8 * (size_t)a0.cap, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, a0.cap, overflow, pa);
@@ -1107,13 +1110,16 @@ bool fused_supported(const br_index* ix, int32_t k, int32_t nq) {
 
 // Fused path over the whole prepared batch.  h_flags[q] != 0 afterwards -> query q must be served by
 // the dense path (not eligible, candidate overflow, or fewer than k docs with a positive score).
+// long_pass: the second pass for queries with up to 64 terms / 40 hot terms (groups of at most 2, no deferral plans).
 int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t nq, int32_t k, int dedup,
                int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st,
-               std::vector<int32_t>* h_flags) {
+               std::vector<int32_t>* h_flags, bool long_pass) {
     int G = nq >= 4 * kNumSMs ? 4 : (nq >= 2 * kNumSMs ? 2 : 1);
     if (ix->tile_g) G = ix->tile_g;
     if (G > 4) G = 4;
-    const int n_groups = (nq + G - 1) / G, umax = G * TILE_QT;
+    if (long_pass && G > 2) G = 2;
+    const int QT = long_pass ? TILE_QT_LONG : TILE_QT;
+    const int n_groups = (nq + G - 1) / G, umax = G * QT;
     const int cap = k <= 32 ? TILE_CAP : TILE_CAP_BIG;
     const int n_tiles = (ix->n_sub + TILE_W - 1) / TILE_W;
     const int64_t n_buckets = (int64_t)n_tiles * n_groups;
@@ -1177,7 +1183,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     BR_CUDA(cudaMemsetAsync(p + o_thr, 0, o_off - o_thr, st));
     BR_CUDA(cudaMemsetAsync(cold_total, 0, 16, st));
     k_tile_prep<<<(n_groups + 3) / 4, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, nq, G, umax, entries, n_entries,
-                                                    elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)ix->tile_dense_min) >> TILE_SHIFT), perm, ix->row_slot, ix->n_srows);
+                                                    elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)ix->tile_dense_min) >> TILE_SHIFT), perm, ix->row_slot, ix->n_srows, QT, long_pass ? 64 : 32);
     BR_CUDA(cudaGetLastError());
     k_fill_offsets<<<blocks_for(nq + 1, 256), 256, 0, st>>>(cand_off, nq, cap);
     BR_CUDA(cudaGetLastError());
@@ -1214,17 +1220,21 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     const PlanArgs pa{q_off, pv.u_terms, pv.u_mult, pv.u_cnt, ix->ub, ix->row_slot, ix->n_srows, (float)ix->defer_pm * 1e-3f, defer_mask, ne_ub};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
                                                                             sizeof(float4) + sizeof(uint32_t) + sizeof(uint2) * TILE_W) +
-                        sizeof(NeEntry) * G * NE_MAX + sizeof(uint16_t) * TILE_W * LIST_CAP + 4 * (20 + 9 * TILE_W) + G * TILE_QT;
+                        sizeof(NeEntry) * G * NE_MAX + sizeof(uint16_t) * TILE_W * LIST_CAP + 4 * (20 + 9 * TILE_W) + G * QT;
     if (k <= 32 && ix->seed_thr) {
         k_seed_thr<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(ix->post, ix->row_ptr, nq, (int)k, elig, thr, pa);
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 1;
     }
-    switch (G) {
-        case 1: BR_TRY(launch_tiles<1>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)); break;
-        case 2: BR_TRY(launch_tiles<2>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)); break;
-        case 4: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)); break;
-        default: BR_TRY(launch_tiles<4>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)); break;
+    if (long_pass) {
+        if (G == 1) BR_TRY((launch_tiles<1, TILE_QT_LONG>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)));
+        else BR_TRY((launch_tiles<2, TILE_QT_LONG>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)));
+    } else {
+        switch (G) {
+            case 1: BR_TRY((launch_tiles<1, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa))); break;
+            case 2: BR_TRY((launch_tiles<2, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa))); break;
+            default: BR_TRY((launch_tiles<4, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa))); break;
+        }
     }
     BR_TRY(launch_rescore_heads(ix, q_off, pv, dedup, nq, cap, cand_cnt, cand, cand_sc, st));
     BR_TRY(launch_final_select(cand, cand_sc, cand_off, 0, nq, k, positive_only, out_ids, out_scores, cnt_tmp, st, cand_cnt));

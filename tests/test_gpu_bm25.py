@@ -321,6 +321,19 @@ def test_long_and_duplicate_heavy_queries():
         ids, sc = m.retrieve_top_n_batch((q_terms, q_off), 10)
         assert np.array_equal(ids.cpu().numpy(), oi) and np.array_equal(sc.cpu().numpy(), os_)
         assert m.query_stats()["queries_dense"] == len(qs)
+        # 33..64 term occurrences (a 17-token query with its bigrams is 33 terms, bm25_ranking.ipynb:105-107): the
+        # long-query pass of the tiled scorer, nothing left for the dense path
+        mid = [np.concatenate([q[:36], q[:4]]) for q in qs] + [q[:33] for q in qs]
+        mo = np.cumsum([0] + [q.size for q in mid]).astype(np.int32)
+        mt = np.concatenate(mid)
+        oi2, os2, _ = co.topk_batch(mt, mo, 10, dedup=dedup)
+        ids2, sc2 = m.retrieve_top_n_batch((mt, mo), 10)
+        assert np.array_equal(ids2.cpu().numpy(), oi2) and np.array_equal(sc2.cpu().numpy(), os2)
+        st = m.query_stats()
+        assert st["queries_dense"] == 0 and st["queries_fused"] == len(mid), st
+        m.set_option("fused_long", 0)
+        ids3, sc3 = m.retrieve_top_n_batch((mt, mo), 10)
+        assert torch.equal(ids3, ids2) and torch.equal(sc3, sc2) and m.query_stats()["queries_dense"] == len(mid)
 
 
 @pytest.mark.parametrize("k", [33, 100, 257, 1024])
