@@ -442,6 +442,10 @@ def main():
     doc_lo, doc_hi = bb[my_blocks[0]][0], bb[my_blocks[-1]][1]
     doc_offsets, token_ids = gen_blocks(args, my_blocks, dev)
     q_terms, q_off, src = gen_queries(args, doc_offsets, token_ids, doc_lo, doc_hi, rank, world)
+    # untimed warm-up build of a small slice (module loading, allocator warm-up), then the timed build of the shard
+    n_warm = min(20_000, int(doc_offsets.numel()) - 1)
+    ShardedBM25.from_local_token_ids(doc_offsets[:n_warm + 1], token_ids[:int(doc_offsets[n_warm])], args.vocab,
+                                     doc_base=doc_lo, device=dev)
     torch.cuda.synchronize()
     t0 = time.time()
     sh = ShardedBM25.from_local_token_ids(doc_offsets, token_ids, args.vocab, doc_base=doc_lo, device=dev)

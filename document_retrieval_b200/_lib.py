@@ -45,6 +45,7 @@ SIGNATURES = {
     "br_set_cosine_option": (C.c_int, [C.c_char_p, C.c_int]),
     "br_cosine_rerank": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "br_dedupe_first_docs": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "br_trim_scratch": (C.c_int, []),
     "br_last_query_stats": (C.c_int, [_P, _P]),
     "br_set_profiling": (C.c_int, [_P, C.c_int]),
     "br_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),

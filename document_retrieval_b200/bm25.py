@@ -217,9 +217,16 @@ class BM25:
 
     def pack_queries(self, queries):
         """list of token lists | (q_terms, q_offsets) -> pinned host (q_terms int32, q_offsets int32)."""
-        if isinstance(queries, tuple) and len(queries) == 2:
+        if isinstance(queries, tuple) and len(queries) == 2 and all(
+                isinstance(x, np.ndarray) or torch.is_tensor(x) for x in queries):
+            # packed form: (q_terms, q_offsets) ARRAYS with q_offsets[0] == 0 and q_offsets[-1] == len(q_terms); a tuple of
+            # two token lists is a batch of two queries, not this
             q_terms = torch.as_tensor(queries[0]).to(torch.int32).contiguous()
             q_off = torch.as_tensor(queries[1]).to(torch.int32).contiguous()
+            if q_off.numel() < 1 or q_terms.dim() != 1 or q_off.dim() != 1:
+                raise ValueError("packed queries: q_terms and q_offsets must be 1-D and q_offsets non-empty")
+            if q_off.device.type == "cpu" and (int(q_off[0]) != 0 or int(q_off[-1]) != q_terms.numel()):
+                raise ValueError("packed queries: q_offsets must start at 0 and end at len(q_terms)")
             return q_terms, q_off
         enc = [self._encode(q) for q in queries]
         lens = np.fromiter((e.size for e in enc), dtype=np.int64, count=len(enc))

@@ -61,6 +61,14 @@ int br_topk_merge(const int64_t* ids_dev, const double* scores_dev, int32_t n_pa
     return br::topk_merge(ids_dev, scores_dev, n_parts, nq, k, out_ids_dev, out_scores_dev, (cudaStream_t)stream);
 }
 
+int br_trim_scratch(void) {
+    int dev = 0;
+    BR_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool = br::scratch_pool_slot(dev);
+    if (pool) BR_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return BR_OK;
+}
+
 int br_last_query_stats(const br_index* ix, br_query_stats* out) {
     BR_REQUIRE(ix && out, BR_ERR_INVALID, "br_last_query_stats: null pointer");
     *out = ix->stats;

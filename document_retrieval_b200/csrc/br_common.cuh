@@ -59,20 +59,37 @@ struct DevBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// Stream-ordered scratch comes from the device's default memory pool.  With the default release threshold (0) every
-// stream synchronisation hands freed memory back to the driver and the next call pays for mapping it again (tens of
-// ms for the larger buffers): keep it in the pool.  Idempotent, per device.
-inline int retain_default_pool() {
-    static bool ready[64] = {};
+// Stream-ordered scratch comes from a PRIVATE memory pool of the library, one per device: with a release threshold of 0
+// every stream synchronisation would hand freed memory back to the driver and the next call pay for mapping it again
+// (tens of ms for the larger buffers), so the pool keeps up to kPoolKeepBytes; anything above that is released at the
+// next synchronisation.  The process's default pool (and with it the host application's own stream-ordered allocations)
+// is left alone; br_trim_scratch() returns the retained memory on request.
+constexpr uint64_t kPoolKeepBytes = 8ull << 30;
+inline cudaMemPool_t& scratch_pool_slot(int dev) {
+    static cudaMemPool_t pools[64] = {};
+    return pools[dev & 63];
+}
+inline int scratch_pool(cudaMemPool_t* out) {
     int dev = 0;
     BR_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !ready[dev]) {
-        cudaMemPool_t pool;
-        BR_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        uint64_t keep = UINT64_MAX;
+    cudaMemPool_t& pool = scratch_pool_slot(dev);
+    if (!pool) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        BR_CUDA(cudaMemPoolCreate(&pool, &props));
+        uint64_t keep = kPoolKeepBytes;
         BR_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        ready[dev] = true;
     }
+    *out = pool;
+    return BR_OK;
+}
+inline int scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+    cudaMemPool_t pool;
+    BR_TRY(scratch_pool(&pool));
+    BR_CUDA(cudaMallocFromPoolAsync(p, bytes ? bytes : 1, pool, st));
     return BR_OK;
 }
 

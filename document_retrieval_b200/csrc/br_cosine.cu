@@ -974,8 +974,7 @@ struct AsyncBuf {   // stream-ordered scratch
     cudaStream_t st;
     explicit AsyncBuf(cudaStream_t s) : st(s) {}
     int alloc(size_t bytes) {
-        BR_TRY(retain_default_pool());
-        BR_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, st));
+        BR_TRY(scratch_alloc(&p, bytes, st));
         return BR_OK;
     }
     ~AsyncBuf() { if (p) cudaFreeAsync(p, st); }

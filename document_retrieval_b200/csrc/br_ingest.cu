@@ -327,9 +327,8 @@ struct Tmp {   // stream-ordered temporaries, released when the call returns
     ~Tmp() { for (void* p : ptrs) if (p) cudaFreeAsync(p, st); }
     template <class T>
     int alloc(T** out, size_t n) {
-        BR_TRY(retain_default_pool());
         void* p = nullptr;
-        BR_CUDA(cudaMallocAsync(&p, sizeof(T) * (n > 0 ? n : 1), st));
+        BR_TRY(scratch_alloc(&p, sizeof(T) * (n > 0 ? n : 1), st));
         ptrs.push_back(p);
         *out = reinterpret_cast<T*>(p);
         return BR_OK;

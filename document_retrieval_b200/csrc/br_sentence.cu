@@ -55,7 +55,7 @@ extern "C" int br_dedupe_first_docs(const int64_t* sentence_ids_dev, const int32
     if (nq == 0) return BR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int* d_bad = nullptr;
-    BR_CUDA(cudaMallocAsync(&d_bad, sizeof(int), st));
+    BR_TRY(br::scratch_alloc((void**)&d_bad, sizeof(int), st));
     BR_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
     br::k_dedupe_first_docs<<<br::blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(sentence_ids_dev, sentence_to_doc_dev, n_sentences,
                                                                                   nq, n, k, out_docs_dev, d_bad);

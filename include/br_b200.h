@@ -225,6 +225,11 @@ int br_cosine_rerank(const void* docs_bf16_dev, const float* doc_inv_norm_dev, i
 int br_dedupe_first_docs(const int64_t* sentence_ids_dev, const int32_t* sentence_to_doc_dev, int64_t n_sentences,
                          int32_t nq, int32_t n, int32_t k, int64_t* out_docs_dev, void* stream);
 
+/* Stream-ordered scratch of the handle-less entry points (cosine, text ingestion) comes from a private memory pool of the
+ * library (one per device) that retains up to 8 GiB between calls; this returns all of it to the driver.  The process's
+ * default memory pool is never touched. */
+int br_trim_scratch(void);
+
 /* Counters of the last br_topk_batch call on this handle (bench / tests): kernels launched,
  * queries served by the fused tiled path, by the dense path, and candidate rows re-scored. */
 typedef struct br_query_stats {
