@@ -338,6 +338,78 @@ def secondary_benchmarks(args, dev, rank, world, dist_on, model=None, q_dev=None
             "note": "re-rank algorithmic bytes = c*D*2 + D*2 + 8k per query (SURVEY 8d); gather-bound", "clocks": clocks3}
         del m3, ci, emb
         torch.cuda.empty_cache()
+    # ---- configs 1 and 2 (small corpora: the reference's own CPU-runnable cases), ids checked against the C oracle
+    if rank == 0 and world == 1:
+        from document_retrieval_b200 import BM25, synth
+        from oracle.c_oracle import COracle
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+        def t_small(fn, reps=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                r = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps, r
+        c1 = synth.make_config("C1")
+        t0 = time.time()
+        m1 = BM25.from_token_ids(c1["doc_offsets"], c1["token_ids"], c1["vocab"], device=dev)
+        torch.cuda.synchronize()
+        b1 = time.time() - t0
+        q1 = (torch.from_numpy(c1["q_terms"]).to(dev), torch.from_numpy(c1["q_offsets"]).to(dev))
+        ms1, (i1, s1) = t_small(lambda: m1.retrieve_top_n_batch(q1, 10))
+        co = COracle(c1["doc_offsets"], c1["token_ids"], c1["vocab"], n_threads=threads)
+        t0 = time.time()
+        oi, osc, _ = co.topk_batch(c1["q_terms"], c1["q_offsets"], 10, n_threads=threads)
+        cpu1 = time.time() - t0
+        nq1 = c1["q_offsets"].size - 1
+        out["bm25_c1"] = {"workload": f"BASELINE config 1: {c1['n_docs']} docs x ~200 tok, {c1['vocab']}-term vocab, {nq1} queries, top-10",
+                          "ms_per_batch": ms1, "queries_per_s": nq1 / (ms1 * 1e-3), "index_build_s": b1,
+                          "ids_and_float64_scores_identical_to_oracle": bool(np.array_equal(i1.cpu().numpy(), oi) and np.array_equal(s1.cpu().numpy(), osc)),
+                          "cpu_port_queries_per_s": nq1 / cpu1, "cpu_cores": threads}
+        del m1, co
+        langs, queries = synth.make_c2(scale=1.0)
+        models, oracles = {}, {}
+        t0 = time.time()
+        for lang, c in langs.items():
+            models[lang] = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"], device=dev)
+        torch.cuda.synchronize()
+        b2 = time.time() - t0
+        by_lang = {}
+        for i, q in enumerate(queries):
+            by_lang.setdefault(q["lang"], []).append(i)
+        packed = {}
+        for lang, idxs in by_lang.items():
+            terms = np.concatenate([queries[i]["terms"] for i in idxs]).astype(np.int32)
+            offs = np.cumsum([0] + [queries[i]["terms"].size for i in idxs]).astype(np.int32)
+            packed[lang] = (torch.from_numpy(terms).to(dev), torch.from_numpy(offs).to(dev), terms, offs)
+
+        def run_c2():
+            return {lang: models[lang].retrieve_top_n_batch((p[0], p[1]), 10)[0] for lang, p in packed.items()}
+        ms2, res2 = t_small(run_c2, reps=10)
+        same, hits, cpu2 = True, 0, 0.0
+        for lang, idxs in by_lang.items():
+            c = langs[lang]
+            co = COracle(c["doc_offsets"], c["token_ids"], c["vocab"], n_threads=threads)
+            t0 = time.time()
+            oi, _, _ = co.topk_batch(packed[lang][2], packed[lang][3], 10, n_threads=threads)
+            cpu2 += time.time() - t0
+            got = res2[lang].cpu().numpy()
+            same = same and bool(np.array_equal(got, oi))
+            hits += sum(1 for j, i in enumerate(idxs) if queries[i]["qrel"] in got[j].tolist())
+            del co
+        out["bm25_c2"] = {"workload": f"BASELINE config 2: 7 per-language indexes, {sum(c['n_docs'] for c in langs.values())} docs, "
+                                      f"{len(queries)} mixed-language queries routed by language, top-10",
+                          "ms_per_batch": ms2, "queries_per_s": len(queries) / (ms2 * 1e-3), "index_build_s": b2,
+                          "recall_at_10": hits / len(queries), "ids_identical_to_oracle": same,
+                          "cpu_port_queries_per_s": len(queries) / cpu2, "cpu_cores": threads}
+        del models
+        torch.cuda.empty_cache()
+
     # ---- index file: BM25.save / BM25.load of this run's index (flat binary, no pickle) - the step whose joblib
     # counterpart took the reference longer than its retrieval (bm25_ranking.ipynb:222-251)
     if rank == 0 and world == 1 and model is not None:

@@ -1024,7 +1024,11 @@ int set_cosine_option(const char* name, int value) {
     if (n == "kernel") { BR_REQUIRE(value >= 0 && value <= 2, BR_ERR_INVALID, "br_set_cosine_option: kernel must be 0, 1 or 2"); g_cos.kernel = value; }
     else if (n == "qs_bn") { BR_REQUIRE(value == 128 || value == 160 || value == 192 || value == 224, BR_ERR_INVALID, "br_set_cosine_option: qs_bn must be 128, 160, 192 or 224"); g_cos.qs_bn = value; }
     else if (n == "qs_window") { BR_REQUIRE(value >= 1 && value <= 4096, BR_ERR_INVALID, "br_set_cosine_option: qs_window must be in [1, 4096]"); g_cos.qs_window = value; }
-    else if (n == "chunk0") { BR_REQUIRE(value >= 1, BR_ERR_INVALID, "br_set_cosine_option: chunk0 must be >= 1"); g_cos.chunk0 = value; }
+    else if (n == "chunk0") {
+        // the first launch runs without thresholds: every row is a candidate, and a query's list holds COS_CAP of them
+        BR_REQUIRE(value >= 1 && value * CG_BM <= COS_CAP, BR_ERR_INVALID, "br_set_cosine_option: chunk0 must be in [1, 4]");
+        g_cos.chunk0 = value;
+    }
     else if (n == "chunk_mult") { BR_REQUIRE(value >= 2 && value <= 64, BR_ERR_INVALID, "br_set_cosine_option: chunk_mult must be in [2, 64]"); g_cos.chunk_mult = value; }
     else if (n == "tighten_threads") { BR_REQUIRE(value >= 32 && value <= TC_T && value % 32 == 0, BR_ERR_INVALID, "br_set_cosine_option: tighten_threads must be a multiple of 32 up to 256"); g_cos.tighten_threads = value; }
     else { set_error("br_set_cosine_option: unknown option " + n); return BR_ERR_INVALID; }
