@@ -1,5 +1,6 @@
 // br_api.cu - C ABI (query side), error reporting, version.
 #include "br_common.cuh"
+#include "br_query.cuh"
 
 namespace br {
 static thread_local std::string g_err;
@@ -61,6 +62,19 @@ int br_topk_merge(const int64_t* ids_dev, const double* scores_dev, int32_t n_pa
     return br::topk_merge(ids_dev, scores_dev, n_parts, nq, k, out_ids_dev, out_scores_dev, (cudaStream_t)stream);
 }
 
+int br_set_thr_exchange(br_index* ix, br_thr_exchange_fn fn, void* user, int rounds) {
+    BR_REQUIRE(ix, BR_ERR_INVALID, "br_set_thr_exchange: null handle");
+    ix->thr_exchange = fn;
+    ix->thr_exchange_user = user;
+    ix->thr_exchange_rounds = fn ? rounds : -1;
+    return BR_OK;
+}
+
+int br_tile_launch_count(const br_index* ix, int32_t k) {
+    if (!ix || !ix->finalized || k < 1 || k > BR_MAX_K) return 0;
+    return br::fused_launch_count(ix, k);
+}
+
 int br_trim_scratch(void) {
     int dev = 0;
     BR_CUDA(cudaGetDevice(&dev));
@@ -95,6 +109,9 @@ int br_set_option(br_index* ix, const char* name, int value) {
     } else if (n == "defer_pm") {
         BR_REQUIRE(value >= 0 && value <= 1000, BR_ERR_INVALID, "br_set_option: defer_pm must be in [0, 1000]");
         ix->defer_pm = value;
+    } else if (n == "tile_growth") {
+        BR_REQUIRE(value >= 2 && value <= 16, BR_ERR_INVALID, "br_set_option: tile_growth must be in [2, 16]");
+        ix->tile_growth = value;
     } else if (n == "tile_dense_min") {
         BR_REQUIRE(value >= 1 && value <= 512, BR_ERR_INVALID, "br_set_option: tile_dense_min must be in [1, 512]");
         ix->tile_dense_min = value;

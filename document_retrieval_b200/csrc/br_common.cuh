@@ -154,8 +154,14 @@ struct br_index {
 
     bool allow_fused = true, allow_fused_bigk = true, allow_fused_long = true;
     int tile_g = 0;
+    // doc-sharded callers: callback that max-reduces thr[Q] over the shards (br_set_thr_exchange), user pointer, and the
+    // number of tile launches after which it is called (plus once after seeding); rounds < 0: off
+    br_thr_exchange_fn thr_exchange = nullptr;
+    void* thr_exchange_user = nullptr;
+    int thr_exchange_rounds = -1;
     bool seed_thr = true;           // threshold seeding before the first launch of the tiled scorer
     int defer_pm = 700;             // MaxScore deferral budget of the tiled scorer, per mille of the threshold (0 = off)
+    int tile_growth = 2;            // every launch covers this many times the tiles of the one before
     int tile_tpb = 16;              // consecutive tiles per CTA in the large launches
     int tile_dense_min = 32;        // average postings of a term per 512-doc sub-range from which its slices are walked
                                     // term by term (whole warp, pipelined) instead of concatenated with the sparse ones

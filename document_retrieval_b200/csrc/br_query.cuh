@@ -29,6 +29,7 @@ int launch_final_select(const int32_t* cand, const double* cand_score, const int
                         int32_t nq, int32_t k, int positive_only, int32_t* out_ids, double* out_scores,
                         int32_t* out_counts, cudaStream_t st, const int32_t* cnt_hint = nullptr);
 bool fused_supported(const br_index* ix, int32_t k, int32_t nq);
+int fused_launch_count(const br_index* ix, int32_t k);
 int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t nq, int32_t k, int dedup,
                int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st,
                std::vector<int32_t>* h_flags, bool long_pass = false);

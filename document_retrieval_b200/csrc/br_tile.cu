@@ -1068,16 +1068,45 @@ __global__ void k_fill_offsets(int64_t* __restrict__ off, int32_t nq, int64_t st
     if (q <= nq) off[q] = (int64_t)q * stride;
 }
 
+// all plans again from the current thresholds (after a cross-shard threshold exchange)
+__global__ void __launch_bounds__(128) k_replan(const float* __restrict__ thr, int32_t nq, const int32_t* __restrict__ elig,
+                                                PlanArgs pa) {
+    const int lane = threadIdx.x & 31;
+    const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (q >= nq || !elig[q]) return;
+    make_plan(pa, q, thr[q], lane);
+}
+
+// Cross-shard threshold exchange (doc-sharded callers, br_set_thr_exchange): the caller's callback replaces thr[Q] by the
+// maximum over all shards - k docs with at least that score exist SOMEWHERE, so it is a valid lower bound of the k-th
+// best score of the whole corpus, the only thing the merged result needs - and the plans follow.
+static int exchange_thr(br_index* ix, float* thr, int32_t nq, const int32_t* elig, const PlanArgs& pa, cudaStream_t st) {
+    const int rc = ix->thr_exchange(thr, nq, (void*)st, ix->thr_exchange_user);
+    BR_REQUIRE(rc == 0, BR_ERR_STATE, "br_topk_batch: the threshold exchange callback failed");
+    k_replan<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(thr, nq, elig, pa);
+    BR_CUDA(cudaGetLastError());
+    ix->stats.kernel_launches += 1;
+    return BR_OK;
+}
+
+// launches of the tile kernel for an index of n_tiles tiles and top-k (doubling chunks)
+static int tile_launch_count(int n_tiles, int k, int growth) {
+    const bool big = k > 32;
+    int t0 = 0, chunk = big ? 1 : std::max(1, std::min(4, TILE_CAP / (TILE_W * 3 * k))), n = 0;
+    while (t0 < n_tiles) { t0 += std::min(std::min(chunk, n_tiles - t0), 32768); chunk *= growth; ++n; }
+    return n;
+}
+
 template <int G, int QT>
 static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t smem, cudaStream_t st, br_index* ix,
-                        int32_t* prev_cnt, int32_t* overflow, const PlanArgs& pa) {
+                        int32_t* prev_cnt, int32_t* overflow, const PlanArgs& pa, int exchange_rounds) {
     BR_CUDA(cudaFuncSetAttribute(k_tile_score<G, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device
     // chunks of doubling size: thresholds learnt on the first 2^c tiles filter the next 2^c
     // first chunk: as many tiles as the candidate buffer certainly holds with thresholds still at zero
     // (every sub-range can emit up to ~3k docs before its first tightening)
     const bool big = a0.cap > TILE_CAP;
     if (big) BR_CUDA(cudaFuncSetAttribute(k_tighten_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TILE_CAP_BIG));
-    int t0 = 0, chunk = big ? 1 : std::max(1, std::min(4, TILE_CAP / (TILE_W * 3 * a0.K)));
+    int t0 = 0, chunk = big ? 1 : std::max(1, std::min(4, TILE_CAP / (TILE_W * 3 * a0.K))), round = 0;
     while (t0 < n_tiles) {
         const int ny = std::min(std::min(chunk, n_tiles - t0), 32768);
         TileArgs a = a0;
@@ -1095,9 +1124,16 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 2;
         t0 += ny;
-        chunk *= 2;
+        chunk *= ix->tile_growth;
+        if (round < exchange_rounds) BR_TRY(exchange_thr(ix, a0.thr, a0.nq, a0.elig, pa, st));   // same count on every shard
+        ++round;
     }
     return BR_OK;
+}
+
+int fused_launch_count(const br_index* ix, int32_t k) {
+    if (!fused_supported(ix, k, 1)) return 0;
+    return tile_launch_count((ix->n_sub + TILE_W - 1) / TILE_W, k, ix->tile_growth);
 }
 
 bool fused_supported(const br_index* ix, int32_t k, int32_t nq) {
@@ -1221,24 +1257,30 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
                                                                             sizeof(float4) + sizeof(uint32_t) + sizeof(uint2) * TILE_W) +
                         sizeof(NeEntry) * G * NE_MAX + sizeof(uint16_t) * TILE_W * LIST_CAP + 4 * (20 + 9 * TILE_W) + G * QT;
+    // threshold exchange with the other shards: only in the regular pass of the first attempt, so that every shard makes
+    // exactly 1 + thr_exchange_rounds calls per batch
+    const bool exchange = ix->thr_exchange != nullptr && ix->thr_exchange_rounds >= 0 && !long_pass && attempt == 0;
+    const int xr = exchange ? ix->thr_exchange_rounds : 0;
     if (k <= 32 && ix->seed_thr) {
         k_seed_thr<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(ix->post, ix->row_ptr, nq, (int)k, elig, thr, pa);
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 1;
     }
+    if (exchange) BR_TRY(exchange_thr(ix, thr, nq, elig, pa, st));
     if (long_pass) {
-        if (G == 1) BR_TRY((launch_tiles<1, TILE_QT_LONG>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)));
-        else BR_TRY((launch_tiles<2, TILE_QT_LONG>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa)));
+        if (G == 1) BR_TRY((launch_tiles<1, TILE_QT_LONG>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr)));
+        else BR_TRY((launch_tiles<2, TILE_QT_LONG>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr)));
     } else {
         switch (G) {
-            case 1: BR_TRY((launch_tiles<1, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa))); break;
-            case 2: BR_TRY((launch_tiles<2, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa))); break;
-            default: BR_TRY((launch_tiles<4, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa))); break;
+            case 1: BR_TRY((launch_tiles<1, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr))); break;
+            case 2: BR_TRY((launch_tiles<2, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr))); break;
+            default: BR_TRY((launch_tiles<4, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr))); break;
         }
     }
     BR_TRY(launch_rescore_heads(ix, q_off, pv, dedup, nq, cap, cand_cnt, cand, cand_sc, st));
     BR_TRY(launch_final_select(cand, cand_sc, cand_off, 0, nq, k, positive_only, out_ids, out_scores, cnt_tmp, st, cand_cnt));
-    const int32_t need = (int32_t)std::min<int64_t>(k, ix->n_docs);
+    // with shared thresholds a shard legitimately returns fewer than k docs (the rest of the corpus holds better ones)
+    const int32_t need = exchange ? 0 : (int32_t)std::min<int64_t>(k, ix->n_docs);
     k_fused_flags<<<blocks_for(nq, 256), 256, 0, st>>>(elig, overflow, cnt_tmp, nq, need, positive_only, flags);
     BR_CUDA(cudaGetLastError());
     ix->stats.kernel_launches += 3;

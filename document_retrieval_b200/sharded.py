@@ -94,8 +94,54 @@ class ShardedBM25:
     """One rank's view of a doc-sharded index.  ``local`` is this rank's ``BM25`` shard (built with
     ``doc_base`` = first global doc id of the shard and the all-reduced statistics)."""
 
-    def __init__(self, local, group=None, merge=merge_topk_cuda):
+    def __init__(self, local, group=None, merge=merge_topk_cuda, share_thresholds=False):
         self.local, self.group, self.merge = local, group, merge
+        self.share_thresholds = share_thresholds
+        self._xr = {}                    # k -> exchange rounds agreed between the ranks (-1: off)
+        self._cb = None
+        self._thr_view = None
+
+    # ---- threshold sharing (br_set_thr_exchange, opt-in): every shard prunes with the best bound any shard has found.
+    # Measured on the C4 workload it is a wash (2 GPUs +2 %, 8 GPUs -0.5 %: the max of the shards' own k-th best scores is
+    # still far from the k-th best of the union, and every exchange is a synchronisation point), hence off by default.
+    def _exchange(self, thr_ptr, nq, stream, user):
+        try:
+            key = (thr_ptr, nq)
+            if self._thr_view is None or self._thr_view[0] != key:
+                class _Arr:
+                    __cuda_array_interface__ = {"shape": (nq,), "typestr": "<f4", "data": (thr_ptr, False), "version": 3}
+                self._thr_view = (key, torch.as_tensor(_Arr(), device=self.local._device))
+            dist.all_reduce(self._thr_view[1], op=dist.ReduceOp.MAX, group=self.group)     # on the current stream
+            return 0
+        except Exception:                # never raise through the C frame
+            import traceback
+            traceback.print_exc()
+            return -1
+
+    def _setup_exchange(self, k):
+        """Agree on the number of exchanges per batch (same on every rank, or none at all) for this k."""
+        if k in self._xr:
+            return self._xr[k]
+        rounds = -1
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if (self.share_thresholds and world > 1 and hasattr(self.local, "_h") and self.local._h is not None
+                and self.merge is merge_topk_cuda):
+            lib = _lib.load()
+            n = int(lib.br_tile_launch_count(self.local._h, int(k)))
+            t = torch.tensor([n], dtype=torch.int64, device=self.local._device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            rounds = int(t.item()) - 1 if int(t.item()) > 0 else -1
+        self._xr[k] = rounds
+        return rounds
+
+    def _set_exchange(self, rounds):
+        lib = _lib.load()
+        if rounds >= 0:
+            if self._cb is None:
+                self._cb = _lib.THR_EXCHANGE_FN(self._exchange)
+            check(lib.br_set_thr_exchange(self.local._h, self._cb, None, int(rounds)), "br_set_thr_exchange")
+        else:
+            check(lib.br_set_thr_exchange(self.local._h, None, None, -1), "br_set_thr_exchange")
 
     @classmethod
     def from_local_token_ids(cls, doc_offsets, token_ids, vocab_size, doc_base, k1=1.5, b=0.75, *,
@@ -115,11 +161,33 @@ class ShardedBM25:
         if hasattr(self.local, "retrieve_records_batch") and self.merge is merge_topk_cuda:
             # CUDA shard: the library emits packed {global id, score} records - one all-gather, merged straight from
             # the gathered buffer
-            rec = self.local.retrieve_records_batch(queries, n)
+            rounds = self._setup_exchange(n)
+            if rounds >= 0:
+                self._set_exchange(rounds)
+            try:
+                rec = self.local.retrieve_records_batch(queries, n)
+            finally:
+                if rounds >= 0:
+                    self._set_exchange(-1)
             allr = gather_records(rec, self.group)
             if allr.shape[0] == 1:
                 return rec[..., 0].contiguous(), rec[..., 1].contiguous().view(torch.float64)
-            return merge_records_cuda(allr, n)
+            ids, sc = merge_records_cuda(allr, n)
+            if rounds >= 0:
+                # with shared thresholds a query that has fewer than n matching docs in the WHOLE corpus comes back short:
+                # those (rare) queries are repeated with local thresholds, whose zero-score fill is exact
+                total = getattr(self, "n_docs_global", None)
+                short = torch.nonzero(ids[:, min(n, total or n) - 1] < 0).flatten()
+                if short.numel():
+                    q_terms, q_off = self.local.pack_queries(queries)
+                    q_terms, q_off = q_terms.cpu(), q_off.cpu()
+                    rows = short.cpu().tolist()
+                    sub_t = torch.cat([q_terms[int(q_off[r]):int(q_off[r + 1])] for r in rows]) if rows else q_terms[:0]
+                    sub_o = torch.tensor([0] + [int(q_off[r + 1] - q_off[r]) for r in rows], dtype=torch.int32).cumsum(0).to(torch.int32)
+                    rec2 = self.local.retrieve_records_batch((sub_t.to(torch.int32), sub_o), n)
+                    i2, s2 = merge_records_cuda(gather_records(rec2, self.group), n)
+                    ids[short], sc[short] = i2, s2
+            return ids, sc
         ids, sc = self.local.retrieve_top_n_batch(queries, n)
         gids = torch.where(ids >= 0, ids.to(torch.int64) + self.local.doc_base, torch.full_like(ids, -1, dtype=torch.int64))
         all_ids, all_sc = gather_candidates(gids, sc, self.group)
