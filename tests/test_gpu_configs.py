@@ -93,13 +93,13 @@ def test_c4_slice_against_the_oracle(c4_slice):
     do, tk, qo, qt, m = c4_slice
     co = COracle(do.cpu().numpy(), tk.cpu().numpy(), 1_000_000)
     oi, osc, _ = co.topk_batch(qt, qo, 10)
-    for pm in (700, 0, 1000, 400):
+    for pm in (800, 0, 1000, 400):
         m.set_option("defer_pm", pm)
         ids, sc = m.retrieve_top_n_batch((qt, qo), 10)
         assert m.query_stats()["queries_fused"] > 1900
         assert np.array_equal(ids.cpu().numpy(), oi), f"defer_pm={pm}"
         assert np.array_equal(sc.cpu().numpy(), osc), f"defer_pm={pm}"
-    m.set_option("defer_pm", 700)
+    m.set_option("defer_pm", 800)
     # duplicates counted (team_run1.py:183) and the top-100 of score_documents_for_query through the large-k tiled path
     o2 = COracle(do.cpu().numpy(), tk.cpu().numpy(), 1_000_000, variant="okapi")
     from document_retrieval_b200 import BM25

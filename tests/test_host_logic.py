@@ -94,3 +94,42 @@ def test_recall_and_test_retrieval_follow_the_notebook_semantics():
     out = retrieve_test_queries(models, id_maps, rows, k=10)
     assert out[3] == [] and out[0][0] == "en0" and out[1][0] == "fr1" and len(out[1]) == 2 and len(out[0]) == 3
     assert evaluate_recall_at_k(models, id_maps, [], k=10) == 0
+
+
+def test_index_file_header_and_packed_query_forms(tmp_path):
+    """Host-side logic that needs no GPU: the index-file reader rejects foreign / corrupt files before touching the
+    device, and pack_queries tells the packed (q_terms, q_offsets) ARRAY form from a batch of two token lists."""
+    import struct
+    import pytest
+    import torch
+    from document_retrieval_b200 import BM25, indexfile
+    from document_retrieval_b200._lib import BRError
+    p = tmp_path / "x.brix"
+    p.write_bytes(b"not an index")
+    with pytest.raises(BRError):
+        indexfile.read_header(str(p))
+    p.write_bytes(indexfile.MAGIC + struct.pack("<Q", 1 << 40))
+    with pytest.raises(BRError):
+        indexfile.read_header(str(p))
+    hdr = b'{"format": 1, "arrays": []}'
+    p.write_bytes(indexfile.MAGIC + struct.pack("<Q", len(hdr)) + hdr)
+    assert indexfile.read_header(str(p))["format"] == 1
+    m = BM25.__new__(BM25)
+    m._vocab, m._terms, m._term_pool, m.vocabulary = None, None, None, None
+    qt, qo = m.pack_queries((np.array([3, 4, 5], np.int32), np.array([0, 1, 3], np.int32)))
+    assert qt.tolist() == [3, 4, 5] and qo.tolist() == [0, 1, 3]
+    qt, qo = m.pack_queries(([3, 4, 5], [0, 1, 3]))                 # two queries given as lists: NOT the packed form
+    assert qt.tolist() == [3, 4, 5, 0, 1, 3] and qo.tolist() == [0, 3, 6]
+    with pytest.raises(ValueError):
+        m.pack_queries((np.array([3, 4, 5], np.int32), np.array([0, 1, 2], np.int32)))   # offsets do not end at len(q_terms)
+    assert torch.is_tensor(qt)
+
+
+def test_per_language_recall_matches_the_oracle():
+    from document_retrieval_b200 import per_language_recall
+    ranked = {10: ["a", "b"], 11: ["c"], 12: [], 13: ["z"]}
+    pos = ["b", "x", "q", "z"]
+    langs = {10: "en", 11: "en", 12: "fr", 13: "ko"}
+    got = per_language_recall(ranked, pos, langs)
+    want = orc.per_language_recall([ranked[k] for k in ranked], pos, [langs[k] for k in ranked])
+    assert got == want == (0.5, {"en": 0.5, "fr": 0.0, "ko": 1.0})
