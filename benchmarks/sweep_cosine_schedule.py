@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from document_retrieval_b200.cosine import CosineIndex, set_cosine_option  # noqa: E402
 
-DEFAULTS = {"kernel": 0, "qs_bn": 224, "qs_window": 64, "chunk0": 1, "chunk_mult": 2, "tighten_threads": 64}
+DEFAULTS = {"kernel": 0, "qs_bn": 224, "qs_window": 64, "chunk0": 1, "chunk_mult": 2, "tighten_threads": 64, "qs_epi": 1}
 
 
 def main():

@@ -9,7 +9,7 @@ import os
 import torch  # noqa: F401  (initialises the CUDA primary context the library shares)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libbr_b200.so")
+SO_PATH = os.environ.get("BR_B200_SO") or os.path.join(_HERE, "libbr_b200.so")   # BR_B200_SO: build-variant experiments
 
 VARIANT_ID = {"notebook": 0, "okapi": 1, "okapi_no_plus1": 2}
 BR_MAX_K = 1024

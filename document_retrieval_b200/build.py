@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SO = os.path.join(HERE, "libbr_b200.so")
+SO = os.path.join(HERE, os.environ.get("BR_SO_NAME", "libbr_b200.so"))   # BR_SO_NAME + BR_NVCC_EXTRA: build-variant experiments
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("BR_NVCC_EXTRA", "").split()
@@ -31,10 +31,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return SO
     objs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = "build" if SO.endswith("libbr_b200.so") else "build_" + os.path.basename(SO)[:-3]
+    os.makedirs(os.path.join(HERE, bdir), exist_ok=True)
     procs = []
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(HERE, bdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -47,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}")
     cmd = [NVCC, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, *objs]
     subprocess.check_call(cmd)
-    with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
+    with open(os.path.join(HERE, bdir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))

@@ -8,7 +8,14 @@
 
 #include "../../include/br_b200.h"
 
+// docs per skip-table sub-range = docs per warp of the tile kernel (2^kSubShift)
+#ifndef BR_TILE_SHIFT
+#define BR_TILE_SHIFT 10
+#endif
+
 namespace br {
+
+constexpr int kSubShift = BR_TILE_SHIFT;
 
 void set_error(const std::string& msg);
 
@@ -162,8 +169,9 @@ struct br_index {
     bool seed_thr = true;           // threshold seeding before the first launch of the tiled scorer
     int defer_pm = 800;             // MaxScore deferral budget of the tiled scorer, per mille of the threshold (0 = off)
     int tile_growth = 2;            // every launch covers this many times the tiles of the one before
+    int sparse_mode = 0;            // sparse phase of the tile kernel: 0 cooperative walk (round 2), 1 / 2 lane per slice, 4 / 2 postings per step
     int tile_tpb = 16;              // consecutive tiles per CTA in the large launches
-    int tile_dense_min = 32;        // average postings of a term per 512-doc sub-range from which its slices are walked
+    int tile_dense_min = 32;        // average postings of a term per sub-range from which its slices are walked
                                     // term by term (whole warp, pipelined) instead of concatenated with the sparse ones
 
     // optional event timing of the scoring kernel

@@ -595,7 +595,7 @@ struct QsIter {
     }
 };
 
-template <int QS_BN, int QS_STAGES>
+template <int QS_BN, int QS_STAGES, int EPI = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QS_THREADS, 1) k_cosine_gemm_qs(const __grid_constant__ CUtensorMap map_docs,
                                                                const __grid_constant__ CUtensorMap map_q, CosArgs a) {
     using Cfg = QsCfg<QS_BN, QS_STAGES>;
@@ -736,7 +736,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QS_THREADS, 1) k_cos
             acc_phase[acc] ^= 1;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)col0;
-            {
+            if constexpr (EPI == 0) {
                 // common case (nothing passes) is branch-free: per 16-column chunk mc = max_j (acc_j * inv_d - thr_j)
                 float mc[NCH];
                 {
@@ -787,9 +787,83 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QS_THREADS, 1) k_cos
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc ? l_tempty1 : l_tempty0);
+            if constexpr (EPI != 0) {
+                // All of the warp's columns are in registers after one wait.  The filter is straight-line code: per chunk
+                // the maximum of acc*inv_d - thr, and a predicated copy of the chunk's 16 accumulators when it holds a
+                // passing column.  The emission code exists ONCE (ncu on the first version, which emitted from 7 x 16
+                // unrolled copies: 35 % of all stall samples were instruction-cache misses on the emission lines).
+                // A lane with passing columns in two or more chunks (thresholds still loose) sends its warp through the
+                // chunk loop, which reads each chunk again from TMEM; otherwise the accumulator stage goes back to the MMA
+                // issuer before anything is emitted.
+                uint32_t hv[16];
+                int hc = 0, nhc = 0;
+                {
+                    uint32_t v[NCH][16];
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) tc_ld_32x16(taddr + c * 16, v[c]);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) hv[j] = 0u;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const float4* t4 = reinterpret_cast<const float4*>(s_thr + col0 + c * 16);
+                        float m = -CUDART_INF_F;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 th = t4[j4];
+                            m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 0]), inv_d, -th.x));
+                            m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 1]), inv_d, -th.y));
+                            m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 2]), inv_d, -th.z));
+                            m = fmaxf(m, fmaf(__uint_as_float(v[c][4 * j4 + 3]), inv_d, -th.w));
+                        }
+                        const bool hit = doc < a.n_docs && m >= 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) hv[j] = hit ? v[c][j] : hv[j];
+                        hc = hit ? c : hc;
+                        nhc += hit ? 1 : 0;
+                    }
+                }
+                const bool multi = __any_sync(0xffffffffu, nhc > 1);
+                if (!multi) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc ? l_tempty1 : l_tempty0);
+                }
+                const int c_begin = multi ? 0 : hc, c_end = multi ? NCH : hc + nhc;
+#pragma unroll 1
+                for (int c = c_begin; c < c_end; ++c) {
+                    if (multi) {                                    // warp-uniform
+                        tc_ld_32x16(taddr + c * 16, hv);
+                        tc_wait_ld();
+                    }
+                    if (doc < a.n_docs) {
+                        const float* thc = s_thr + col0 + c * 16;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float sc = __uint_as_float(hv[j]) * inv_d;
+                            if (sc >= thc[j]) {
+                                const int col = col0 + c * 16 + j;
+                                const int q = un.qb * QS_BN + col;
+                                const int pos = atomicAdd(a.cand_cnt + q, 1);
+                                if (pos < COS_CAP) {
+                                    a.cand[(int64_t)q * COS_CAP + pos] = (int32_t)doc;
+                                    a.cand_h[(int64_t)q * COS_CAP + pos] = sc * s_inq[col];
+                                }
+                            }
+                        }
+                    }
+                }
+                if (multi) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc ? l_tempty1 : l_tempty0);
+                }
+            }
+            if constexpr (EPI == 0) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc ? l_tempty1 : l_tempty0);
+            }
             acc ^= 1;
         }
     }
@@ -1015,6 +1089,7 @@ struct CosOptions {
     int chunk0 = 1;          // doc tiles of the first launch
     int chunk_mult = 2;      // growth of the launches
     int tighten_threads = 64;
+    int qs_epi = 1;          // epilogue of the 224-wide query-stationary kernel: 0 filter + re-read of every passing chunk (7 x 16 unrolled emission sites), 1 compact: one emission site, accumulator stage released before the emission
 };
 static CosOptions g_cos;
 
@@ -1030,6 +1105,7 @@ int set_cosine_option(const char* name, int value) {
         g_cos.chunk0 = value;
     }
     else if (n == "chunk_mult") { BR_REQUIRE(value >= 2 && value <= 64, BR_ERR_INVALID, "br_set_cosine_option: chunk_mult must be in [2, 64]"); g_cos.chunk_mult = value; }
+    else if (n == "qs_epi") { BR_REQUIRE(value >= 0 && value <= 1, BR_ERR_INVALID, "br_set_cosine_option: qs_epi must be 0 or 1"); g_cos.qs_epi = value; }
     else if (n == "tighten_threads") { BR_REQUIRE(value >= 32 && value <= TC_T && value % 32 == 0, BR_ERR_INVALID, "br_set_cosine_option: tighten_threads must be a multiple of 32 up to 256"); g_cos.tighten_threads = value; }
     else { set_error("br_set_cosine_option: unknown option " + n); return BR_ERR_INVALID; }
     return BR_OK;
@@ -1054,6 +1130,7 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
     BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_qs<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QsCfg<128, 8>::SMEM));
     BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_qs<192, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QsCfg<192, 5>::SMEM));
     BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_qs<224, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QsCfg<224, 3>::SMEM));
+    BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_qs<224, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QsCfg<224, 3>::SMEM));
     BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_qs<160, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QsCfg<160, 6>::SMEM));
     BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));      // per device
     BR_CUDA(cudaFuncSetAttribute(k_cosine_gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM));
@@ -1086,6 +1163,7 @@ int cosine_topk(const void* docs, const float* inv_nd, int64_t n_docs, int32_t d
             const int grid = 2 * (int)std::min<int64_t>(units, kNumSMs / 2);
             if (qs_bn == 128) k_cosine_gemm_qs<128, 8><<<grid, QS_THREADS, QsCfg<128, 8>::SMEM, st>>>(map_d, map_q, a);
             else if (qs_bn == 192) k_cosine_gemm_qs<192, 5><<<grid, QS_THREADS, QsCfg<192, 5>::SMEM, st>>>(map_d, map_q, a);
+            else if (qs_bn == 224 && g_cos.qs_epi == 1) k_cosine_gemm_qs<224, 3, 1><<<grid, QS_THREADS, QsCfg<224, 3>::SMEM, st>>>(map_d, map_q, a);
             else if (qs_bn == 224) k_cosine_gemm_qs<224, 3><<<grid, QS_THREADS, QsCfg<224, 3>::SMEM, st>>>(map_d, map_q, a);
             else k_cosine_gemm_qs<160, 6><<<grid, QS_THREADS, QsCfg<160, 6>::SMEM, st>>>(map_d, map_q, a);
         } else if (use_mc) {

@@ -37,10 +37,7 @@
 namespace br {
 
 constexpr int TILE_W = 8;            // warps per CTA = sub-ranges per tile
-#ifndef BR_TILE_SHIFT
-#define BR_TILE_SHIFT 9
-#endif
-constexpr int TILE_SHIFT = BR_TILE_SHIFT;   // 512 docs per sub-range (must equal br_index::sub_shift)
+constexpr int TILE_SHIFT = kSubShift;         // 512 docs per sub-range (must equal br_index::sub_shift)
 constexpr int TILE_S = 1 << TILE_SHIFT;
 constexpr int TILE_DOCS_SHIFT = TILE_SHIFT + 3;   // log2(W * S)
 constexpr int TILE_QT = 20;          // max distinct hot terms of one query in the regular pass (groups of up to 4 queries)
@@ -50,6 +47,10 @@ constexpr int TILE_CAP = 1024;       // candidates kept per query between tighte
 constexpr int TILE_CAP_BIG = 8192;   // the same for 32 < k <= 1024: one tile of 4096 docs may pass entirely before the first
                                      // threshold exists, later chunks add about k candidates each
 static_assert((1 << 3) == TILE_W, "TILE_DOCS_SHIFT assumes W == 8");
+// queries per CTA: the fp32 accumulators [G][W][S] stay at 64 KB so that 3 CTAs share an SM (4 queries x 512 docs per
+// warp in round 1 / early round 2; 2 queries x 1024 docs now: slices twice as long fill the lanes of the sparse walk
+// better - 134k -> 150k queries/s on the C4 workload)
+constexpr int TILE_GMAX = (64 * 1024) / (TILE_W * TILE_S * 4) >= 4 ? 4 : ((64 * 1024) / (TILE_W * TILE_S * 4) >= 2 ? 2 : 1);
 
 struct __align__(16) TileEntry {
     int32_t term;
@@ -346,7 +347,7 @@ constexpr int LIST_CAP = 64;      // crossing-list slots per warp and sub-range 
 // still stream rows / have no threshold yet, or when a crossing list overflows.
 // After the CTA prologue there is no block barrier: every warp fetches the slice bounds of its own sub-range (one tile
 // ahead, into registers) and its own copy of the thresholds.
-template <int G, int QT>
+template <int G, int QT, int SPM>
 __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* acc = reinterpret_cast<float*>(smem_raw);                                     // [G][W][S]
@@ -556,6 +557,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
     }
     __syncwarp();
 
+    if constexpr (SPM == 0) {
     // Phase A - sparse slices (most (term, sub-range) pairs hold 0-8 postings).  The lanes are split into G groups of
     // LQ = 32/G, one per query; a group walks the non-empty slices of its own query's terms, one term at a time, LQ
     // postings per step.  The lanes of a group then touch distinct docs of one term, and different groups different
@@ -622,6 +624,56 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
         }
     }
     __syncwarp();
+    } else {
+    constexpr int SPS = SPM == 1 ? 4 : 2;
+    // Phase A - sparse slices (most (term, sub-range) pairs hold 0-8 postings).  The lanes are split into G groups of
+    // LQ = 32/G, one per query, and every LANE walks the slice of one term of its query, up to 4 postings per step, all
+    // loads of a step in flight together: a warp-tile costs one L2 round trip for its postings instead of one per
+    // non-empty slice (round 2 walked the slices of a query one after the other, 8 postings per step - ncu: 5 cycles of
+    // long-scoreboard stall per issued instruction on that chain).  Two lanes of a group can now meet in one accumulator
+    // (two terms of the query in one doc), so the update is a shared-memory atomic add; the lane whose add completes a
+    // doc's sum sees it reach t1 and records the crossing.  The fp32 sum order inside the band does not matter: the band
+    // is re-scored in float64 (3.4).
+    {
+        constexpr int LQ = 32 / G;
+        const int qg = lane / LQ, lq = lane % LQ;
+        float* myq = my + qg * ROW;
+        const float tq = s_t1[qg];
+        const int nt = s_nql[qg];
+        int nt_max = nt;
+#pragma unroll
+        for (int o = LQ; o < 32; o <<= 1) nt_max = max(nt_max, __shfl_xor_sync(0xffffffffu, nt_max, o));
+#pragma unroll 1
+        for (int r0 = 0; r0 < nt_max; r0 += LQ) {
+            uint32_t c = 0, h = 0;
+            const uint2* pp = reinterpret_cast<const uint2*>(a.post);
+            float mu = 1.f;
+            if (r0 + lq < nt) {
+                const int u = s_ql[qg * QT + r0 + lq];
+                const uint2 bd = s_bnd[u];
+                c = bd.x; h = bd.y;
+                pp += s_base[u];
+                if (a.has_mult) mu = reinterpret_cast<const float*>(s_fm + u)[qg];
+            }
+            while (__any_sync(0xffffffffu, c < h)) {
+                uint2 pv[SPS];
+#pragma unroll
+                for (int x = 0; x < SPS; ++x)
+                    if (c + x < h) pv[x] = __ldg(pp + c + x);
+#pragma unroll
+                for (int x = 0; x < SPS; ++x)
+                    if (c + x < h) {
+                        const uint32_t idx = pv[x].x - doc0;
+                        const float add = a.has_mult ? __uint_as_float(pv[x].y) * mu : __uint_as_float(pv[x].y);
+                        const float val = atomicAdd(myq + idx, add) + add;
+                        if (val >= tq) push(qg, idx);
+                    }
+                c += SPS;
+            }
+        }
+    }
+    __syncwarp();
+    }
     // Phase B - dense slices (terms with >= tile_dense_min postings per sub-range on average that are still streamed:
     // rare once the deferral plans exist), whole warp per term, 64 postings per step.  Inside a term all docs are
     // distinct, so the read-modify-writes of a step are independent.  No atomics.
@@ -1105,10 +1157,10 @@ static int tile_launch_count(int n_tiles, int k, int growth) {
     return n;
 }
 
-template <int G, int QT>
-static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t smem, cudaStream_t st, br_index* ix,
+template <int G, int QT, int SPM>
+static int launch_tiles_m(const TileArgs& a0, int n_groups, int n_tiles, size_t smem, cudaStream_t st, br_index* ix,
                         int32_t* prev_cnt, int32_t* overflow, const PlanArgs& pa, int exchange_rounds) {
-    BR_CUDA(cudaFuncSetAttribute(k_tile_score<G, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device
+    BR_CUDA(cudaFuncSetAttribute(k_tile_score<G, QT, SPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device
     // chunks of doubling size: thresholds learnt on the first 2^c tiles filter the next 2^c
     // first chunk: as many tiles as the candidate buffer certainly holds with thresholds still at zero
     // (every sub-range can emit up to ~3k docs before its first tightening)
@@ -1124,7 +1176,7 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
         a.tpb = 1;
         while (a.tpb * 2 <= ix->tile_tpb && ny >= 4 * a.tpb) a.tpb *= 2;
         ix->prof_begin(st);
-        k_tile_score<G, QT><<<dim3((unsigned)n_groups, (unsigned)((ny + a.tpb - 1) / a.tpb)), TILE_W * 32, smem, st>>>(a);
+        k_tile_score<G, QT, SPM><<<dim3((unsigned)n_groups, (unsigned)((ny + a.tpb - 1) / a.tpb)), TILE_W * 32, smem, st>>>(a);
         BR_CUDA(cudaGetLastError());
         ix->prof_end(st);
         if (big) k_tighten_big<<<a0.nq, TG_T, 8 * (size_t)a0.cap, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, a0.cap, overflow, pa);
@@ -1137,6 +1189,16 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
         ++round;
     }
     return BR_OK;
+}
+
+template <int G, int QT>
+static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t smem, cudaStream_t st, br_index* ix,
+                        int32_t* prev_cnt, int32_t* overflow, const PlanArgs& pa, int exchange_rounds) {
+    switch (ix->sparse_mode) {
+        case 0: return launch_tiles_m<G, QT, 0>(a0, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, exchange_rounds);
+        case 2: return launch_tiles_m<G, QT, 2>(a0, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, exchange_rounds);
+        default: return launch_tiles_m<G, QT, 1>(a0, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, exchange_rounds);
+    }
 }
 
 int fused_launch_count(const br_index* ix, int32_t k) {
@@ -1160,7 +1222,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
                std::vector<int32_t>* h_flags, bool long_pass) {
     int G = nq >= 4 * kNumSMs ? 4 : (nq >= 2 * kNumSMs ? 2 : 1);
     if (ix->tile_g) G = ix->tile_g;
-    if (G > 4) G = 4;
+    if (G > TILE_GMAX) G = TILE_GMAX;
     if (long_pass && G > 2) G = 2;
     const int QT = long_pass ? TILE_QT_LONG : TILE_QT;
     const int n_groups = (nq + G - 1) / G, umax = G * QT;
@@ -1282,7 +1344,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
         switch (G) {
             case 1: BR_TRY((launch_tiles<1, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr))); break;
             case 2: BR_TRY((launch_tiles<2, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr))); break;
-            default: BR_TRY((launch_tiles<4, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr))); break;
+            default: BR_TRY((launch_tiles<TILE_GMAX, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr))); break;
         }
     }
     BR_TRY(launch_rescore_heads(ix, q_off, pv, dedup, nq, cap, cand_cnt, cand, cand_sc, st));
