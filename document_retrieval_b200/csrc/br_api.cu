@@ -116,7 +116,7 @@ int br_set_option(br_index* ix, const char* name, int value) {
         BR_REQUIRE(value >= 1 && value <= 512, BR_ERR_INVALID, "br_set_option: tile_dense_min must be in [1, 512]");
         ix->tile_dense_min = value;
     } else if (n == "sparse_mode") {
-        BR_REQUIRE(value >= 0 && value <= 2, BR_ERR_INVALID, "br_set_option: sparse_mode must be 0, 1 or 2");
+        BR_REQUIRE(value >= 0 && value <= 1, BR_ERR_INVALID, "br_set_option: sparse_mode must be 0 or 1");
         ix->sparse_mode = value;
     } else if (n == "tile_tpb") {
         BR_REQUIRE(value >= 1 && value <= 64, BR_ERR_INVALID, "br_set_option: tile_tpb must be in [1, 64]");

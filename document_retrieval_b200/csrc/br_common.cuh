@@ -167,9 +167,9 @@ struct br_index {
     void* thr_exchange_user = nullptr;
     int thr_exchange_rounds = -1;
     bool seed_thr = true;           // threshold seeding before the first launch of the tiled scorer
-    int defer_pm = 800;             // MaxScore deferral budget of the tiled scorer, per mille of the threshold (0 = off)
+    int defer_pm = 700;             // MaxScore deferral budget of the tiled scorer, per mille of the threshold (0 = off)
     int tile_growth = 2;            // every launch covers this many times the tiles of the one before
-    int sparse_mode = 0;            // sparse phase of the tile kernel: 0 cooperative walk (round 2), 1 / 2 lane per slice, 4 / 2 postings per step
+    int sparse_mode = 1;            // sparse phase of the tile kernel: 0 next non-empty slice pulled over by shuffles, 1 term list walked from shared memory
     int tile_tpb = 16;              // consecutive tiles per CTA in the large launches
     int tile_dense_min = 32;        // average postings of a term per sub-range from which its slices are walked
                                     // term by term (whole warp, pipelined) instead of concatenated with the sparse ones

@@ -499,6 +499,13 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
         s_t1[lane] = (scan || qi < 0) ? CUDART_INF_F : t;
     }
     if (lane == 0) *s_lcnt = 0;
+    // bucket bounds of this (tile, group)'s cold postings: requested here, used after the posting phases
+    uint32_t cold0 = 0, cold1 = 0;
+    if (a.cold_off) {
+        const uint32_t* co = a.cold_off + ((int64_t)tile * a.n_groups + g);
+        cold0 = __ldg(co);
+        cold1 = __ldg(co + 1);
+    }
     __syncwarp();
     float t1[G];
     unsigned scan_q = 0;
@@ -625,15 +632,11 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
     }
     __syncwarp();
     } else {
-    constexpr int SPS = SPM == 1 ? 4 : 2;
-    // Phase A - sparse slices (most (term, sub-range) pairs hold 0-8 postings).  The lanes are split into G groups of
-    // LQ = 32/G, one per query, and every LANE walks the slice of one term of its query, up to 4 postings per step, all
-    // loads of a step in flight together: a warp-tile costs one L2 round trip for its postings instead of one per
-    // non-empty slice (round 2 walked the slices of a query one after the other, 8 postings per step - ncu: 5 cycles of
-    // long-scoreboard stall per issued instruction on that chain).  Two lanes of a group can now meet in one accumulator
-    // (two terms of the query in one doc), so the update is a shared-memory atomic add; the lane whose add completes a
-    // doc's sum sees it reach t1 and records the crossing.  The fp32 sum order inside the band does not matter: the band
-    // is re-scored in float64 (3.4).
+    // Phase A, second form (sparse_mode 1): every lane group walks the term list of its own query straight from shared
+    // memory - slice bounds, list base and multiplicity of term i are broadcast reads, the posting of term i+1 is
+    // requested before term i is added - instead of pulling the next non-empty slice over from the lane that fetched its
+    // bounds (three shuffles, a find-first-set and two votes per step in the first form; ncu put 42 % of the stall
+    // samples of the 1024-tile launch on that loop, most of them branch-resolving / short-scoreboard, not memory).
     {
         constexpr int LQ = 32 / G;
         const int qg = lane / LQ, lq = lane % LQ;
@@ -643,33 +646,47 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
         int nt_max = nt;
 #pragma unroll
         for (int o = LQ; o < 32; o <<= 1) nt_max = max(nt_max, __shfl_xor_sync(0xffffffffu, nt_max, o));
-#pragma unroll 1
-        for (int r0 = 0; r0 < nt_max; r0 += LQ) {
-            uint32_t c = 0, h = 0;
-            const uint2* pp = reinterpret_cast<const uint2*>(a.post);
-            float mu = 1.f;
-            if (r0 + lq < nt) {
-                const int u = s_ql[qg * QT + r0 + lq];
+        const uint2* const post2 = reinterpret_cast<const uint2*>(a.post);
+        uint32_t c_hi = 0, c_lo = 0, c_pb = 0;
+        float c_mu = 1.f;
+        uint2 c_p = make_uint2(0u, 0u);
+        auto fetch = [&](int it, uint32_t& lo, uint32_t& hi, uint32_t& pb, float& mu, uint2& p) {
+            lo = hi = 0;
+            if (it < nt) {
+                const int u = s_ql[qg * QT + it];
                 const uint2 bd = s_bnd[u];
-                c = bd.x; h = bd.y;
-                pp += s_base[u];
+                lo = bd.x; hi = bd.y;
+                pb = (uint32_t)s_base[u];                           // posting index of the term's list (nnz < 2^32)
                 if (a.has_mult) mu = reinterpret_cast<const float*>(s_fm + u)[qg];
+                if (lo + lq < hi) p = __ldg(post2 + pb + lo + lq);
             }
-            while (__any_sync(0xffffffffu, c < h)) {
-                uint2 pv[SPS];
-#pragma unroll
-                for (int x = 0; x < SPS; ++x)
-                    if (c + x < h) pv[x] = __ldg(pp + c + x);
-#pragma unroll
-                for (int x = 0; x < SPS; ++x)
-                    if (c + x < h) {
-                        const uint32_t idx = pv[x].x - doc0;
-                        const float add = a.has_mult ? __uint_as_float(pv[x].y) * mu : __uint_as_float(pv[x].y);
-                        const float val = atomicAdd(myq + idx, add) + add;
-                        if (val >= tq) push(qg, idx);
-                    }
-                c += SPS;
+        };
+        fetch(0, c_lo, c_hi, c_pb, c_mu, c_p);
+#pragma unroll 1
+        for (int it = 0; it < nt_max; ++it) {
+            uint32_t n_lo, n_hi, n_pb = 0;
+            float n_mu = 1.f;
+            uint2 n_p = make_uint2(0u, 0u);
+            fetch(it + 1, n_lo, n_hi, n_pb, n_mu, n_p);
+            if (c_lo + lq < c_hi) {
+                const uint32_t idx = c_p.x - doc0;
+                const float val = fmaf(__uint_as_float(c_p.y), c_mu, myq[idx]);
+                myq[idx] = val;
+                if (val >= tq) push(qg, idx);
             }
+            // a slice longer than the lane group (rare for a sparse-class term)
+            for (uint32_t c = c_lo + LQ; __any_sync(0xffffffffu, c < c_hi); c += LQ) {
+                __syncwarp();
+                if (c + lq < c_hi) {
+                    const uint2 p = __ldg(post2 + c_pb + c + lq);
+                    const uint32_t idx = p.x - doc0;
+                    const float val = fmaf(__uint_as_float(p.y), c_mu, myq[idx]);
+                    myq[idx] = val;
+                    if (val >= tq) push(qg, idx);
+                }
+            }
+            __syncwarp();
+            c_lo = n_lo; c_hi = n_hi; c_pb = n_pb; c_mu = n_mu; c_p = n_p;
         }
     }
     __syncwarp();
@@ -711,8 +728,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
     __syncwarp();
     // cold postings of this (tile, group) bucket that fall in this warp's sub-range
     if (a.cold_off) {
-        const int64_t b = (int64_t)tile * a.n_groups + g;
-        const uint32_t c0 = a.cold_off[b], c1 = min(a.cold_off[b + 1], a.cold_cap);
+        const uint32_t c0 = cold0, c1 = min(cold1, a.cold_cap);
         for (uint32_t i = c0 + lane; i < c1; i += 32) {
             const ColdEntry ce = a.cold[i];
             const uint32_t l = ce.key & ((1u << TILE_DOCS_SHIFT) - 1), q = ce.key >> TILE_DOCS_SHIFT;
@@ -1196,7 +1212,6 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
                         int32_t* prev_cnt, int32_t* overflow, const PlanArgs& pa, int exchange_rounds) {
     switch (ix->sparse_mode) {
         case 0: return launch_tiles_m<G, QT, 0>(a0, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, exchange_rounds);
-        case 2: return launch_tiles_m<G, QT, 2>(a0, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, exchange_rounds);
         default: return launch_tiles_m<G, QT, 1>(a0, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, exchange_rounds);
     }
 }
