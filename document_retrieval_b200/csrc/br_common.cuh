@@ -10,7 +10,7 @@
 
 // docs per skip-table sub-range = docs per warp of the tile kernel (2^kSubShift)
 #ifndef BR_TILE_SHIFT
-#define BR_TILE_SHIFT 10
+#define BR_TILE_SHIFT 11
 #endif
 
 namespace br {
@@ -167,7 +167,7 @@ struct br_index {
     void* thr_exchange_user = nullptr;
     int thr_exchange_rounds = -1;
     bool seed_thr = true;           // threshold seeding before the first launch of the tiled scorer
-    int defer_pm = 700;             // MaxScore deferral budget of the tiled scorer, per mille of the threshold (0 = off)
+    int defer_pm = 650;             // MaxScore deferral budget of the tiled scorer, per mille of the threshold (0 = off)
     int tile_growth = 2;            // every launch covers this many times the tiles of the one before
     int sparse_mode = 1;            // sparse phase of the tile kernel: 0 next non-empty slice pulled over by shuffles, 1 term list walked from shared memory
     int tile_tpb = 16;              // consecutive tiles per CTA in the large launches

@@ -44,12 +44,15 @@ constexpr int TILE_QT = 20;          // max distinct hot terms of one query in t
 constexpr int TILE_QT_LONG = 40;     // the same in the long-query pass (groups of up to 2 queries with up to 64 terms, e.g.
                                      // bigram-expanded queries, bm25_ranking.ipynb:105-107); more -> dense path
 constexpr int TILE_CAP = 1024;       // candidates kept per query between tighten rounds (k <= 32)
-constexpr int TILE_CAP_BIG = 8192;   // the same for 32 < k <= 1024: one tile of 4096 docs may pass entirely before the first
+constexpr int TILE_CAP_BIG = (8 << kSubShift) > 8192 ? (8 << kSubShift) : 8192;   // the same for 32 < k <= 1024: one tile of 4096 docs may pass entirely before the first
                                      // threshold exists, later chunks add about k candidates each
 static_assert((1 << 3) == TILE_W, "TILE_DOCS_SHIFT assumes W == 8");
 // queries per CTA: the fp32 accumulators [G][W][S] stay at 64 KB so that 3 CTAs share an SM (4 queries x 512 docs per
 // warp in round 1 / early round 2; 2 queries x 1024 docs now: slices twice as long fill the lanes of the sparse walk
 // better - 134k -> 150k queries/s on the C4 workload)
+// tiles of the first launch (thresholds come from the seeding only): at most 32k docs, so that the docs passing a loose
+// threshold fit the candidate list
+constexpr int TILE_CHUNK0 = (32768 >> TILE_DOCS_SHIFT) >= 1 ? (32768 >> TILE_DOCS_SHIFT) : 1;
 constexpr int TILE_GMAX = (64 * 1024) / (TILE_W * TILE_S * 4) >= 4 ? 4 : ((64 * 1024) / (TILE_W * TILE_S * 4) >= 2 ? 2 : 1);
 
 struct __align__(16) TileEntry {
@@ -805,11 +808,12 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
         if (nne > 0) {
             // (overflow path) complete the partial scores that may still reach the threshold, in place
             const NeEntry* ne = s_ne + q * NE_MAX;
-            unsigned pm = 0;
+            static_assert(TILE_S / 32 <= 64, "completion mask of the scan epilogue: one bit per doc of a lane");
+            unsigned long long pm = 0;
 #pragma unroll
-            for (int j = 0; j < TILE_S / 32; ++j) pm |= (v[j] >= t1q && v[j] > 0.f) ? (1u << j) : 0u;
+            for (int j = 0; j < TILE_S / 32; ++j) pm |= (v[j] >= t1q && v[j] > 0.f) ? (1ull << j) : 0ull;
             while (pm) {
-                const int j = __ffs(pm) - 1;
+                const int j = __ffsll((long long)pm) - 1;
                 pm &= pm - 1;
                 const uint32_t idx = (uint32_t)((j >> 2) * 128 + lane * 4 + (j & 3));
                 const float* col = a.rows + (doc0 + idx);
@@ -1039,19 +1043,21 @@ __global__ void __launch_bounds__(TGS_T) k_tighten(float* __restrict__ thr, int3
 // arbitrary order - every survivor is re-scored in float64 and ordered by k_final_select afterwards.
 __global__ void __launch_bounds__(TG_T) k_tighten_big(float* __restrict__ thr, int32_t* __restrict__ cand_cnt,
                                                       int32_t* __restrict__ prev_cnt, int32_t* __restrict__ cand,
-                                                      float* __restrict__ cand_h, int K, int cap,
+                                                      float* __restrict__ cand_h, int K, int cap, int scap,
                                                       int32_t* __restrict__ overflow, PlanArgs pa) {
+    // scap <= cap: list entries the shared-memory copy holds in this round (the whole region after the first launch,
+    // which can pass a full tile; half of it later, when the lists are ~K long - a longer one goes to the dense path)
     extern __shared__ __align__(16) unsigned char tb_smem[];
-    uint32_t* s_h = reinterpret_cast<uint32_t*>(tb_smem);             // [cap] score bits
-    int32_t* s_id = reinterpret_cast<int32_t*>(s_h + cap);            // [cap]
+    uint32_t* s_h = reinterpret_cast<uint32_t*>(tb_smem);             // [scap] score bits
+    int32_t* s_id = reinterpret_cast<int32_t*>(s_h + scap);           // [scap]
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_prefix, s_need;
     const int q = blockIdx.x;
     int n = cand_cnt[q];
     if (n == prev_cnt[q]) return;                      // nothing emitted since the last round
-    if (n > cap) {
+    if (n > scap) {
         if (threadIdx.x == 0) overflow[q] = 1;
-        n = cap;
+        n = scap;
     }
     int32_t* ids = cand + (int64_t)q * cap;
     float* hs = cand_h + (int64_t)q * cap;
@@ -1168,7 +1174,7 @@ static int exchange_thr(br_index* ix, float* thr, int32_t nq, const int32_t* eli
 // launches of the tile kernel for an index of n_tiles tiles and top-k (doubling chunks)
 static int tile_launch_count(int n_tiles, int k, int growth) {
     const bool big = k > 32;
-    int t0 = 0, chunk = big ? 1 : std::max(1, std::min(4, TILE_CAP / (TILE_W * 3 * k))), n = 0;
+    int t0 = 0, chunk = big ? 1 : std::max(1, std::min(TILE_CHUNK0, TILE_CAP / (TILE_W * 3 * k))), n = 0;
     while (t0 < n_tiles) { t0 += std::min(std::min(chunk, n_tiles - t0), 32768); chunk *= growth; ++n; }
     return n;
 }
@@ -1182,7 +1188,7 @@ static int launch_tiles_m(const TileArgs& a0, int n_groups, int n_tiles, size_t 
     // (every sub-range can emit up to ~3k docs before its first tightening)
     const bool big = a0.cap > TILE_CAP;
     if (big) BR_CUDA(cudaFuncSetAttribute(k_tighten_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TILE_CAP_BIG));
-    int t0 = 0, chunk = big ? 1 : std::max(1, std::min(4, TILE_CAP / (TILE_W * 3 * a0.K))), round = 0;
+    int t0 = 0, chunk = big ? 1 : std::max(1, std::min(TILE_CHUNK0, TILE_CAP / (TILE_W * 3 * a0.K))), round = 0;
     while (t0 < n_tiles) {
         const int ny = std::min(std::min(chunk, n_tiles - t0), 32768);
         TileArgs a = a0;
@@ -1195,7 +1201,10 @@ static int launch_tiles_m(const TileArgs& a0, int n_groups, int n_tiles, size_t 
         k_tile_score<G, QT, SPM><<<dim3((unsigned)n_groups, (unsigned)((ny + a.tpb - 1) / a.tpb)), TILE_W * 32, smem, st>>>(a);
         BR_CUDA(cudaGetLastError());
         ix->prof_end(st);
-        if (big) k_tighten_big<<<a0.nq, TG_T, 8 * (size_t)a0.cap, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, a0.cap, overflow, pa);
+        if (big) {
+            const int scap = round == 0 ? a0.cap : a0.cap / 2;
+            k_tighten_big<<<a0.nq, TG_T, 8 * (size_t)scap, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, a0.cap, scap, overflow, pa);
+        }
         else k_tighten<<<a0.nq, TGS_T, 0, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, overflow, pa);
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 2;
