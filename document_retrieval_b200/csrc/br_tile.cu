@@ -704,17 +704,25 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
         const float4 f4 = s_fm[u];
         const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
         const uint2* p = reinterpret_cast<const uint2*>(a.post) + s_base[u];
+        // the next 64 postings are requested before the current 64 are added (ncu: 10 % of the stall samples of the
+        // 2048-doc version sat on the first use of an unprefetched chunk)
+        uint2 nv2[2];
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            nv2[x] = make_uint2(0xffffffffu, 0u);
+            if (bd.x + lane + 32 * x < bd.y) nv2[x] = __ldg(p + bd.x + lane + 32 * x);
+        }
         for (uint32_t c = bd.x; c < bd.y; c += 64) {
             uint2 v[2];
-            bool ok[2];
 #pragma unroll
             for (int x = 0; x < 2; ++x) {
-                ok[x] = c + lane + 32 * x < bd.y;
-                if (ok[x]) v[x] = __ldg(p + c + lane + 32 * x);
+                v[x] = nv2[x];
+                nv2[x] = make_uint2(0xffffffffu, 0u);
+                if (c + 64 + lane + 32 * x < bd.y) nv2[x] = __ldg(p + c + 64 + lane + 32 * x);
             }
 #pragma unroll
             for (int x = 0; x < 2; ++x) {
-                if (ok[x]) {
+                if (v[x].x != 0xffffffffu) {
                     const uint32_t idx = v[x].x - doc0;
 #pragma unroll
                     for (int q = 0; q < G; ++q) {
