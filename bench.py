@@ -47,6 +47,8 @@ def parse():
     p.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-secondary", action="store_true", help="skip the cosine / index-file figures of `secondary`")
+    p.add_argument("--share-thresholds", type=int, default=-1,
+                   help="cross-shard threshold exchange of the doc-sharded index (N > 1): 1 on, 0 off, -1 the library default")
     p.add_argument("--opt", action="append", default=[], metavar="NAME=INT",
                    help="br_set_option on the index (tuning experiments, e.g. defer_pm=800); not used by the driver")
     return p.parse_args()
@@ -407,7 +409,26 @@ def secondary_benchmarks(args, dev, rank, world, dist_on, model=None, q_dev=None
                           "ms_per_batch": ms2, "queries_per_s": len(queries) / (ms2 * 1e-3), "index_build_s": b2,
                           "recall_at_10": hits / len(queries), "ids_identical_to_oracle": same,
                           "cpu_port_queries_per_s": len(queries) / cpu2, "cpu_cores": threads}
-        del models
+        # TF-IDF cosine candidate stage (cosine_similarity_bm25_reranking.py:210-229) on the largest language index:
+        # tiled scorer over the tf*idf^2/||d|| table against the dense scatter-add path it replaced
+        big = max(langs, key=lambda l: langs[l]["n_docs"])
+        cb = langs[big]
+        mt = BM25.from_token_ids(cb["doc_offsets"], cb["token_ids"], cb["vocab"], variant="okapi_no_plus1", dedup_query=False,
+                                 device=dev)
+        qt = (packed[big][0], packed[big][1])
+        mt.tfidf_cosine_top_n_batch(qt, 200)
+        ms_t, (it, st_) = t_small(lambda: mt.tfidf_cosine_top_n_batch(qt, 200), reps=5)
+        stats_t = mt.query_stats()
+        mt.set_option("fused", 0)
+        ms_d, (idn, sdn) = t_small(lambda: mt.tfidf_cosine_top_n_batch(qt, 200), reps=2)
+        nqt = int(packed[big][3].size - 1)
+        out["tfidf_stage"] = {"workload": f"TF-IDF cosine top-200 candidates, largest language index of config 2 ({cb['n_docs']} docs), "
+                                          f"{nqt} queries, float64 re-scored band",
+                              "ms_per_batch": ms_t, "queries_per_s": nqt / (ms_t * 1e-3),
+                              "queries_on_tiled_path": int(stats_t["queries_fused"]), "queries_on_dense_path": int(stats_t["queries_dense"]),
+                              "dense_scatter_add_path_ms": ms_d,
+                              "identical_to_dense_path": bool(torch.equal(it, idn) and torch.equal(st_, sdn))}
+        del models, mt
         torch.cuda.empty_cache()
 
     # ---- index file: BM25.save / BM25.load of this run's index (flat binary, no pickle) - the step whose joblib
@@ -525,6 +546,8 @@ def main():
     build_s = time.time() - t0
     n_tokens_rank = int(token_ids.numel())
     model = sh.local
+    if args.share_thresholds >= 0:
+        sh.share_thresholds = bool(args.share_thresholds)
     for o in args.opt:
         name, val = o.split("=")
         model.set_option(name, int(val))

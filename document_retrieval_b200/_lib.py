@@ -45,7 +45,7 @@ SIGNATURES = {
     "br_set_cosine_option": (C.c_int, [C.c_char_p, C.c_int]),
     "br_cosine_rerank": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "br_dedupe_first_docs": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
-    "br_set_thr_exchange": (C.c_int, [_P, _P, _P, C.c_int]),
+    "br_set_thr_exchange": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),
     "br_tile_launch_count": (C.c_int, [_P, C.c_int32]),
     "br_trim_scratch": (C.c_int, []),
     "br_last_query_stats": (C.c_int, [_P, _P]),
@@ -61,7 +61,7 @@ SIGNATURES = {
 }
 
 
-THR_EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p)
+THR_EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
 
 
 class QueryStats(C.Structure):

@@ -62,8 +62,10 @@ int br_topk_merge(const int64_t* ids_dev, const double* scores_dev, int32_t n_pa
     return br::topk_merge(ids_dev, scores_dev, n_parts, nq, k, out_ids_dev, out_scores_dev, (cudaStream_t)stream);
 }
 
-int br_set_thr_exchange(br_index* ix, br_thr_exchange_fn fn, void* user, int rounds) {
+int br_set_thr_exchange(br_index* ix, br_thr_exchange_fn fn, void* user, int rounds, int world) {
     BR_REQUIRE(ix, BR_ERR_INVALID, "br_set_thr_exchange: null handle");
+    BR_REQUIRE(!fn || (world >= 1 && world <= 16), BR_ERR_INVALID, "br_set_thr_exchange: world must be in [1, 16]");
+    ix->thr_exchange_world = fn ? world : 1;
     ix->thr_exchange = fn;
     ix->thr_exchange_user = user;
     ix->thr_exchange_rounds = fn ? rounds : -1;

@@ -166,6 +166,7 @@ struct br_index {
     br_thr_exchange_fn thr_exchange = nullptr;
     void* thr_exchange_user = nullptr;
     int thr_exchange_rounds = -1;
+    int thr_exchange_world = 1;
     bool seed_thr = true;           // threshold seeding before the first launch of the tiled scorer
     int defer_pm = 650;             // MaxScore deferral budget of the tiled scorer, per mille of the threshold (0 = off)
     int tile_growth = 2;            // every launch covers this many times the tiles of the one before

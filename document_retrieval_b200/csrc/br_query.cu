@@ -532,6 +532,23 @@ __global__ void k_tfidf_weights(const int64_t* __restrict__ row_ptr, int32_t voc
 // (cosine_similarity_bm25_reranking.py:88,121-126,210-226): doc entries float32(tf*idf) scaled by the float64
 // 1/doc_norm, query entries float32(float32(idf) * float32(1/||q||)), products and sum in float64, terms in ascending
 // id.  ||q|| is a float32 BLAS dot in the reference (platform-dependent last bit); here float32(sqrt(float64 sum)).
+__device__ __forceinline__ double rescore_cos_one(const RescoreIndex& r, const double* __restrict__ inv_norm, const int32_t* terms,
+                                                  int32_t nt, int32_t doc) {
+    double n2 = 0.0;
+    for (int32_t i = 0; i < nt; ++i) { const double x = (double)(float)r.idf[terms[i]]; n2 += x * x; }
+    const float inv_q = 1.0f / (float)sqrt(n2);
+    const double inv_d = inv_norm[doc];
+    double s = 0.0;
+    for (int32_t i = 0; i < nt; ++i) {
+        const int32_t t = terms[i];
+        const int32_t tf = lookup_tf(r, t, (uint32_t)doc);
+        if (tf == 0) continue;
+        const double e = (double)(float)((double)tf * r.idf[t]);
+        const double qn = (double)((float)r.idf[t] * inv_q);
+        s = __dadd_rn(s, __dmul_rn(__dmul_rn(e, inv_d), qn));
+    }
+    return s;
+}
 __global__ void k_rescore_cos(RescoreIndex r, const double* __restrict__ inv_norm, const int32_t* __restrict__ q_off, PrepView v,
                               const int64_t* __restrict__ cand_off, int32_t q_begin, int32_t nq,
                               const int32_t* __restrict__ cand, double* __restrict__ out) {
@@ -544,22 +561,21 @@ __global__ void k_rescore_cos(RescoreIndex r, const double* __restrict__ inv_nor
             const int32_t mid = (lo + hi) >> 1;
             if (cand_off[mid] <= c) lo = mid; else hi = mid;
         }
-        const int32_t q = lo, off = q_off[q], nt = v.u_cnt[q];
-        const int32_t* terms = v.u_terms + off;              // distinct in-corpus terms, ascending
-        double n2 = 0.0;
-        for (int32_t i = 0; i < nt; ++i) { const double x = (double)(float)r.idf[terms[i]]; n2 += x * x; }
-        const float inv_q = 1.0f / (float)sqrt(n2);
-        const double inv_d = inv_norm[doc];
-        double s = 0.0;
-        for (int32_t i = 0; i < nt; ++i) {
-            const int32_t t = terms[i];
-            const int32_t tf = lookup_tf(r, t, (uint32_t)doc);
-            if (tf == 0) continue;
-            const double e = (double)(float)((double)tf * r.idf[t]);
-            const double qn = (double)((float)r.idf[t] * inv_q);
-            s = __dadd_rn(s, __dmul_rn(__dmul_rn(e, inv_d), qn));
-        }
-        out[c] = s;
+        const int32_t q = lo;
+        out[c] = rescore_cos_one(r, inv_norm, v.u_terms + q_off[q], v.u_cnt[q], doc);   // distinct in-corpus terms, ascending
+    }
+}
+// the same over the fixed-stride candidate regions of the fused path
+__global__ void __launch_bounds__(64) k_rescore_cos_heads(RescoreIndex r, const double* __restrict__ inv_norm,
+                                                          const int32_t* __restrict__ q_off, PrepView v, int32_t stride,
+                                                          const int32_t* __restrict__ cnt, const int32_t* __restrict__ cand,
+                                                          double* __restrict__ cand_score) {
+    const int q = blockIdx.x;
+    const int n = min(cnt[q], stride);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int64_t c = (int64_t)q * stride + i;
+        const int32_t doc = cand[c];
+        if (doc >= 0) cand_score[c] = rescore_cos_one(r, inv_norm, v.u_terms + q_off[q], v.u_cnt[q], doc);
     }
 }
 // fused path: query q owns the fixed-stride region [q*stride, (q+1)*stride), only its first cnt[q] slots are live
@@ -608,8 +624,9 @@ int launch_rescore(br_index* ix, const int32_t* q_off, const PrepView& pv, int d
 }
 
 int launch_rescore_heads(br_index* ix, const int32_t* q_off, const PrepView& pv, int dedup, int32_t nq, int32_t stride,
-                         const int32_t* cnt, const int32_t* cand, double* cand_score, cudaStream_t st) {
-    k_rescore_heads<<<nq, 64, 0, st>>>(rescore_view(ix), q_off, pv, dedup, stride, cnt, cand, cand_score);
+                         const int32_t* cnt, const int32_t* cand, double* cand_score, cudaStream_t st, bool cos) {
+    if (cos) k_rescore_cos_heads<<<nq, 64, 0, st>>>(rescore_view(ix), ix->cos_inv_norm, q_off, pv, stride, cnt, cand, cand_score);
+    else k_rescore_heads<<<nq, 64, 0, st>>>(rescore_view(ix), q_off, pv, dedup, stride, cnt, cand, cand_score);
     BR_CUDA(cudaGetLastError());
     return BR_OK;
 }
@@ -746,33 +763,16 @@ __global__ void k_pack_records(const int32_t* __restrict__ ids, const double* __
     out[i] = br_record{d >= 0 ? (int64_t)d + doc_base : (int64_t)-1, sc[i]};
 }
 
-int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, int32_t n_terms, int32_t k, int dedup,
-               int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, br_record* out_recs,
-               cudaStream_t st) {
-    BR_REQUIRE(ix && q_terms && q_off && ((out_ids && out_scores) || out_recs), BR_ERR_INVALID, "br_topk_batch: null pointer");
-    BR_REQUIRE(ix->finalized, BR_ERR_STATE, "br_topk_batch: call br_index_finalize first");
-    BR_REQUIRE(k >= 1 && k <= BR_MAX_K, BR_ERR_INVALID, "br_topk_batch: k must be in [1, BR_MAX_K]");
-    BR_REQUIRE(nq >= 0, BR_ERR_INVALID, "br_topk_batch: nq < 0");
-    if (nq == 0) return BR_OK;
-    BR_CUDA(cudaSetDevice(ix->device));
-    ix->stats = br_query_stats{};
-    if (!out_ids || !out_scores) {                         // records only: ids / scores go to scratch
-        BR_TRY(ix->ws_rec.reserve((size_t)nq * k * 12 + 512));
-        out_ids = ix->ws_rec.as<int32_t>();
-        out_scores = (double*)(ix->ws_rec.as<char>() + (((size_t)nq * k * 4 + 255) & ~(size_t)255));
-    }
-    PrepView pv;
-    int64_t* chunk_start;
-    int32_t T;
-    BR_TRY(prep_queries(ix, q_terms, q_off, nq, dedup, st, &pv, &chunk_start, &T, n_terms));
-    // algorithmic bytes of this batch: 8 B per posting of every distinct in-vocab query term
-    std::vector<int64_t> hP((size_t)nq);
-    BR_CUDA(cudaMemcpyAsync(hP.data(), pv.P, sizeof(int64_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
-    if (!fused_supported(ix, k, nq)) {
-        BR_TRY(topk_dense(ix, q_off, pv, chunk_start, 0, nq, k, dedup, positive_only, out_ids, out_scores, out_counts, st));
+// A prepared batch through the tiled path, then - for the queries it cannot serve exactly - the long-query pass and the
+// dense path.  post_table: weight table of the TF-IDF cosine stage (nullptr: BM25).
+static int serve_prepared(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, int32_t T, int32_t k, int dedup,
+                          int positive_only, const PrepView& pv, const int64_t* chunk_start, int32_t* out_ids,
+                          double* out_scores, int32_t* out_counts, cudaStream_t st, const br_posting* post_table) {
+    if (!fused_supported(ix, k, nq, post_table != nullptr)) {
+        BR_TRY(topk_dense(ix, q_off, pv, chunk_start, 0, nq, k, dedup, positive_only, out_ids, out_scores, out_counts, st, post_table));
     } else {
         std::vector<int32_t> flags;
-        BR_TRY(topk_fused(ix, q_off, pv, nq, k, dedup, positive_only, out_ids, out_scores, out_counts, st, &flags));
+        BR_TRY(topk_fused(ix, q_off, pv, nq, k, dedup, positive_only, out_ids, out_scores, out_counts, st, &flags, false, post_table));
         {   // offsets past n_terms make queries empty: report before the scratch of this batch is reused below
             int32_t h_bad = 0;
             BR_CUDA(cudaMemcpyAsync(&h_bad, pv.bad, 4, cudaMemcpyDeviceToHost, st));
@@ -819,11 +819,11 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
                 std::vector<int32_t> next;
                 if (long_pass) {
                     std::vector<int32_t> f2;
-                    BR_TRY(topk_fused(ix, d_o, spv, ns, k, dedup, positive_only, d_i, d_s, d_c, st, &f2, true));
+                    BR_TRY(topk_fused(ix, d_o, spv, ns, k, dedup, positive_only, d_i, d_s, d_c, st, &f2, true, post_table));
                     for (int32_t i = 0; i < ns; ++i) if (f2[(size_t)i]) next.push_back(redo[(size_t)i]);
                     ix->stats.queries_fused += ns - (int64_t)next.size();
                 } else {
-                    BR_TRY(topk_dense(ix, d_o, spv, s_chunk, 0, ns, k, dedup, positive_only, d_i, d_s, d_c, st));
+                    BR_TRY(topk_dense(ix, d_o, spv, s_chunk, 0, ns, k, dedup, positive_only, d_i, d_s, d_c, st, post_table));
                 }
                 // rows of queries that go on to the next pass are overwritten there (same stream)
                 k_scatter_rows<<<blocks_for((int64_t)ns * k, 256), 256, 0, st>>>(d_q, ns, k, d_i, d_s, d_c, out_ids, out_scores,
@@ -835,6 +835,33 @@ int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
             }
         }
     }
+    return BR_OK;
+}
+
+int topk_batch(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32_t nq, int32_t n_terms, int32_t k, int dedup,
+               int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, br_record* out_recs,
+               cudaStream_t st) {
+    BR_REQUIRE(ix && q_terms && q_off && ((out_ids && out_scores) || out_recs), BR_ERR_INVALID, "br_topk_batch: null pointer");
+    BR_REQUIRE(ix->finalized, BR_ERR_STATE, "br_topk_batch: call br_index_finalize first");
+    BR_REQUIRE(k >= 1 && k <= BR_MAX_K, BR_ERR_INVALID, "br_topk_batch: k must be in [1, BR_MAX_K]");
+    BR_REQUIRE(nq >= 0, BR_ERR_INVALID, "br_topk_batch: nq < 0");
+    if (nq == 0) return BR_OK;
+    BR_CUDA(cudaSetDevice(ix->device));
+    ix->stats = br_query_stats{};
+    if (!out_ids || !out_scores) {                         // records only: ids / scores go to scratch
+        BR_TRY(ix->ws_rec.reserve((size_t)nq * k * 12 + 512));
+        out_ids = ix->ws_rec.as<int32_t>();
+        out_scores = (double*)(ix->ws_rec.as<char>() + (((size_t)nq * k * 4 + 255) & ~(size_t)255));
+    }
+    PrepView pv;
+    int64_t* chunk_start;
+    int32_t T;
+    BR_TRY(prep_queries(ix, q_terms, q_off, nq, dedup, st, &pv, &chunk_start, &T, n_terms));
+    // algorithmic bytes of this batch: 8 B per posting of every distinct in-vocab query term
+    std::vector<int64_t> hP((size_t)nq);
+    BR_CUDA(cudaMemcpyAsync(hP.data(), pv.P, sizeof(int64_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    BR_TRY(serve_prepared(ix, q_terms, q_off, nq, T, k, dedup, positive_only, pv, chunk_start, out_ids, out_scores, out_counts, st,
+                          nullptr));
     if (out_recs) {
         k_pack_records<<<blocks_for((int64_t)nq * k, 256), 256, 0, st>>>(out_ids, out_scores, (int64_t)nq * k, ix->doc_base, out_recs);
         BR_CUDA(cudaGetLastError());
@@ -902,7 +929,9 @@ int tfidf_topk(br_index* ix, const int32_t* q_terms, const int32_t* q_off, int32
     int32_t T;
     BR_TRY(prep_queries(ix, q_terms, q_off, nq, 1 /* binary query tf: generate_query_embedding sets, not adds */, st, &pv,
                         &chunk_start, &T));
-    BR_TRY(topk_dense(ix, q_off, pv, chunk_start, 0, nq, k, 1, 0, out_ids, out_scores, out_counts, st, ix->post_cos));
+    // same tiled scorer as BM25 over the tf*idf^2/||d|| table (round 2 ran this stage on the dense scatter-add path)
+    BR_TRY(serve_prepared(ix, q_terms, q_off, nq, T, k, 1, 0, pv, chunk_start, out_ids, out_scores, out_counts, st, ix->post_cos));
+    BR_CUDA(cudaStreamSynchronize(st));
     ix->prof_collect();
     return BR_OK;
 }

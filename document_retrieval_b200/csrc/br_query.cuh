@@ -24,14 +24,14 @@ struct PrepView {
 int launch_rescore(br_index* ix, const int32_t* q_off, const PrepView& pv, int dedup, const int64_t* cand_off,
                    int32_t q_begin, int32_t nq, const int32_t* cand, double* cand_score, int64_t total, cudaStream_t st);
 int launch_rescore_heads(br_index* ix, const int32_t* q_off, const PrepView& pv, int dedup, int32_t nq, int32_t stride,
-                         const int32_t* cnt, const int32_t* cand, double* cand_score, cudaStream_t st);
+                         const int32_t* cnt, const int32_t* cand, double* cand_score, cudaStream_t st, bool cos = false);
 int launch_final_select(const int32_t* cand, const double* cand_score, const int64_t* cand_off, int32_t q_begin,
                         int32_t nq, int32_t k, int positive_only, int32_t* out_ids, double* out_scores,
                         int32_t* out_counts, cudaStream_t st, const int32_t* cnt_hint = nullptr);
-bool fused_supported(const br_index* ix, int32_t k, int32_t nq);
+bool fused_supported(const br_index* ix, int32_t k, int32_t nq, bool cos = false);
 int fused_launch_count(const br_index* ix, int32_t k);
 int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t nq, int32_t k, int dedup,
                int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st,
-               std::vector<int32_t>* h_flags, bool long_pass = false);
+               std::vector<int32_t>* h_flags, bool long_pass = false, const br_posting* post_table = nullptr);
 
 }  // namespace br

@@ -1167,15 +1167,70 @@ __global__ void __launch_bounds__(128) k_replan(const float* __restrict__ thr, i
     make_plan(pa, q, thr[q], lane);
 }
 
-// Cross-shard threshold exchange (doc-sharded callers, br_set_thr_exchange): the caller's callback replaces thr[Q] by the
-// maximum over all shards - k docs with at least that score exist SOMEWHERE, so it is a valid lower bound of the k-th
-// best score of the whole corpus, the only thing the merged result needs - and the plans follow.
-static int exchange_thr(br_index* ix, float* thr, int32_t nq, const int32_t* elig, const PlanArgs& pa, cudaStream_t st) {
-    const int rc = ix->thr_exchange(thr, nq, (void*)st, ix->thr_exchange_user);
+// Cross-shard threshold exchange (doc-sharded callers, br_set_thr_exchange).  After the seeding the shards' thr[Q] are
+// gathered and every shard takes the maximum; after a tile launch the shards' current K best fp32 scores of every query
+// (the heads of the candidate lists k_tighten has just sorted) are gathered and thr[q] is raised to the K-th largest of the
+// world x K values: K distinct docs of the whole corpus score at least that much, so it is a valid lower bound of the
+// K-th best score of the WHOLE corpus - the bound a single index would have after the same fraction of its docs - and the
+// plans follow.
+__global__ void k_xchg_heads(const float* __restrict__ cand_h, const int32_t* __restrict__ cand_cnt, int cap, int32_t nq, int K,
+                             float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)nq * K) return;
+    const int q = (int)(i / K), j = (int)(i - (int64_t)q * K);
+    out[i] = j < min(cand_cnt[q], cap) ? cand_h[(int64_t)q * cap + j] : 0.f;
+}
+constexpr int XCHG_PER = 16;          // world x K <= 32 x XCHG_PER values per query
+__global__ void __launch_bounds__(128) k_xchg_union(const float* __restrict__ gathered, int world, int32_t nq, int n_per,
+                                                    int K, float* __restrict__ thr) {
+    const int lane = threadIdx.x & 31;
+    const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (q >= nq) return;
+    const int n = world * n_per;        // n_per = 1: the shards' thresholds (maximum); n_per = K: their K best scores
+    float v[XCHG_PER];
+#pragma unroll
+    for (int j = 0; j < XCHG_PER; ++j) {
+        const int i = lane + 32 * j;
+        v[j] = -1.f;
+        if (i < n) { const int r = i / n_per, c = i - r * n_per; v[j] = gathered[((int64_t)r * nq + q) * n_per + c]; }
+    }
+    const int rounds = n_per == 1 ? 1 : K;
+    float kth = 0.f;
+    for (int r = 0; r < rounds; ++r) {
+        float m = -1.f;
+#pragma unroll
+        for (int j = 0; j < XCHG_PER; ++j) m = fmaxf(m, v[j]);
+        float M = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+        const int winner = __ffs(__ballot_sync(0xffffffffu, m == M)) - 1;
+        if (lane == winner) {
+            bool removed = false;
+#pragma unroll
+            for (int j = 0; j < XCHG_PER; ++j)
+                if (!removed && v[j] == M) { v[j] = -1.f; removed = true; }
+        }
+        kth = M;
+    }
+    if (lane == 0 && kth > thr[q]) thr[q] = kth;
+}
+static int exchange_thr(br_index* ix, float* thr, int32_t nq, const int32_t* elig, const PlanArgs& pa, cudaStream_t st,
+                        const TileArgs* a, float* x_local, float* x_gathered) {
+    const int world = ix->thr_exchange_world;
+    const int n_per = a ? a->K : 1;
+    const float* local = thr;
+    if (a) {
+        k_xchg_heads<<<blocks_for((int64_t)nq * a->K, 256), 256, 0, st>>>(a->cand_h, a->cand_cnt, a->cap, nq, a->K, x_local);
+        BR_CUDA(cudaGetLastError());
+        local = x_local;
+    }
+    const int rc = ix->thr_exchange(local, x_gathered, (int64_t)nq * n_per, (void*)st, ix->thr_exchange_user);
     BR_REQUIRE(rc == 0, BR_ERR_STATE, "br_topk_batch: the threshold exchange callback failed");
+    k_xchg_union<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(x_gathered, world, nq, n_per, a ? a->K : 1, thr);
+    BR_CUDA(cudaGetLastError());
     k_replan<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(thr, nq, elig, pa);
     BR_CUDA(cudaGetLastError());
-    ix->stats.kernel_launches += 1;
+    ix->stats.kernel_launches += a ? 3 : 2;
     return BR_OK;
 }
 
@@ -1189,7 +1244,8 @@ static int tile_launch_count(int n_tiles, int k, int growth) {
 
 template <int G, int QT, int SPM>
 static int launch_tiles_m(const TileArgs& a0, int n_groups, int n_tiles, size_t smem, cudaStream_t st, br_index* ix,
-                        int32_t* prev_cnt, int32_t* overflow, const PlanArgs& pa, int exchange_rounds) {
+                        int32_t* prev_cnt, int32_t* overflow, const PlanArgs& pa, int exchange_rounds, float* x_local,
+                        float* x_gathered) {
     BR_CUDA(cudaFuncSetAttribute(k_tile_score<G, QT, SPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device
     // chunks of doubling size: thresholds learnt on the first 2^c tiles filter the next 2^c
     // first chunk: as many tiles as the candidate buffer certainly holds with thresholds still at zero
@@ -1218,7 +1274,7 @@ static int launch_tiles_m(const TileArgs& a0, int n_groups, int n_tiles, size_t 
         ix->stats.kernel_launches += 2;
         t0 += ny;
         chunk *= ix->tile_growth;
-        if (round < exchange_rounds) BR_TRY(exchange_thr(ix, a0.thr, a0.nq, a0.elig, pa, st));   // same count on every shard
+        if (round < exchange_rounds) BR_TRY(exchange_thr(ix, a0.thr, a0.nq, a0.elig, pa, st, &a0, x_local, x_gathered));   // same count on every shard
         ++round;
     }
     return BR_OK;
@@ -1226,10 +1282,11 @@ static int launch_tiles_m(const TileArgs& a0, int n_groups, int n_tiles, size_t 
 
 template <int G, int QT>
 static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t smem, cudaStream_t st, br_index* ix,
-                        int32_t* prev_cnt, int32_t* overflow, const PlanArgs& pa, int exchange_rounds) {
+                        int32_t* prev_cnt, int32_t* overflow, const PlanArgs& pa, int exchange_rounds, float* x_local,
+                        float* x_gathered) {
     switch (ix->sparse_mode) {
-        case 0: return launch_tiles_m<G, QT, 0>(a0, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, exchange_rounds);
-        default: return launch_tiles_m<G, QT, 1>(a0, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, exchange_rounds);
+        case 0: return launch_tiles_m<G, QT, 0>(a0, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, exchange_rounds, x_local, x_gathered);
+        default: return launch_tiles_m<G, QT, 1>(a0, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, exchange_rounds, x_local, x_gathered);
     }
 }
 
@@ -1238,11 +1295,11 @@ int fused_launch_count(const br_index* ix, int32_t k) {
     return tile_launch_count((ix->n_sub + TILE_W - 1) / TILE_W, k, ix->tile_growth);
 }
 
-bool fused_supported(const br_index* ix, int32_t k, int32_t nq) {
+bool fused_supported(const br_index* ix, int32_t k, int32_t nq, bool cos) {
     const bool disabled = false, no_big = !ix->allow_fused_bigk;
     // 32 < k <= 1024: candidate regions of TILE_CAP_BIG slots per query (16 B each) - bounded to 6 GB of scratch
     const bool k_ok = k <= 32 || (!no_big && k <= 1024 && (int64_t)nq * TILE_CAP_BIG * 16 <= (6LL << 30));
-    return !disabled && ix->allow_fused && k_ok && ix->variant != BR_OKAPI_NO_PLUS1 && ix->n_hot > 0 &&
+    return !disabled && ix->allow_fused && k_ok && (cos || ix->variant != BR_OKAPI_NO_PLUS1) && ix->n_hot > 0 &&
            ix->sub_shift == TILE_SHIFT && ix->skip != nullptr;
 }
 
@@ -1251,7 +1308,13 @@ bool fused_supported(const br_index* ix, int32_t k, int32_t nq) {
 // long_pass: the second pass for queries with up to 64 terms / 40 hot terms (groups of at most 2, no deferral plans).
 int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t nq, int32_t k, int dedup,
                int positive_only, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st,
-               std::vector<int32_t>* h_flags, bool long_pass) {
+               std::vector<int32_t>* h_flags, bool long_pass, const br_posting* post_table) {
+    // post_table != nullptr: the TF-IDF cosine stage (br_tfidf_cosine_topk) - same kernels over the weight table
+    // tf*idf^2/||d|| (all weights >= 0 whatever the idf variant), no deferral (the look-up rows and upper bounds hold
+    // BM25 weights), candidates re-scored by k_rescore_cos
+    const bool cos = post_table != nullptr;
+    const br_posting* const post = cos ? post_table : ix->post;
+    const int n_srows = cos ? 0 : ix->n_srows;
     int G = nq >= 4 * kNumSMs ? 4 : (nq >= 2 * kNumSMs ? 2 : 1);
     if (ix->tile_g) G = ix->tile_g;
     if (G > TILE_GMAX) G = TILE_GMAX;
@@ -1273,7 +1336,8 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
                  o_cur = carve(4 * (size_t)(n_buckets + 1)), o_part = carve(4 * (size_t)(n_scan_blocks + 1)),
                  o_poff = carve(8 * (size_t)(n_scan_blocks + 2)),
                  o_cand = carve(4 * (size_t)nq * cap), o_ch = carve(4 * (size_t)nq * cap),
-                 o_cs = carve(8 * (size_t)nq * cap), o_perm = carve(4 * Q), o_inv = carve(4 * Q), o_sk = carve(12 * Q);
+                 o_cs = carve(8 * (size_t)nq * cap), o_perm = carve(4 * Q), o_inv = carve(4 * Q), o_sk = carve(12 * Q),
+                 o_xl = carve(4 * Q * (size_t)std::min<int32_t>(k, 32)), o_xg = carve(4 * Q * (size_t)std::min<int32_t>(k, 32) * (size_t)std::max(1, ix->thr_exchange_world));
     BR_TRY(ix->ws_tile.reserve(bytes));
     char* p = ix->ws_tile.as<char>();
     TileEntry* entries = (TileEntry*)(p + o_ent);
@@ -1299,6 +1363,8 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     double* cand_sc = (double*)(p + o_cs);
     int32_t* perm = (int32_t*)(p + o_perm);
     int32_t* inv_perm = (int32_t*)(p + o_inv);
+    float* x_local = (float*)(p + o_xl);
+    float* x_gathered = (float*)(p + o_xg);
 
     // group queries that share the most frequent terms: sort by signature (bit 31 = most frequent term), on the device
     {
@@ -1321,7 +1387,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
     BR_CUDA(cudaMemsetAsync(p + o_thr, 0, o_off - o_thr, st));
     BR_CUDA(cudaMemsetAsync(cold_total, 0, 16, st));
     k_tile_prep<<<(n_groups + 3) / 4, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, nq, G, umax, entries, n_entries,
-                                                    elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)ix->tile_dense_min) >> TILE_SHIFT), perm, ix->row_slot, ix->n_srows, QT, long_pass ? 64 : 32);
+                                                    elig, cold_total, std::max<int64_t>(1, (ix->n_docs * (int64_t)ix->tile_dense_min) >> TILE_SHIFT), perm, ix->row_slot, n_srows, QT, long_pass ? 64 : 32);
     BR_CUDA(cudaGetLastError());
     k_fill_offsets<<<blocks_for(nq + 1, 256), 256, 0, st>>>(cand_off, nq, cap);
     BR_CUDA(cudaGetLastError());
@@ -1337,7 +1403,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
         ColdEntry* d_cold = ix->ws_cold.as<ColdEntry>();
         BR_CUDA(cudaMemsetAsync(b_cnt, 0, 4 * (size_t)(n_buckets + 1), st));
         const unsigned qb = blocks_for((int64_t)nq * 32, 128);
-        k_cold_pass<false><<<qb, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, ix->post, nq, G, n_groups, elig, inv_perm,
+        k_cold_pass<false><<<qb, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, post, nq, G, n_groups, elig, inv_perm,
                                               b_cnt, nullptr, 0u);
         BR_CUDA(cudaGetLastError());
         k_scan_reduce<<<(unsigned)n_scan_blocks, SCAN_T, 0, st>>>(b_cnt, n_buckets, part);
@@ -1346,40 +1412,41 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
         BR_CUDA(cudaGetLastError());
         k_scan_apply<<<(unsigned)n_scan_blocks, SCAN_T, 0, st>>>(b_cnt, n_buckets, part_off, b_off, b_cur);
         BR_CUDA(cudaGetLastError());
-        k_cold_pass<true><<<qb, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, ix->post, nq, G, n_groups, elig, inv_perm,
+        k_cold_pass<true><<<qb, 128, 0, st>>>(pv, q_off, ix->hot_slot, ix->row_ptr, post, nq, G, n_groups, elig, inv_perm,
                                              b_cur, d_cold, cold_cap);
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 5;
         cold = d_cold;
         cold_off = b_off;
     }
-    TileArgs a{ix->post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
+    TileArgs a{post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
                cold_off, cold, cold_cap, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, cap, (int)k, 0, 0, 1, dedup ? 0 : 1, perm, defer_mask, ne_ub, ix->row_slot};
-    const PlanArgs pa{q_off, pv.u_terms, pv.u_mult, pv.u_cnt, ix->ub, ix->row_slot, ix->n_srows, (float)ix->defer_pm * 1e-3f, defer_mask, ne_ub};
+    const PlanArgs pa{q_off, pv.u_terms, pv.u_mult, pv.u_cnt, ix->ub, ix->row_slot, n_srows, cos ? 0.f : (float)ix->defer_pm * 1e-3f, defer_mask, ne_ub};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
                                                                             sizeof(float4) + sizeof(uint32_t) + sizeof(uint2) * TILE_W) +
                         sizeof(NeEntry) * G * NE_MAX + sizeof(uint16_t) * TILE_W * LIST_CAP + 4 * (20 + 9 * TILE_W) + G * QT;
     // threshold exchange with the other shards: only in the regular pass of the first attempt, so that every shard makes
     // exactly 1 + thr_exchange_rounds calls per batch
-    const bool exchange = ix->thr_exchange != nullptr && ix->thr_exchange_rounds >= 0 && !long_pass && attempt == 0;
+    const bool exchange = !cos && ix->thr_exchange != nullptr && ix->thr_exchange_rounds >= 0 && !long_pass && attempt == 0 && k <= 32 &&
+                          ix->thr_exchange_world * (int)k <= 32 * XCHG_PER;
     const int xr = exchange ? ix->thr_exchange_rounds : 0;
     if (k <= 32 && ix->seed_thr) {
-        k_seed_thr<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(ix->post, ix->row_ptr, nq, (int)k, elig, thr, pa);
+        k_seed_thr<<<blocks_for((int64_t)nq * 32, 128), 128, 0, st>>>(post, ix->row_ptr, nq, (int)k, elig, thr, pa);
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 1;
     }
-    if (exchange) BR_TRY(exchange_thr(ix, thr, nq, elig, pa, st));
+    if (exchange) BR_TRY(exchange_thr(ix, thr, nq, elig, pa, st, nullptr, x_local, x_gathered));
     if (long_pass) {
-        if (G == 1) BR_TRY((launch_tiles<1, TILE_QT_LONG>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr)));
-        else BR_TRY((launch_tiles<2, TILE_QT_LONG>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr)));
+        if (G == 1) BR_TRY((launch_tiles<1, TILE_QT_LONG>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr, x_local, x_gathered)));
+        else BR_TRY((launch_tiles<2, TILE_QT_LONG>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr, x_local, x_gathered)));
     } else {
         switch (G) {
-            case 1: BR_TRY((launch_tiles<1, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr))); break;
-            case 2: BR_TRY((launch_tiles<2, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr))); break;
-            default: BR_TRY((launch_tiles<TILE_GMAX, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr))); break;
+            case 1: BR_TRY((launch_tiles<1, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr, x_local, x_gathered))); break;
+            case 2: BR_TRY((launch_tiles<2, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr, x_local, x_gathered))); break;
+            default: BR_TRY((launch_tiles<TILE_GMAX, TILE_QT>(a, n_groups, n_tiles, smem, st, ix, prev_cnt, overflow, pa, xr, x_local, x_gathered))); break;
         }
     }
-    BR_TRY(launch_rescore_heads(ix, q_off, pv, dedup, nq, cap, cand_cnt, cand, cand_sc, st));
+    BR_TRY(launch_rescore_heads(ix, q_off, pv, dedup, nq, cap, cand_cnt, cand, cand_sc, st, cos));
     BR_TRY(launch_final_select(cand, cand_sc, cand_off, 0, nq, k, positive_only, out_ids, out_scores, cnt_tmp, st, cand_cnt));
     // with shared thresholds a shard legitimately returns fewer than k docs (the rest of the corpus holds better ones)
     const int32_t need = exchange ? 0 : (int32_t)std::min<int64_t>(k, ix->n_docs);

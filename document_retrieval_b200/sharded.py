@@ -94,24 +94,30 @@ class ShardedBM25:
     """One rank's view of a doc-sharded index.  ``local`` is this rank's ``BM25`` shard (built with
     ``doc_base`` = first global doc id of the shard and the all-reduced statistics)."""
 
-    def __init__(self, local, group=None, merge=merge_topk_cuda, share_thresholds=False):
+    def __init__(self, local, group=None, merge=merge_topk_cuda, share_thresholds=True):
         self.local, self.group, self.merge = local, group, merge
         self.share_thresholds = share_thresholds
         self._xr = {}                    # k -> exchange rounds agreed between the ranks (-1: off)
         self._cb = None
-        self._thr_view = None
+        self._thr_views = {}
 
-    # ---- threshold sharing (br_set_thr_exchange, opt-in): every shard prunes with the best bound any shard has found.
-    # Measured on the C4 workload it is a wash (2 GPUs +2 %, 8 GPUs -0.5 %: the max of the shards' own k-th best scores is
-    # still far from the k-th best of the union, and every exchange is a synchronisation point), hence off by default.
-    def _exchange(self, thr_ptr, nq, stream, user):
+    # ---- threshold sharing (br_set_thr_exchange): every shard prunes with a bound learnt on the WHOLE corpus.  The library
+    # hands over its thresholds (after seeding) or its current k best scores per query (after a tile launch); this callback
+    # all-gathers them over the shards on the current stream and the library takes the maximum / the k-th largest of the
+    # union - the threshold a single index would have after the same fraction of its docs.
+    def _exchange(self, local_ptr, gathered_ptr, n_floats, stream, user):
         try:
-            key = (thr_ptr, nq)
-            if self._thr_view is None or self._thr_view[0] != key:
-                class _Arr:
-                    __cuda_array_interface__ = {"shape": (nq,), "typestr": "<f4", "data": (thr_ptr, False), "version": 3}
-                self._thr_view = (key, torch.as_tensor(_Arr(), device=self.local._device))
-            dist.all_reduce(self._thr_view[1], op=dist.ReduceOp.MAX, group=self.group)     # on the current stream
+            world = dist.get_world_size(self.group)
+            key = (local_ptr, gathered_ptr, n_floats)
+            view = self._thr_views.get(key)
+            if view is None:
+                def wrap(ptr, n):
+                    class _Arr:
+                        __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+                    return torch.as_tensor(_Arr(), device=self.local._device)
+                view = (wrap(local_ptr, n_floats), wrap(gathered_ptr, n_floats * world))
+                self._thr_views[key] = view
+            dist.all_gather_into_tensor(view[1], view[0], group=self.group)     # on the current stream
             return 0
         except Exception:                # never raise through the C frame
             import traceback
@@ -139,9 +145,9 @@ class ShardedBM25:
         if rounds >= 0:
             if self._cb is None:
                 self._cb = _lib.THR_EXCHANGE_FN(self._exchange)
-            check(lib.br_set_thr_exchange(self.local._h, self._cb, None, int(rounds)), "br_set_thr_exchange")
+            check(lib.br_set_thr_exchange(self.local._h, self._cb, None, int(rounds), dist.get_world_size(self.group)), "br_set_thr_exchange")
         else:
-            check(lib.br_set_thr_exchange(self.local._h, None, None, -1), "br_set_thr_exchange")
+            check(lib.br_set_thr_exchange(self.local._h, None, None, -1, 1), "br_set_thr_exchange")
 
     @classmethod
     def from_local_token_ids(cls, doc_offsets, token_ids, vocab_size, doc_base, k1=1.5, b=0.75, *,

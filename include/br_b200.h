@@ -179,15 +179,19 @@ int br_rerank_v3_scores(br_index* ix, const int32_t* q_terms_dev, const int32_t*
                         void* stream);
 
 /* Threshold sharing between the shards of a doc-sharded index.  The tiled scorer prunes with a running lower bound
- * thr[q] of each query's k-th best score.  A shard alone learns it from its own docs only; with this callback set, the
- * library calls fn(thr_dev float[nq], nq, stream, user) once after its threshold seeding and once after each of the first
- * `rounds` tile launches of a batch, and fn must replace thr_dev in place by the element-wise MAXIMUM over all shards
- * (an NCCL all-reduce enqueued on `stream`; return 0).  The maximum is a valid bound for the top-k of the WHOLE corpus,
- * which is all the merge needs; a shard may then return fewer than k docs for a query.  Every shard must use the same
- * `rounds` (at most br_tile_launch_count - 1 of the smallest shard) so that all of them make the same number of calls
- * per batch; fn == NULL or rounds < 0 switches the exchange off.  sharded.py's ShardedBM25 sets this up. */
-typedef int (*br_thr_exchange_fn)(float* thr_dev, int32_t nq, void* stream, void* user);
-int br_set_thr_exchange(br_index* ix, br_thr_exchange_fn fn, void* user, int rounds);
+ * thr[q] of each query's k-th best score.  A shard alone learns it from its own docs only - from 1/N of the corpus, so its
+ * launches run with the loose thresholds the single index only has in its first tiles.  With this callback set (k <= 32),
+ * the library calls fn(local_dev, gathered_dev, n_floats, stream, user) once after its threshold seeding (local = thr[nq])
+ * and once after each of the first `rounds` tile launches of a batch (local = the shard's current k best fp32 scores of
+ * every query, float[nq, k], zero-padded); fn must ALL-GATHER the n_floats floats of every shard into
+ * gathered_dev float[world, n_floats] (an NCCL all-gather enqueued on `stream`; return 0).  The library then raises
+ * thr[q] to the maximum of the shards' seeds / to the k-th largest of the world x k gathered scores: k distinct docs of the
+ * WHOLE corpus score at least that much, which is all the merge needs; a shard may then return fewer than k docs for a
+ * query.  Every shard must use the same `rounds` (at most br_tile_launch_count - 1 of the smallest shard) and `world`, so
+ * that all of them make the same calls per batch; fn == NULL or rounds < 0 switches the exchange off.  sharded.py's
+ * ShardedBM25 sets this up. */
+typedef int (*br_thr_exchange_fn)(const float* local_dev, float* gathered_dev, int64_t n_floats, void* stream, void* user);
+int br_set_thr_exchange(br_index* ix, br_thr_exchange_fn fn, void* user, int rounds, int world);
 /* Tile-kernel launches a batch with this k makes on this index (0: the tiled path does not apply). */
 int br_tile_launch_count(const br_index* ix, int32_t k);
 

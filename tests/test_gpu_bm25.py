@@ -402,6 +402,24 @@ def test_tfidf_candidate_stage_is_exact(golden):
     assert checked >= 35
 
 
+def test_tfidf_stage_tiled_path_equals_dense_path():
+    """The TF-IDF candidate stage runs on the tiled scorer (weight table tf*idf^2/||d||, no deferral, k = 200 -> large-k
+    candidate regions, float64 re-score of the band); it must return exactly what the dense scatter-add path returns."""
+    from document_retrieval_b200 import BM25
+    c = synth.make_config("C1")
+    q = (c["q_terms"], c["q_offsets"])
+    nq = c["q_offsets"].size - 1
+    m = BM25.from_token_ids(c["doc_offsets"], c["token_ids"], c["vocab"], variant="okapi_no_plus1", dedup_query=False)
+    for k in (10, 200):
+        m.set_option("fused", 1)
+        a = m.tfidf_cosine_top_n_batch(q, k)
+        assert m.query_stats()["queries_fused"] > 0.8 * nq
+        m.set_option("fused", 0)
+        b = m.tfidf_cosine_top_n_batch(q, k)
+        assert m.query_stats()["queries_fused"] == 0
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
 def test_language_filtered_pipeline_and_per_language_recall(golden):
     """text_preprocessing_and_embedding_setup.py:333-352,534-562: candidates restricted to the query's language
     (per-language GPU sub-indexes finalised with the global statistics) against the numpy restatement."""
