@@ -681,8 +681,11 @@ def main():
                          "stall_cycles_per_issue": lim["stall_cycles_per_issue"], "launch_ms": lim["duration_ms"],
                          "launch_inst_executed": lim["inst_executed"], "source": "profiles/r2_tile_limiter.json (ncu --set full)",
                          "profile_matches_shipped_source": lim["profile_matches_shipped_source"],
-                         "binding": "latency at 37% occupancy (3 CTAs/SM, 64 KB of shared-memory accumulators each): "
-                                    "long-scoreboard stalls on L2 posting loads; neither HBM nor issue slots are saturated"},
+                         "binding": "latency at 36% occupancy (3 CTAs/SM: 64 KB of shared-memory accumulators and 80 registers "
+                                    "per thread each): long-scoreboard stalls on posting slices, look-up rows and skip-table "
+                                    "entries served by L2; neither HBM nor issue slots are saturated",
+                         "profiled_launch": "the 256-tile launch (48 % of the step's tiles); `traffic` and "
+                                            "`launch_inst_executed` are that launch's, not the average launch's"},
                      "note": "achieved = ALGORITHMIC bytes (8 B x sum df of every query's distinct terms, no credit for "
                              "cross-query reuse or pruning, SURVEY 8d) / CUDA-event time of the scoring kernel launches. The kernel "
                              "does not touch most of those bytes: exact MaxScore deferral streams only the query's rare terms "

@@ -531,7 +531,7 @@ int index_finalize(br_index* ix, double k1, double b, int variant, double n_stat
     }
     // hot-term skip tables (shard-local structure: decided from the local df)
     if (!ix->skip) {
-        ix->sub_shift = kSubShift;                       // 512-doc sub-ranges (= TILE_SHIFT of br_tile.cu)
+        ix->sub_shift = kSubShift;                       // docs per sub-range (= TILE_SHIFT of br_tile.cu)
         ix->n_sub = (int32_t)((ix->n_docs + (1LL << ix->sub_shift) - 1) >> ix->sub_shift);
         const uint32_t hot_min = (uint32_t)fmax(4.0, 0.25 * (double)ix->n_sub);
         ix->hot_min = hot_min;

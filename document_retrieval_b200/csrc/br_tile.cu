@@ -1,29 +1,30 @@
-// br_tile.cu - the fused BM25 path for small k: doc-range tiled term-at-a-time scoring with the
-// accumulators in shared memory and the top-k selection fused into the tile epilogue.
+// br_tile.cu - the fused BM25 path: doc-range tiled term-at-a-time scoring with the accumulators in shared memory
+// and the top-k selection fused into the tile epilogue.
 //
-// Why: a dense [Q, N] fp32 accumulator costs 8 B x N of HBM traffic per query (zero + read back) and
-// a global atomic per posting; at N = 8.8M that is more than the postings themselves (hard
-// part 2).  Here a CTA owns (a tile of W x 512 consecutive docs) x (a group of G queries); each of
-// its W warps owns one 512-doc sub-range and walks, for every term of the group's union term list,
-// the slice of that term's posting list that falls in its sub-range (slice bounds come from the
-// per-term skip table built with the index) and adds the packed fp32 weights into its private
-// [G, 512] accumulator rows: plain LDS/FFMA/STS, no atomics, no block barrier after the prologue,
-// deterministic order.  A posting loaded once serves every query of the group that contains the term,
-// and the CTAs of all groups visit a tile back to back (blockIdx.x = group), so the tile's posting
-// slices come from HBM once per batch and from L2 afterwards.
+// Why: a dense [Q, N] fp32 accumulator costs 8 B x N of HBM traffic per query (zero + read back) and a global atomic
+// per posting; at N = 8.8M that is more than the postings themselves (hard part 2).  Here a CTA owns (a tile
+// of W x S consecutive docs) x (a group of G queries); each of its W = 8 warps owns one sub-range of S = 2^kSubShift
+// docs and walks, for the terms the queries' plans stream, the slice of the term's posting list that falls in its
+// sub-range (slice bounds come from the per-term skip table built with the index) and adds the packed fp32 weights
+// into its private [G, S] accumulator rows: plain LDS/FFMA/STS, no atomics, no block barrier after the prologue,
+// deterministic order.  The accumulators are 64 KB per CTA (3 CTAs per SM) whatever the shape: G x S = 2048 -
+// 4 queries x 512 docs in round 1, 1 query x 2048 docs now (measured on the C4 workload: 134k q/s at 4 x 512, 164k at
+// 2 x 1024, 191k at 1 x 2048: a (query, sub-range) costs a fixed ~100 warp instructions of bookkeeping whatever it
+// holds, and a 2048-doc slice of a rare term fills the 32 lanes of the walk where a 512-doc slice held 2-3 postings).
+// The CTAs of all groups visit a tile back to back (blockIdx.x = group), so the tile's posting slices come from HBM
+// once per batch and from L2 afterwards.
 //
-// Terms too rare for a skip table ("cold": df < hot_min) are bucketed per batch instead: a counting
-// sort of their postings by (tile, group) (k_cold_count / scan / k_cold_scatter); the CTA of a bucket
-// adds those few entries with shared-memory atomics before its epilogue.  So the tile accumulators
-// hold the complete fp32 score of every doc.
+// Terms too rare for a skip table ("cold": df < hot_min) are bucketed per batch instead: a counting sort of their
+// postings by (tile, group) (k_cold_pass / scan); the CTA of a bucket adds those few entries with shared-memory atomics
+// before its epilogue.
 //
-// Epilogue + selection: thr[q] is a lower bound of the k-th best fp32 score of query q over the shard.
-// A doc is emitted as a candidate iff score >= thr*(1-1e-5) (the band that makes the float64 re-score
-// exact, see br_query.cu).  thr rises two ways: inside the kernel, when a sub-range holds k better docs
-// in k different lanes (atomicMax); and between launches - tiles are processed in chunks of doubling
-// size, and after each chunk k_tighten sets thr[q] to the k-th best score among the candidates emitted
-// so far and compacts the list.  With doubling chunks every chunk emits about k new candidates per
-// query, so the candidate list stays ~k long and the float64 re-score costs almost nothing.
+// Epilogue + selection: thr[q] is a lower bound of the k-th best fp32 score of query q over the shard (over the whole
+// corpus with the cross-shard exchange).  A doc is emitted as a candidate iff score >= thr*(1-1e-5) (the band that
+// makes the float64 re-score exact, see br_query.cu).  thr rises two ways: inside the kernel, when a sub-range holds k
+// better docs in k different lanes (atomicMax); and between launches - tiles are processed in chunks of doubling size,
+// and after each chunk k_tighten sets thr[q] to the k-th best score among the candidates emitted so far and compacts
+// the list.  With doubling chunks every chunk emits about k new candidates per query, so the candidate list stays ~k
+// long and the float64 re-score costs almost nothing.
 #include <math_constants.h>
 
 #include <algorithm>
@@ -37,19 +38,17 @@
 namespace br {
 
 constexpr int TILE_W = 8;            // warps per CTA = sub-ranges per tile
-constexpr int TILE_SHIFT = kSubShift;         // 512 docs per sub-range (must equal br_index::sub_shift)
+constexpr int TILE_SHIFT = kSubShift;         // docs per sub-range = 2^kSubShift (br_common.cuh; equals br_index::sub_shift)
 constexpr int TILE_S = 1 << TILE_SHIFT;
 constexpr int TILE_DOCS_SHIFT = TILE_SHIFT + 3;   // log2(W * S)
-constexpr int TILE_QT = 20;          // max distinct hot terms of one query in the regular pass (groups of up to 4 queries)
-constexpr int TILE_QT_LONG = 40;     // the same in the long-query pass (groups of up to 2 queries with up to 64 terms, e.g.
+constexpr int TILE_QT = 20;          // max distinct hot terms of one query in the regular pass
+constexpr int TILE_QT_LONG = 40;     // the same in the long-query pass (queries with up to 64 terms, e.g.
                                      // bigram-expanded queries, bm25_ranking.ipynb:105-107); more -> dense path
 constexpr int TILE_CAP = 1024;       // candidates kept per query between tighten rounds (k <= 32)
-constexpr int TILE_CAP_BIG = (8 << kSubShift) > 8192 ? (8 << kSubShift) : 8192;   // the same for 32 < k <= 1024: one tile of 4096 docs may pass entirely before the first
-                                     // threshold exists, later chunks add about k candidates each
+// the same for 32 < k <= 1024: one whole tile may pass before the first threshold exists, later chunks add about k each
+constexpr int TILE_CAP_BIG = (8 << kSubShift) > 8192 ? (8 << kSubShift) : 8192;
 static_assert((1 << 3) == TILE_W, "TILE_DOCS_SHIFT assumes W == 8");
-// queries per CTA: the fp32 accumulators [G][W][S] stay at 64 KB so that 3 CTAs share an SM (4 queries x 512 docs per
-// warp in round 1 / early round 2; 2 queries x 1024 docs now: slices twice as long fill the lanes of the sparse walk
-// better - 134k -> 150k queries/s on the C4 workload)
+// queries per CTA: the fp32 accumulators [G][W][S] stay at 64 KB so that 3 CTAs share an SM
 // tiles of the first launch (thresholds come from the seeding only): at most 32k docs, so that the docs passing a loose
 // threshold fit the candidate list
 constexpr int TILE_CHUNK0 = (32768 >> TILE_DOCS_SHIFT) >= 1 ? (32768 >> TILE_DOCS_SHIFT) : 1;
@@ -334,7 +333,10 @@ __device__ __forceinline__ float sel_q(const float (&v)[G], int q) {
     return r;
 }
 
-constexpr int LIST_CAP = 64;      // crossing-list slots per warp and sub-range (overflow -> full scan of the sub-range)
+#ifndef BR_LIST_CAP
+#define BR_LIST_CAP 64
+#endif
+constexpr int LIST_CAP = BR_LIST_CAP;      // crossing-list slots per warp and sub-range (overflow -> full scan of the sub-range)
 
 // MaxScore deferral (exact): between launches every query gets a plan (make_plan): the terms with the smallest upper
 // bounds ub[t] = max posting weight, as long as their sum stays below a fraction of the query's threshold, are
@@ -346,7 +348,7 @@ constexpr int LIST_CAP = 64;      // crossing-list slots per warp and sub-range 
 // Without streamed rows every accumulator starts at zero and only grows, so the lane that has just updated one knows
 // whether it has reached t1 = thr*(1-band) - sum(deferred ub): it records (query, doc) in its warp's crossing list,
 // and after the posting phases the warp completes and filters just the listed docs (an atomic exchange on the
-// accumulator removes duplicates).  The 512 accumulators of a (query, sub-range) are scanned only for queries that
+// accumulator removes duplicates).  The S accumulators of a (query, sub-range) are scanned only for queries that
 // still stream rows / have no threshold yet, or when a crossing list overflows.
 // After the CTA prologue there is no block barrier: every warp fetches the slice bounds of its own sub-range (one tile
 // ahead, into registers) and its own copy of the thresholds.
@@ -793,7 +795,7 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
     }
     __syncwarp();
 
-    // scan epilogue: threshold filter over all 512 accumulators of a query (streamed rows, no threshold yet, overflow)
+    // scan epilogue: threshold filter over all S accumulators of a query (streamed rows, no threshold yet, overflow)
     if (scan_q)
 #pragma unroll 1
     for (int q = 0; q < G; ++q) {
