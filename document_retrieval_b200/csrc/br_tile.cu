@@ -45,8 +45,9 @@ constexpr int TILE_QT = 20;          // max distinct hot terms of one query in t
 constexpr int TILE_QT_LONG = 40;     // the same in the long-query pass (queries with up to 64 terms, e.g.
                                      // bigram-expanded queries, bm25_ranking.ipynb:105-107); more -> dense path
 constexpr int TILE_CAP = 1024;       // candidates kept per query between tighten rounds (k <= 32)
-// the same for 32 < k <= 1024: one whole tile may pass before the first threshold exists, later chunks add about k each
-constexpr int TILE_CAP_BIG = (8 << kSubShift) > 8192 ? (8 << kSubShift) : 8192;
+// the same for 32 < k <= 1024: everything passes before the first threshold exists (the first launch covers TILE_CAP_BIG docs),
+// later chunks add about k each
+constexpr int TILE_CAP_BIG = (4 << kSubShift) > 8192 ? (4 << kSubShift) : 8192;
 static_assert((1 << 3) == TILE_W, "TILE_DOCS_SHIFT assumes W == 8");
 // queries per CTA: the fp32 accumulators [G][W][S] stay at 64 KB so that 3 CTAs share an SM
 // tiles of the first launch (thresholds come from the seeding only): at most 32k docs, so that the docs passing a loose
@@ -316,6 +317,7 @@ struct TileArgs {
     int K;
     int tile0;
     int tile_end;                 // tiles [tile0, tile_end) in this launch
+    int sub_begin, sub_end;       // sub-ranges [sub_begin, sub_end) of those tiles (the large-k path starts with part of a tile)
     int tpb;                      // consecutive tiles per CTA
     int has_mult;                 // 0: every multiplicity is 1 (set(query) semantics)
     const int32_t* perm;          // group g, slot i -> query perm[g*G+i] (queries sorted by frequent-term signature)
@@ -490,9 +492,10 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
 #pragma unroll 1
     for (int tile = tile_first; tile < tile_last; ++tile) {
     const int sub = tile * TILE_W + w;
-    if (sub >= a.n_sub) break;                                        // warp-uniform; the later tiles are out of range too
+    if (sub >= a.sub_end) break;                                      // warp-uniform; the later tiles are out of range too
     store_bounds();
     if (tile + 1 < tile_last && sub + TILE_W < a.n_sub) load_bounds(sub + TILE_W);     // in flight during this tile
+    if (sub < a.sub_begin) continue;                                  // (large-k path: launch that starts inside a tile)
     // thresholds of this tile (a stale, lower value is always valid); t1: partial scores below it cannot reach thr.
     // Queries that are scanned anyway (streamed rows / no threshold yet) never push: their t1 is +inf in shared memory.
     if (lane < G) {
@@ -1237,10 +1240,11 @@ static int exchange_thr(br_index* ix, float* thr, int32_t nq, const int32_t* eli
 }
 
 // launches of the tile kernel for an index of n_tiles tiles and top-k (doubling chunks)
-static int tile_launch_count(int n_tiles, int k, int growth) {
+static int tile_launch_count(int n_tiles, int n_sub, int k, int growth) {
     const bool big = k > 32;
-    int t0 = 0, chunk = big ? 1 : std::max(1, std::min(TILE_CHUNK0, TILE_CAP / (TILE_W * 3 * k))), n = 0;
-    while (t0 < n_tiles) { t0 += std::min(std::min(chunk, n_tiles - t0), 32768); chunk *= growth; ++n; }
+    const int unit = big ? 1 : TILE_W, n_units = big ? n_sub : n_tiles;
+    int t0 = 0, chunk = big ? std::max(1, TILE_CAP_BIG / TILE_S) : std::max(1, std::min(TILE_CHUNK0, TILE_CAP / (TILE_W * 3 * k))), n = 0;
+    while (t0 < n_units) { t0 += std::min(std::min(chunk, n_units - t0), 32768 * unit); chunk *= growth; ++n; }
     return n;
 }
 
@@ -1254,12 +1258,19 @@ static int launch_tiles_m(const TileArgs& a0, int n_groups, int n_tiles, size_t 
     // (every sub-range can emit up to ~3k docs before its first tightening)
     const bool big = a0.cap > TILE_CAP;
     if (big) BR_CUDA(cudaFuncSetAttribute(k_tighten_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TILE_CAP_BIG));
-    int t0 = 0, chunk = big ? 1 : std::max(1, std::min(TILE_CHUNK0, TILE_CAP / (TILE_W * 3 * a0.K))), round = 0;
-    while (t0 < n_tiles) {
-        const int ny = std::min(std::min(chunk, n_tiles - t0), 32768);
+    // k <= 32: whole tiles.  Large k: sub-ranges - before the first threshold exists everything passes, so the first launch
+    // covers only as many docs as a candidate region holds (TILE_CAP_BIG / S sub-ranges, half a tile), then doubles.
+    const int unit = big ? 1 : TILE_W;                  // sub-ranges per scheduling unit
+    const int n_units = big ? a0.n_sub : n_tiles;
+    int t0 = 0, chunk = big ? std::max(1, TILE_CAP_BIG / TILE_S) : std::max(1, std::min(TILE_CHUNK0, TILE_CAP / (TILE_W * 3 * a0.K))), round = 0;
+    while (t0 < n_units) {
+        const int nu = std::min(std::min(chunk, n_units - t0), 32768 * unit);
         TileArgs a = a0;
-        a.tile0 = t0;
-        a.tile_end = t0 + ny;
+        a.sub_begin = t0 * unit;
+        a.sub_end = std::min((t0 + nu) * unit, a0.n_sub);
+        a.tile0 = a.sub_begin / TILE_W;
+        a.tile_end = (a.sub_end + TILE_W - 1) / TILE_W;
+        const int ny = a.tile_end - a.tile0;
         // consecutive tiles per CTA: amortises the CTA prologue in the large launches, keeps the small ones wide
         a.tpb = 1;
         while (a.tpb * 2 <= ix->tile_tpb && ny >= 4 * a.tpb) a.tpb *= 2;
@@ -1267,14 +1278,11 @@ static int launch_tiles_m(const TileArgs& a0, int n_groups, int n_tiles, size_t 
         k_tile_score<G, QT, SPM><<<dim3((unsigned)n_groups, (unsigned)((ny + a.tpb - 1) / a.tpb)), TILE_W * 32, smem, st>>>(a);
         BR_CUDA(cudaGetLastError());
         ix->prof_end(st);
-        if (big) {
-            const int scap = round == 0 ? a0.cap : a0.cap / 2;
-            k_tighten_big<<<a0.nq, TG_T, 8 * (size_t)scap, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, a0.cap, scap, overflow, pa);
-        }
+        if (big) k_tighten_big<<<a0.nq, TG_T, 8 * (size_t)a0.cap, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, a0.cap, a0.cap, overflow, pa);
         else k_tighten<<<a0.nq, TGS_T, 0, st>>>(a0.thr, a0.cand_cnt, prev_cnt, a0.cand, a0.cand_h, a0.K, overflow, pa);
         BR_CUDA(cudaGetLastError());
         ix->stats.kernel_launches += 2;
-        t0 += ny;
+        t0 += nu;
         chunk *= ix->tile_growth;
         if (round < exchange_rounds) BR_TRY(exchange_thr(ix, a0.thr, a0.nq, a0.elig, pa, st, &a0, x_local, x_gathered));   // same count on every shard
         ++round;
@@ -1294,7 +1302,7 @@ static int launch_tiles(const TileArgs& a0, int n_groups, int n_tiles, size_t sm
 
 int fused_launch_count(const br_index* ix, int32_t k) {
     if (!fused_supported(ix, k, 1)) return 0;
-    return tile_launch_count((ix->n_sub + TILE_W - 1) / TILE_W, k, ix->tile_growth);
+    return tile_launch_count((ix->n_sub + TILE_W - 1) / TILE_W, ix->n_sub, k, ix->tile_growth);
 }
 
 bool fused_supported(const br_index* ix, int32_t k, int32_t nq, bool cos) {
@@ -1422,7 +1430,7 @@ int topk_fused(br_index* ix, const int32_t* q_off, const PrepView& pv, int32_t n
         cold_off = b_off;
     }
     TileArgs a{post, ix->row_ptr, ix->skip, ix->n_sub, ix->n_docs, entries, n_entries, umax, nq, n_groups, elig,
-               cold_off, cold, cold_cap, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, cap, (int)k, 0, 0, 1, dedup ? 0 : 1, perm, defer_mask, ne_ub, ix->row_slot};
+               cold_off, cold, cold_cap, ix->dense_rows, ix->n_pad, thr, cand_cnt, cand, cand_h, cap, (int)k, 0, 0, 0, 0, 1, dedup ? 0 : 1, perm, defer_mask, ne_ub, ix->row_slot};
     const PlanArgs pa{q_off, pv.u_terms, pv.u_mult, pv.u_cnt, ix->ub, ix->row_slot, n_srows, cos ? 0.f : (float)ix->defer_pm * 1e-3f, defer_mask, ne_ub};
     const size_t smem = sizeof(float) * G * TILE_W * TILE_S + (size_t)umax * (sizeof(TileEntry) + sizeof(int64_t) +
                                                                             sizeof(float4) + sizeof(uint32_t) + sizeof(uint2) * TILE_W) +
