@@ -488,14 +488,15 @@ __global__ void __launch_bounds__(TILE_W * 32, 3) k_tile_score(TileArgs a) {
             if (u < U) s_bnd[u] = make_uint2(nlo[r], nhi[r]);     // row terms keep empty slices
         }
     };
-    if (tile_first * TILE_W + w < a.n_sub) load_bounds(tile_first * TILE_W + w);
+    // (large-k path: a launch may start inside its first tile - the warps below sub_begin start one tile later)
+    const int tile_begin_w = tile_first + ((tile_first * TILE_W + w < a.sub_begin) ? 1 : 0);
+    if (tile_begin_w * TILE_W + w < a.n_sub) load_bounds(tile_begin_w * TILE_W + w);
 #pragma unroll 1
-    for (int tile = tile_first; tile < tile_last; ++tile) {
+    for (int tile = tile_begin_w; tile < tile_last; ++tile) {
     const int sub = tile * TILE_W + w;
     if (sub >= a.sub_end) break;                                      // warp-uniform; the later tiles are out of range too
     store_bounds();
     if (tile + 1 < tile_last && sub + TILE_W < a.n_sub) load_bounds(sub + TILE_W);     // in flight during this tile
-    if (sub < a.sub_begin) continue;                                  // (large-k path: launch that starts inside a tile)
     // thresholds of this tile (a stale, lower value is always valid); t1: partial scores below it cannot reach thr.
     // Queries that are scanned anyway (streamed rows / no threshold yet) never push: their t1 is +inf in shared memory.
     if (lane < G) {
