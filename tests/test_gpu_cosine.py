@@ -56,12 +56,14 @@ def test_cosine_topk_random(n, d, nq, k):
 
 
 @pytest.mark.parametrize("opt", [{"kernel": 1}, {"kernel": 2}, {"qs_bn": 128}, {"qs_bn": 160}, {"qs_bn": 192},
-                                 {"qs_window": 3}, {"chunk0": 4, "chunk_mult": 3}])
+                                 {"qs_window": 3}, {"chunk0": 4, "chunk_mult": 3}, {"qs_epi": 0}])
 def test_cosine_kernel_variants_agree(opt):
     """Every GEMM variant (query-stationary CTA pairs at each block width, 2-CTA multicast, one CTA per tile) returns
-    the same ids and bit-identical similarities as the default: same K order of accumulation per element."""
+    the same ids and bit-identical similarities as the default: same K order of accumulation per element.  qs_epi 0 is
+    the first epilogue of the query-stationary kernel (re-read of every passing chunk, 7 x 16 emission sites) against the
+    single-site one."""
     from document_retrieval_b200.cosine import CosineIndex, set_cosine_option
-    defaults = {"kernel": 0, "qs_bn": 224, "qs_window": 64, "chunk0": 1, "chunk_mult": 2}
+    defaults = {"kernel": 0, "qs_bn": 224, "qs_window": 64, "chunk0": 1, "chunk_mult": 2, "qs_epi": 1}
     g = torch.Generator().manual_seed(99)
     docs = torch.randn(9000, 320, generator=g).to(torch.bfloat16)
     qs = torch.randn(700, 320, generator=g).to(torch.bfloat16)
