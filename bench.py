@@ -681,6 +681,8 @@ def main():
                          "stall_cycles_per_issue": lim["stall_cycles_per_issue"], "launch_ms": lim["duration_ms"],
                          "launch_inst_executed": lim["inst_executed"], "source": "profiles/r2_tile_limiter.json (ncu --set full)",
                          "profile_matches_shipped_source": lim["profile_matches_shipped_source"],
+                         "frac_of_issue_peak": (lim["issue_active_pct"] or 0) / 100.0,
+                         "frac_of_hbm_peak_actually_moved": lim["dram_frac"],
                          "binding": "latency at 36% occupancy (3 CTAs/SM: 64 KB of shared-memory accumulators and 80 registers "
                                     "per thread each): long-scoreboard stalls on posting slices, look-up rows and skip-table "
                                     "entries served by L2; neither HBM nor issue slots are saturated",
