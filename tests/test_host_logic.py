@@ -133,3 +133,32 @@ def test_per_language_recall_matches_the_oracle():
     got = per_language_recall(ranked, pos, langs)
     want = orc.per_language_recall([ranked[k] for k in ranked], pos, [langs[k] for k in ranked])
     assert got == want == (0.5, {"en": 0.5, "fr": 0.0, "ko": 1.0})
+
+
+def test_ctypes_binding_matches_the_header():
+    """_lib.SIGNATURES mirrors include/br_b200.h one to one: same entry points, same number of arguments (an ABI drift
+    like a callback or an argument added on one side only would otherwise surface as a crash on the GPU box), and the
+    built library exports every one of them (no compute call: loading and symbol lookup only)."""
+    import ctypes as C
+    import os
+    import re
+    from document_retrieval_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "br_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)                     # comments mention entry points too
+    decl = {}
+    for m in re.finditer(r"\b(br_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        name, args = m.group(1), " ".join(m.group(2).split())
+        if "(*" in m.group(0).split(name)[0][-12:]:                        # a function-pointer typedef, not an entry point
+            continue
+        decl[name] = 0 if args in ("", "void") else args.count(",") + 1
+    typedefs = set(re.findall(r"typedef[^;]*\(\s*\*\s*(br_[a-z0-9_]+)\s*\)", hdr))
+    for t in typedefs:
+        decl.pop(t, None)
+    assert set(decl) == set(_lib.SIGNATURES), (sorted(set(decl) ^ set(_lib.SIGNATURES)))
+    for name, n_args in decl.items():
+        assert len(_lib.SIGNATURES[name][1]) == n_args, (name, n_args, len(_lib.SIGNATURES[name][1]))
+    if os.path.isfile(_lib.SO_PATH):
+        lib = C.CDLL(_lib.SO_PATH)
+        for name in decl:
+            assert hasattr(lib, name), name
